@@ -1,0 +1,46 @@
+/* =============================================================================
+ * include/hevm_ext.h -- inspection / micro-benchmark hooks (own extension)
+ *
+ * The reference exposes ciphertexts only as an opaque seal::Ciphertext*
+ * (getCtxt, SEAL_HEVM.cpp:470-473).  Bit-exact parity tests and the op
+ * microbenchmarks need raw residues, so both libB200_HEVM.so and the CPU oracle
+ * export these hooks with identical meaning.  All buffers are HOST memory,
+ * ciphertext layout is SEAL's: u64[2][level][N], NTT form.
+ * ========================================================================== */
+#ifndef HEVM_EXT_H
+#define HEVM_EXT_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* what: 0 logN, 1 L (#primes incl. special), 2 seed, 3 #ct regs, 4 #pt regs, 5 #galois keys */
+int64_t hevmx_param(void *vm, int what);
+void hevmx_primes(void *vm, uint64_t *out /*[L]*/);
+void hevmx_roots(void *vm, uint64_t *out /*[L] minimal primitive 2N-th roots*/);
+void hevmx_resize(void *vm, int64_t n_ct, int64_t n_pt); /* size register files without a program */
+void hevmx_ct_info(void *vm, int64_t reg, int64_t *level, double *scale);
+void hevmx_ct_read(void *vm, int64_t reg, uint64_t *out);
+void hevmx_ct_write(void *vm, int64_t reg, const uint64_t *in, int64_t level, double scale);
+void hevmx_pt_info(void *vm, int64_t reg, int64_t *level, double *scale);
+void hevmx_pt_read(void *vm, int64_t reg, uint64_t *out);
+void hevmx_pt_write(void *vm, int64_t reg, const uint64_t *in, int64_t level, double scale);
+/* execute ONE HEVM operation {opcode,dst,lhs,rhs} (HEVMHeader.h:27-32) asynchronously */
+void hevmx_exec(void *vm, int64_t opcode, int64_t dst, int64_t lhs, int64_t rhs);
+void hevmx_sync(void *vm);
+/* NTT / INTT of `count` consecutive N-word limbs under prime `prime_idx` (host in/out) */
+void hevmx_ntt(void *vm, uint64_t *data, int64_t prime_idx, int64_t count, int inverse);
+void hevmx_encode(void *vm, int64_t ptreg, const double *vals, int64_t len, int64_t level, int64_t scale_bits);
+void hevmx_decode(void *vm, int64_t ptreg, double *out /*N/2*/);
+void hevmx_decrypt_to_pt(void *vm, int64_t ctreg, int64_t ptreg);
+void hevmx_encrypt_pt(void *vm, int64_t ptreg, int64_t ctreg);
+void hevmx_set_enc_counter(void *vm, uint64_t counter);
+/* which: 0 sk[L][N], 1 pk[2][L][N], 2 relin[L-1][2][L][N], 3 galois key of `elt`; returns #words (or -1) */
+int64_t hevmx_key_read(void *vm, int which, uint64_t elt, uint64_t *out);
+int64_t hevmx_galois_elt(void *vm, int64_t step);
+const char *hevmx_backend(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,27 @@
+import os
+import sys
+from pathlib import Path
+
+import pytest
+
+REPO = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(REPO))
+sys.path.insert(0, str(REPO / "tests"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle_lib():
+    import subprocess
+    from dacapo_b200 import _binding
+    subprocess.run(["make", "-s", "-C", str(REPO / "oracle")], check=True)
+    return _binding.bind(_binding.ORACLE_LIB)
+
+
+@pytest.fixture(scope="session")
+def b200_lib():
+    from dacapo_b200 import _binding
+    return _binding.bind(_binding.B200_LIB)
