@@ -238,8 +238,8 @@ def test_encrypt_decrypt_and_homomorphic_identities(vm):
     rng = np.random.default_rng(8)
     n = vm.N // 2
     x, y = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
-    vm.encode(0, x, 3, 40)
-    vm.encode(1, y, 3, 40)
+    vm.encode(0, x, 3, 50)
+    vm.encode(1, y, 3, 50)
     vm.encrypt_pt(0, 0)
     vm.encrypt_pt(1, 1)
     assert np.max(np.abs(vm.decrypt_decode(0, 2) - x)) < 1e-7
@@ -279,12 +279,12 @@ def test_aliasing(vm):
 # ---- program container ------------------------------------------------------------------------------
 def test_hevm_program_roundtrip(vm, tmp_path):
     p = asm.Program(init_level=3)
-    x = p.arg(40, 3)
+    x = p.arg(50, 3)
     t, u = p.new_ct(), p.new_ct()
     c = p.const([0.5, -0.25])
     pt = p.new_pt()
     ones = p.new_pt()
-    p.encode(pt, c, 3, 40)
+    p.encode(pt, c, 3, 50)
     p.encode(ones, -1, 2, 20)
     p.emit(asm.PLACEHOLDER, 0xBEEF, 0xDEAD, 0xF00D)
     p.emit(asm.MULCP, t, x, pt)
