@@ -1,0 +1,364 @@
+// Warp-synchronous negacyclic NTT building blocks (N = 2^LOGN, LOGN = 7 + LOGB).
+//
+// Replaces SEAL 4.0 ntt_negacyclic_harvey(_lazy) / inverse_ntt_negacyclic_harvey that the
+// reference reaches through seal::Evaluator (reference: lib/Runtime/SEAL_HEVM.cpp:273,283,
+// 315-316).  Same transform: forward = Cooley-Tukey with twiddle table tw[bitrev(k)] = psi^k,
+// natural in -> bit-reversed out; inverse = Gentleman-Sande + N^-1.  Any schedule of the
+// same butterfly DAG gives the same canonical residues, so the schedule is B200-first:
+//
+//   N = 2^7 (rows) x 2^LOGB (cols).  Two passes per transform, one HBM/L2 round trip between:
+//   pass A  "strided":    a warp owns a tile of 128 rows x 4 cols (32 B sectors, 16 values/lane)
+//                         and does the 7 stages whose butterfly span is >= one row.
+//   pass B  "contiguous": a warp owns one row (2^LOGB contiguous values, 8 or 16 per lane) and
+//                         does the remaining LOGB stages.
+//   Inside a pass, values live in registers; a warp-private padded shared-memory tile is used
+//   only to re-distribute values between rounds of 2-4 register-resident stages (__syncwarp,
+//   never __syncthreads).  Shared tile index idx -> idx + idx/16 makes every 64-bit access
+//   pattern used here bank-conflict free.
+//
+// Everything is __host__ __device__: `FOR_LANES` runs the per-lane code on the 32 lanes of a
+// real warp on the GPU, and as a 32-iteration loop over an array of lane states in the
+// test-only CPU warp emulator (tests/emul/warp_emul.cpp).  The product never runs it on the host.
+#pragma once
+#include "modarith.cuh"
+
+#define HEVM_MAXL 32
+
+struct NttTables {
+  int logN, L;
+  const Tw *tw;  // [L][N]  forward twiddles, tw[m+i] for stage with m groups, group i
+  const Tw *itw; // [L][N]  inverses of the above
+  ModQ mod[HEVM_MAXL];
+  Tw invn[HEVM_MAXL];           // N^-1
+  Tw invn_w[HEVM_MAXL];         // N^-1 * itw[1]
+  Tw qinv[HEVM_MAXL][HEVM_MAXL]; // qinv[a][b] = q_a^-1 mod q_b  (a != b)
+};
+
+#if defined(__CUDA_ARCH__)
+#define LANE_DECL const int lane = threadIdx.x & 31
+#define FOR_LANES(S, st, ...)                                                                                         \
+  {                                                                                                                    \
+    auto &S = st[0];                                                                                                   \
+    __VA_ARGS__;                                                                                                       \
+    __syncwarp();                                                                                                      \
+  }
+#define NLANE_STATE 1
+HD Tw ldtw(const Tw *p) {
+  ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(p));
+  Tw t;
+  t.w = v.x;
+  t.wq = v.y;
+  return t;
+}
+// streaming 64-bit / 256-bit accesses (no L1 allocation: each value is touched once per pass)
+HD u64 ldg_stream(const u64 *p) {
+  u64 v;
+  asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+HD void ldg_stream4(const u64 *p, u64 &a, u64 &b, u64 &c, u64 &d) {
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
+HD void stg4(u64 *p, u64 a, u64 b, u64 c, u64 d) {
+  asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+#else
+#define LANE_DECL
+#define FOR_LANES(S, st, ...)                                                                                         \
+  for (int lane = 0; lane < 32; lane++) {                                                                              \
+    auto &S = st[lane];                                                                                                \
+    __VA_ARGS__;                                                                                                       \
+  }
+#define NLANE_STATE 32
+HD Tw ldtw(const Tw *p) { return *p; }
+HD u64 ldg_stream(const u64 *p) { return *p; }
+HD void ldg_stream4(const u64 *p, u64 &a, u64 &b, u64 &c, u64 &d) { a = p[0], b = p[1], c = p[2], d = p[3]; }
+HD void stg4(u64 *p, u64 a, u64 b, u64 c, u64 d) { p[0] = a, p[1] = b, p[2] = c, p[3] = d; }
+#endif
+
+HD int padx(int idx) { return idx + (idx >> 4); }
+#define TILE_A_WORDS 544 // 512 + 512/16
+template <int LOGB> struct TileB {
+  static constexpr int E = (1 << LOGB) / 32;                   // values per lane
+  static constexpr int WORDS = (1 << LOGB) + ((1 << LOGB) >> 4); // padded
+};
+#define WARP_SMEM_WORDS 544 // max(TILE_A_WORDS, TileB<9>::WORDS)
+
+// =====================================================================================
+// Pass A (strided): tile = 128 rows x 4 cols, tile index = row*4 + col.
+//   layout R  ("row-major lanes"): x[e] <-> row = e*8 + (lane>>2),       col = lane&3, idx = e*32 + lane
+//   layout S  ("stage lanes"):     x[e] <-> row = (lane>>2)*16 + e,      col = lane&3, idx = (lane>>2)*64 + e*4 + (lane&3)
+// forward: stages 0-3 in layout R (row bits 6..3), stages 4-6 in layout S (row bits 2..0)
+// inverse: row gaps 1,2,4 in layout S, row gaps 8..64 in layout R (last one carries N^-1)
+// =====================================================================================
+HD int rowR(int lane, int e) { return e * 8 + (lane >> 2); }
+HD int rowS(int lane, int e) { return (lane >> 2) * 16 + e; }
+HD int idxR(int lane, int e) { return e * 32 + lane; }
+HD int idxS(int lane, int e) { return (lane >> 2) * 64 + e * 4 + (lane & 3); }
+
+HD void fwdA_stages_R(u64 (&x)[16], const Tw *tw, u64 q, u64 q2) {
+#pragma unroll
+  for (int s = 0; s < 4; s++) {
+    const int half = 8 >> s;
+    Tw t[8];
+#pragma unroll
+    for (int g = 0; g < (1 << s); g++) t[g] = ldtw(tw + (1 << s) + g);
+#pragma unroll
+    for (int e = 0; e < 16; e++)
+      if (!(e & half)) ct_bfly(x[e], x[e + half], t[e >> (4 - s)], q, q2);
+  }
+}
+HD void fwdA_stages_S(u64 (&x)[16], int lane, const Tw *tw, u64 q, u64 q2) {
+  const int rbase = (lane >> 2) * 16;
+#pragma unroll
+  for (int s = 4; s < 7; s++) {
+    const int half = 1 << (6 - s);
+#pragma unroll
+    for (int e = 0; e < 16; e++)
+      if (!(e & half)) {
+        Tw t = ldtw(tw + (1 << s) + ((rbase + e) >> (7 - s)));
+        ct_bfly(x[e], x[e + half], t, q, q2);
+      }
+  }
+}
+// inverse, layout S: row gaps 1,2,4  (m = 64,32,16 groups)
+HD void invA_stages_S(u64 (&x)[16], int lane, const Tw *itw, u64 q, u64 q2) {
+  const int rbase = (lane >> 2) * 16;
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const int half = 1 << j;
+#pragma unroll
+    for (int e = 0; e < 16; e++)
+      if (!(e & half)) {
+        Tw t = ldtw(itw + (64 >> j) + ((rbase + e) >> (j + 1)));
+        gs_bfly(x[e], x[e + half], t, q, q2);
+      }
+  }
+}
+// inverse, layout R: row gaps 8,16,32,64 (m = 8,4,2,1); the last stage applies N^-1; output canonical
+HD void invA_stages_R(u64 (&x)[16], const Tw *itw, u64 q, u64 q2, Tw invn, Tw invn_w) {
+#pragma unroll
+  for (int j = 3; j < 6; j++) {
+    const int half = 1 << (j - 3);
+    Tw t[8];
+#pragma unroll
+    for (int g = 0; g < (64 >> j); g++) t[g] = ldtw(itw + (64 >> j) + g);
+#pragma unroll
+    for (int e = 0; e < 16; e++)
+      if (!(e & half)) gs_bfly(x[e], x[e + half], t[e >> (j - 2)], q, q2);
+  }
+#pragma unroll
+  for (int e = 0; e < 8; e++) {
+    u64 u = x[e], v = x[e + 8];
+    x[e] = csub(shoup_lazy(u + v, invn, q), q);
+    x[e + 8] = csub(shoup_lazy(u + q2 - v, invn_w, q), q);
+  }
+}
+
+// =====================================================================================
+// Pass B (contiguous): a row of 2^LOGB values, E = 2^LOGB/32 per lane, row index r in [0,128).
+//   layout H ("high bits in registers"): x[e] <-> idx = e*32 + lane
+//   layout M ("middle bits in registers", LOGB=8): idx = hi*32 + e*4 + (lane&3), hi = ((lane>>2)&3)*2 + (lane>>4)
+//   layout C ("consecutive"):            x[e] <-> idx = lane*E + e
+// forward LOGB=8: stages k=0..2 in H (distance 128,64,32), k=3..5 in M (16,8,4), k=6,7 in C (2,1)
+// inverse LOGB=8: gaps 1,2 in C; 4,8,16 in M; 32,64,128 in H
+// twiddle of local stage k, local group g:  tw[(128<<k) + (r<<k) + g]
+// =====================================================================================
+HD int idxH(int lane, int e) { return e * 32 + lane; }
+HD int idxM8(int lane, int e) { return ((((lane >> 2) & 3) * 2 + (lane >> 4)) << 5) + e * 4 + (lane & 3); }
+HD int idxC8(int lane, int e) { return lane * 8 + e; }
+
+HD void fwdB8_stages_H(u64 (&x)[8], int r, const Tw *tw, u64 q, u64 q2) {
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const int half = 4 >> k;
+    Tw t[4];
+#pragma unroll
+    for (int g = 0; g < (1 << k); g++) t[g] = ldtw(tw + (128 << k) + (r << k) + g);
+#pragma unroll
+    for (int e = 0; e < 8; e++)
+      if (!(e & half)) ct_bfly(x[e], x[e + half], t[e >> (3 - k)], q, q2);
+  }
+}
+HD void fwdB8_stages_M(u64 (&x)[8], int lane, int r, const Tw *tw, u64 q, u64 q2) {
+  const int base = idxM8(lane, 0);
+#pragma unroll
+  for (int k = 3; k < 6; k++) {
+    const int half = 4 >> (k - 3);
+#pragma unroll
+    for (int e = 0; e < 8; e++)
+      if (!(e & half)) {
+        Tw t = ldtw(tw + (128 << k) + (r << k) + ((base + e * 4) >> (8 - k)));
+        ct_bfly(x[e], x[e + half], t, q, q2);
+      }
+  }
+}
+HD void fwdB8_stages_C(u64 (&x)[8], int lane, int r, const Tw *tw, u64 q, u64 q2) {
+  const int base = lane * 8;
+#pragma unroll
+  for (int k = 6; k < 8; k++) {
+    const int half = 2 >> (k - 6);
+#pragma unroll
+    for (int e = 0; e < 8; e++)
+      if (!(e & half)) {
+        Tw t = ldtw(tw + (128 << k) + (r << k) + ((base + e) >> (8 - k)));
+        ct_bfly(x[e], x[e + half], t, q, q2);
+      }
+  }
+}
+// inverse: gap 2^j, m_loc = 128>>j, twiddle itw[128*m_loc + r*m_loc + (idx >> (j+1))]
+HD void invB8_stages_C(u64 (&x)[8], int lane, int r, const Tw *itw, u64 q, u64 q2) {
+  const int base = lane * 8;
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    const int half = 1 << j, ml = 128 >> j;
+#pragma unroll
+    for (int e = 0; e < 8; e++)
+      if (!(e & half)) {
+        Tw t = ldtw(itw + 128 * ml + r * ml + ((base + e) >> (j + 1)));
+        gs_bfly(x[e], x[e + half], t, q, q2);
+      }
+  }
+}
+HD void invB8_stages_M(u64 (&x)[8], int lane, int r, const Tw *itw, u64 q, u64 q2) {
+  const int base = idxM8(lane, 0);
+#pragma unroll
+  for (int j = 2; j < 5; j++) {
+    const int half = 1 << (j - 2), ml = 128 >> j;
+#pragma unroll
+    for (int e = 0; e < 8; e++)
+      if (!(e & half)) {
+        Tw t = ldtw(itw + 128 * ml + r * ml + ((base + e * 4) >> (j + 1)));
+        gs_bfly(x[e], x[e + half], t, q, q2);
+      }
+  }
+}
+HD void invB8_stages_H(u64 (&x)[8], int r, const Tw *itw, u64 q, u64 q2) {
+#pragma unroll
+  for (int j = 5; j < 8; j++) {
+    const int half = 1 << (j - 5), ml = 128 >> j;
+    Tw t[4];
+#pragma unroll
+    for (int g = 0; g < ml; g++) t[g] = ldtw(itw + 128 * ml + r * ml + g);
+#pragma unroll
+    for (int e = 0; e < 8; e++)
+      if (!(e & half)) gs_bfly(x[e], x[e + half], t[e >> (j - 4)], q, q2);
+  }
+}
+
+// ---- lane state carried across FOR_LANES phases ---------------------------------------
+struct LaneA {
+  u64 x[16];
+  u64 y[16];
+};
+struct LaneB8 {
+  u64 x[8];
+  u64 z[8]; // second result (ct x ct mod-down handles both output polys in one job)
+};
+
+// =====================================================================================
+// Warp-level pass bodies.  `sm` is the warp-private shared tile (WARP_SMEM_WORDS words).
+// =====================================================================================
+
+// forward pass A on values already held in layout R by st[].y (lazy < 4q); result -> dst tile
+// (128 rows x 4 cols at column c0 of the limb `dst`, row pitch = 2^LOGB)
+template <int LOGB>
+HD void warp_fwdA_from_regs(LaneA *st, u64 *sm, u64 *dst, int c0, const Tw *tw, u64 q) {
+  const u64 q2 = 2 * q;
+  LANE_DECL;
+  FOR_LANES(S, st, {
+    fwdA_stages_R(S.y, tw, q, q2);
+#pragma unroll
+    for (int e = 0; e < 16; e++) sm[padx(idxR(lane, e))] = S.y[e];
+  });
+  FOR_LANES(S, st, {
+#pragma unroll
+    for (int e = 0; e < 16; e++) S.y[e] = sm[padx(idxS(lane, e))];
+    fwdA_stages_S(S.y, lane, tw, q, q2);
+#pragma unroll
+    for (int e = 0; e < 16; e++) dst[((size_t)rowS(lane, e) << LOGB) + c0 + (lane & 3)] = S.y[e];
+  });
+}
+
+// inverse pass A: src tile (layout S load) -> canonical coefficients in st[].x, layout R
+template <int LOGB>
+HD void warp_invA_to_regs(LaneA *st, u64 *sm, const u64 *src, int c0, const Tw *itw, u64 q, Tw invn, Tw invn_w) {
+  const u64 q2 = 2 * q;
+  LANE_DECL;
+  FOR_LANES(S, st, {
+#pragma unroll
+    for (int e = 0; e < 16; e++) S.x[e] = ldg_stream(src + ((size_t)rowS(lane, e) << LOGB) + c0 + (lane & 3));
+    invA_stages_S(S.x, lane, itw, q, q2);
+#pragma unroll
+    for (int e = 0; e < 16; e++) sm[padx(idxS(lane, e))] = S.x[e];
+  });
+  FOR_LANES(S, st, {
+#pragma unroll
+    for (int e = 0; e < 16; e++) S.x[e] = sm[padx(idxR(lane, e))];
+    invA_stages_R(S.x, itw, q, q2, invn, invn_w);
+  });
+}
+
+// forward pass B, LOGB = 8: values in st[].x layout H (lazy < 4q) -> st[].x layout C (lazy < 4q)
+HD void warp_fwdB8_regs(LaneB8 *st, u64 *sm, int r, const Tw *tw, u64 q) {
+  const u64 q2 = 2 * q;
+  LANE_DECL;
+  FOR_LANES(S, st, {
+    fwdB8_stages_H(S.x, r, tw, q, q2);
+#pragma unroll
+    for (int e = 0; e < 8; e++) sm[padx(idxH(lane, e))] = S.x[e];
+  });
+  FOR_LANES(S, st, {
+#pragma unroll
+    for (int e = 0; e < 8; e++) S.x[e] = sm[padx(idxM8(lane, e))];
+    fwdB8_stages_M(S.x, lane, r, tw, q, q2);
+#pragma unroll
+    for (int e = 0; e < 8; e++) sm[padx(idxM8(lane, e))] = S.x[e];
+  });
+  FOR_LANES(S, st, {
+#pragma unroll
+    for (int e = 0; e < 8; e++) S.x[e] = sm[padx(idxC8(lane, e))];
+    fwdB8_stages_C(S.x, lane, r, tw, q, q2);
+  });
+}
+// inverse pass B, LOGB = 8: st[].x layout C (values < 2q) -> st[].x layout H (lazy < 2q)
+HD void warp_invB8_regs(LaneB8 *st, u64 *sm, int r, const Tw *itw, u64 q) {
+  const u64 q2 = 2 * q;
+  LANE_DECL;
+  FOR_LANES(S, st, {
+    invB8_stages_C(S.x, lane, r, itw, q, q2);
+#pragma unroll
+    for (int e = 0; e < 8; e++) sm[padx(idxC8(lane, e))] = S.x[e];
+  });
+  FOR_LANES(S, st, {
+#pragma unroll
+    for (int e = 0; e < 8; e++) S.x[e] = sm[padx(idxM8(lane, e))];
+    invB8_stages_M(S.x, lane, r, itw, q, q2);
+#pragma unroll
+    for (int e = 0; e < 8; e++) sm[padx(idxM8(lane, e))] = S.x[e];
+  });
+  FOR_LANES(S, st, {
+#pragma unroll
+    for (int e = 0; e < 8; e++) S.x[e] = sm[padx(idxH(lane, e))];
+    invB8_stages_H(S.x, r, itw, q, q2);
+  });
+}
+
+// Galois automorphism in the bit-reversed NTT domain (SEAL GaloisTool::apply_galois_ntt):
+// out[i] = in[ bitrev( ((elt * (2*bitrev(i)+1)) >> 1) & (N-1) ) ]
+HD u32 brev32(u32 v) {
+#if defined(__CUDA_ARCH__)
+  return __brev(v);
+#else
+  v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+  v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+  v = ((v >> 4) & 0x0F0F0F0Fu) | ((v & 0x0F0F0F0Fu) << 4);
+  v = ((v >> 8) & 0x00FF00FFu) | ((v & 0x00FF00FFu) << 8);
+  return (v >> 16) | (v << 16);
+#endif
+}
+HD u32 galois_src_index(u32 i, u32 elt, int logN) {
+  u32 rev = brev32(i) >> (32 - logN);
+  u32 raw = (u32)((((u64)elt * (2 * (u64)rev + 1)) >> 1) & ((1u << logN) - 1));
+  return brev32(raw) >> (32 - logN);
+}

@@ -1,0 +1,157 @@
+// Host-side orchestration of the NTT-based operations: which warp-job kernels run, in
+// which order, over which scratch buffers.  Templated on a Launcher so that the very same
+// sequencing is exercised by the GPU launcher (kernels.cu) and by the test-only CPU warp
+// emulator (tests/emul/warp_emul.cpp).  No arithmetic happens here.
+//
+// Reference semantics (SEAL 4.0 via lib/Runtime/SEAL_HEVM.cpp):
+//   keyswitch : Evaluator::switch_key_inplace   (rotate: SEAL_HEVM.cpp:273, mulcc+relin: 315-316)
+//   rescale   : RNSTool::divide_and_round_q_last_ntt_inplace (SEAL_HEVM.cpp:283, also inside encrypt)
+#pragma once
+#include "ntt_bodies.cuh"
+
+struct Scratch {      // device (or emulator-host) buffers, sized for the top level
+  u64 *s1 = nullptr;  // [L][N]      inverse pass-B output
+  u64 *t = nullptr;   // [L][N]      coefficient-form digits / rounding term
+  u64 *s2 = nullptr;  // [L][L-1][N] forward pass-A output of every (I,J) digit  (also NTT staging)
+  u64 *acc = nullptr; // [2][L][N]   key-switch accumulators
+  u64 *s4 = nullptr;  // [2][L][N]   forward pass-A output of the rounding terms
+  u64 *pc0 = nullptr; // [L][N]      permuted c0 (rotate)
+  static size_t words(int L, size_t N) { return ((size_t)L + L + (size_t)L * (L - 1) + 2 * L + 2 * L + L) * N; }
+  void carve(u64 *base, int L, size_t N) {
+    s1 = base;
+    t = s1 + (size_t)L * N;
+    s2 = t + (size_t)L * N;
+    acc = s2 + (size_t)L * (L - 1) * N;
+    s4 = acc + (size_t)2 * L * N;
+    pc0 = s4 + (size_t)2 * L * N;
+  }
+};
+
+template <class LA> struct HeOps {
+  LA &la;
+  const NttTables *T; // device-visible tables
+  int logN, L;
+  size_t N;
+  Scratch sc;
+  HeOps(LA &l, const NttTables *tab, int logn, int nprimes) : la(l), T(tab), logN(logn), L(nprimes), N((size_t)1 << logn) {}
+  int sp() const { return L - 1; }
+
+  // forward NTT of nl limbs (limb k under prime prime0 + k*pstep); src may equal dst; canonical output
+  void ntt_fwd(const u64 *src, u64 *dst, int nl, int prime0, int pstep) {
+    for (int done = 0; done < nl;) { // staged through s2 in chunks
+      int chunk = nl - done;
+      int cap = L * (L - 1);
+      if (chunk > cap) chunk = cap;
+      ArgsFwdA a{};
+      a.T = T, a.src = src + (size_t)done * N, a.dst = sc.s2, a.nd = chunk, a.prime0 = prime0 + done * pstep, a.pstep = pstep;
+      la.template fwd_A<PRE_NONE>(a, chunk * TILES_A);
+      ArgsFwdB b{};
+      b.T = T, b.src = sc.s2, b.dst = dst + (size_t)done * N, b.nd = chunk, b.prime0 = a.prime0, b.pstep = pstep;
+      la.template fwd_B<EPI_CANON>(b, chunk * ROWS);
+      done += chunk;
+    }
+  }
+  // inverse NTT (canonical coefficients).  round=1 adds floor(q/2) mod q.
+  void ntt_inv(const u64 *src, u64 *dst, int nl, int prime0, int pstep, int round = 0) {
+    for (int done = 0; done < nl;) {
+      int chunk = nl - done;
+      int cap = L * (L - 1);
+      if (chunk > cap) chunk = cap;
+      ArgsInttB a{};
+      a.T = T, a.src = src + (size_t)done * N, a.dst = sc.s2, a.nl = chunk, a.prime0 = prime0 + done * pstep, a.pstep = pstep;
+      la.template intt_B<LD_PLAIN>(a, chunk * ROWS);
+      ArgsInttA b{};
+      b.T = T, b.src = sc.s2, b.dst = dst + (size_t)done * N, b.nl = chunk, b.prime0 = a.prime0, b.pstep = pstep, b.round = round;
+      la.intt_A(b, chunk * TILES_A);
+      done += chunk;
+    }
+  }
+
+  // ---- key switching --------------------------------------------------------------------
+  // mode LD_GALOIS : dst = (perm(c0), 0) + KS(perm(c1))   with src ciphertext `a`, Galois element elt
+  // mode LD_PRODUCT: dst = (a0 b0, a0 b1 + a1 b0) + KS(a1 b1)           (multiply + relinearize)
+  // `pitch` = words between the two polys of every ciphertext operand.  dst may alias a or b.
+  void keyswitch(int mode, const u64 *a, const u64 *b, u64 *dst, size_t pitch, int l, const u64 *key, u32 elt) {
+    // 1. t = INTT(target): inverse pass B fused with the gather / the tensor product d2
+    {
+      ArgsInttB x{};
+      x.T = T, x.dst = sc.s1, x.nl = l, x.prime0 = 0, x.pstep = 1, x.elt = elt;
+      if (mode == LD_GALOIS) {
+        x.src = a + pitch, x.c0 = a, x.pc0 = sc.pc0;
+        la.template intt_B<LD_GALOIS>(x, l * ROWS);
+      } else {
+        x.src = a + pitch, x.src2 = b + pitch;
+        la.template intt_B<LD_PRODUCT>(x, l * ROWS);
+      }
+      ArgsInttA y{};
+      y.T = T, y.src = sc.s1, y.dst = sc.t, y.nl = l, y.prime0 = 0, y.pstep = 1, y.round = 0;
+      la.intt_A(y, l * TILES_A);
+    }
+    // 2. mod-up: (t_J mod q_I) -> forward pass A, for every output prime I and digit J != I
+    {
+      ArgsFwdA x{};
+      x.T = T, x.src = sc.t, x.dst = sc.s2, x.nd = (l + 1) * l, x.l = l, x.sp = sp();
+      la.template fwd_A<PRE_MODUP>(x, (l + 1) * l * TILES_A);
+    }
+    // 3. forward pass B + inner product with the key over all digits
+    {
+      ArgsFwdB x{};
+      x.T = T, x.src = sc.s2, x.dst = sc.acc, x.l = l, x.sp = sp(), x.key = key, x.Ltot = L, x.ld = mode, x.elt = elt;
+      x.tgt = a + pitch, x.tgt2 = (mode == LD_PRODUCT) ? b + pitch : nullptr;
+      la.template fwd_B<EPI_MAC>(x, (l + 1) * ROWS);
+    }
+    // 4. mod-down by the special prime with rounding, fused with the final accumulate
+    {
+      // r = INTT_p(acc[K][l]) + p/2   (two limbs at stride (l+1)*N: run them as two 1-limb launches)
+      for (int K = 0; K < 2; K++) {
+        ArgsInttB x{};
+        x.T = T, x.src = sc.acc + ((size_t)K * (l + 1) + l) * N, x.dst = sc.s1 + (size_t)K * N, x.nl = 1, x.prime0 = sp(), x.pstep = 0;
+        la.template intt_B<LD_PLAIN>(x, ROWS);
+      }
+      ArgsInttA y{};
+      y.T = T, y.src = sc.s1, y.dst = sc.t, y.nl = 2, y.prime0 = sp(), y.pstep = 0, y.round = 1;
+      la.intt_A(y, 2 * TILES_A);
+      ArgsFwdA z{};
+      z.T = T, z.src = sc.t, z.dst = sc.s4, z.nd = 2 * l, z.l = l, z.plast = sp();
+      la.template fwd_A<PRE_ROUND>(z, 2 * l * TILES_A);
+      ArgsFwdB w{};
+      w.T = T, w.src = sc.s4, w.dst = dst, w.l = l, w.sp = sp(), w.acc = sc.acc, w.pitch = pitch, w.plast = sp();
+      if (mode == LD_GALOIS) {
+        w.add0 = sc.pc0;
+        la.template fwd_B<EPI_MODDOWN_GALOIS>(w, 2 * l * ROWS);
+      } else {
+        w.add0 = a, w.add1 = b;
+        la.template fwd_B<EPI_MODDOWN_RELIN>(w, l * ROWS);
+      }
+    }
+  }
+
+  // ---- rescale: npoly polys with l limbs -> l-1 limbs (divide by q_{l-1} and round) -------
+  // src/dst poly pitches may differ (encrypt uses a compact (l)-limb temporary).
+  void rescale(const u64 *src, size_t src_pitch, u64 *dst, size_t dst_pitch, int l) {
+    for (int K = 0; K < 2; K++) {
+      ArgsInttB x{};
+      x.T = T, x.src = src + (size_t)K * src_pitch + (size_t)(l - 1) * N, x.dst = sc.s1 + (size_t)K * N, x.nl = 1, x.prime0 = l - 1, x.pstep = 0;
+      la.template intt_B<LD_PLAIN>(x, ROWS);
+    }
+    ArgsInttA y{};
+    y.T = T, y.src = sc.s1, y.dst = sc.t, y.nl = 2, y.prime0 = l - 1, y.pstep = 0, y.round = 1;
+    la.intt_A(y, 2 * TILES_A);
+    ArgsFwdA z{};
+    z.T = T, z.src = sc.t, z.dst = sc.s4, z.nd = 2 * (l - 1), z.l = l - 1, z.plast = l - 1;
+    la.template fwd_A<PRE_ROUND>(z, 2 * (l - 1) * TILES_A);
+    if (src_pitch != dst_pitch) {
+      // epilogue addresses input and output with one pitch: run per poly
+      for (int K = 0; K < 2; K++) {
+        ArgsFwdB w{};
+        w.T = T, w.src = sc.s4 + (size_t)K * (l - 1) * N, w.dst = dst + (size_t)K * dst_pitch, w.l = l - 1, w.add0 = src + (size_t)K * src_pitch;
+        w.pitch = 0, w.plast = l - 1;
+        la.template fwd_B<EPI_RESCALE>(w, (l - 1) * ROWS);
+      }
+    } else {
+      ArgsFwdB w{};
+      w.T = T, w.src = sc.s4, w.dst = dst, w.l = l - 1, w.add0 = src, w.pitch = dst_pitch, w.plast = l - 1;
+      la.template fwd_B<EPI_RESCALE>(w, 2 * (l - 1) * ROWS);
+    }
+  }
+};

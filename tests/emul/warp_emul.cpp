@@ -1,0 +1,82 @@
+// TEST INFRASTRUCTURE ONLY -- CPU warp emulator for the CUDA warp-job bodies.
+//
+// Compiles dacapo_b200/csrc/{ntt_core,ntt_bodies}.cuh and the launcher-templated
+// orchestration (ops.hpp) for the host: every warp job is replayed as a 32-iteration loop
+// over lane states with a plain array standing in for the warp's shared-memory tile.  This
+// lets the CPU-only test tier (-m "not gpu") check the index maths, twiddle indexing and
+// fusion logic of the kernels bit-for-bit against the oracle without a GPU.  It is never
+// linked into libB200_HEVM.so and is not a fallback: the product has no host execution path.
+#include "../../dacapo_b200/csrc/host_params.hpp"
+#include "../../dacapo_b200/csrc/ops.hpp"
+#include <cstring>
+
+struct EmuLauncher {
+  template <int LD> void intt_B(const ArgsInttB &a, int njobs) {
+    for (int j = 0; j < njobs; j++) {
+      LaneB8 st[32];
+      u64 sm[WARP_SMEM_WORDS];
+      body_intt_B<LD>(a, j, st, sm);
+    }
+  }
+  void intt_A(const ArgsInttA &a, int njobs) {
+    for (int j = 0; j < njobs; j++) {
+      LaneA st[32];
+      u64 sm[WARP_SMEM_WORDS];
+      body_intt_A(a, j, st, sm);
+    }
+  }
+  template <int PRE> void fwd_A(const ArgsFwdA &a, int njobs) {
+    for (int j = 0; j < njobs; j++) {
+      LaneA st[32];
+      u64 sm[WARP_SMEM_WORDS];
+      body_fwd_A<PRE>(a, j, st, sm);
+    }
+  }
+  template <int EPI> void fwd_B(const ArgsFwdB &a, int njobs) {
+    for (int j = 0; j < njobs; j++) {
+      LaneB8 st[32];
+      u64 sm[WARP_SMEM_WORDS];
+      body_fwd_B<EPI>(a, j, st, sm);
+    }
+  }
+};
+
+struct Emu {
+  hp::HostParams P;
+  EmuLauncher la;
+  HeOps<EmuLauncher> *ops;
+  std::vector<u64> scratch;
+};
+
+extern "C" {
+void *emul_create(int logN, int L, int bits) {
+  auto e = new Emu();
+  e->P.build(logN, L, bits);
+  e->P.tab.tw = e->P.tw.data();
+  e->P.tab.itw = e->P.itw.data();
+  e->ops = new HeOps<EmuLauncher>(e->la, &e->P.tab, logN, L);
+  e->scratch.resize(Scratch::words(L, e->P.N));
+  e->ops->sc.carve(e->scratch.data(), L, e->P.N);
+  return e;
+}
+void emul_primes(void *h, u64 *q, u64 *psi) {
+  auto e = (Emu *)h;
+  for (int i = 0; i < e->P.L; i++) q[i] = e->P.q[i], psi[i] = e->P.psi[i];
+}
+void emul_ntt(void *h, u64 *data, int prime, int count, int inverse) {
+  auto e = (Emu *)h;
+  if (inverse)
+    e->ops->ntt_inv(data, data, count, prime, 0);
+  else
+    e->ops->ntt_fwd(data, data, count, prime, 0);
+}
+// ciphertext operands: compact [2][l][N]; dst may alias a or b
+void emul_keyswitch(void *h, int mode, const u64 *a, const u64 *b, u64 *dst, int l, const u64 *key, u32 elt) {
+  auto e = (Emu *)h;
+  e->ops->keyswitch(mode, a, b, dst, (size_t)l * e->P.N, l, key, elt);
+}
+void emul_rescale(void *h, const u64 *src, u64 *dst, int l) {
+  auto e = (Emu *)h;
+  e->ops->rescale(src, (size_t)l * e->P.N, dst, (size_t)(l - 1) * e->P.N, l);
+}
+}

@@ -1,0 +1,111 @@
+"""CPU tier: the CUDA warp-job bodies, replayed lane-by-lane by the test-only warp emulator
+(tests/emul/warp_emul.cpp), must reproduce the oracle bit-for-bit at the real ring size
+N = 2^15.  This checks the kernels' index maths / fusion logic without a GPU; the `-m gpu`
+tests then check the same kernels on the device through the C ABI.
+"""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from dacapo_b200 import hevm_asm as asm
+from util import VM
+
+HERE = Path(__file__).resolve().parent
+u64p = C.POINTER(C.c_uint64)
+LOGN, NPR = 15, 4
+
+
+@pytest.fixture(scope="module")
+def emul():
+    so = HERE / "emul" / "libwarp_emul.so"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", str(so), str(HERE / "emul" / "warp_emul.cpp")], check=True)
+    lib = C.CDLL(str(so))
+    lib.emul_create.restype = C.c_void_p
+    lib.emul_create.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.emul_primes.argtypes = [C.c_void_p, u64p, u64p]
+    lib.emul_ntt.argtypes = [C.c_void_p, u64p, C.c_int, C.c_int, C.c_int]
+    lib.emul_keyswitch.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p, C.c_int, u64p, C.c_uint32]
+    lib.emul_rescale.argtypes = [C.c_void_p, u64p, u64p, C.c_int]
+    return lib, lib.emul_create(LOGN, NPR, 60)
+
+
+@pytest.fixture(scope="module")
+def vm(oracle_lib):
+    return VM(oracle_lib, LOGN, NPR, nct=4, npt=1)
+
+
+def _p(a):
+    return a.ctypes.data_as(u64p)
+
+
+def test_host_params_match_oracle(emul, vm):
+    lib, h = emul
+    q, psi = np.zeros(NPR, dtype=np.uint64), np.zeros(NPR, dtype=np.uint64)
+    lib.emul_primes(h, _p(q), _p(psi))
+    assert [int(x) for x in q] == vm.primes
+    assert [int(x) for x in psi] == vm.roots
+
+
+@pytest.mark.parametrize("prime", [0, NPR - 1])
+def test_ntt_kernels_vs_oracle(emul, vm, prime):
+    lib, h = emul
+    rng = np.random.default_rng(prime)
+    f = rng.integers(0, vm.primes[prime], size=(2, vm.N), dtype=np.uint64)
+    f[1, :4] = [0, 1, vm.primes[prime] - 1, vm.primes[prime] - 2]
+    exp = vm.ntt(f, prime)
+    got = f.copy()
+    lib.emul_ntt(h, _p(got), prime, 2, 0)
+    assert np.array_equal(got, exp)
+    lib.emul_ntt(h, _p(got), prime, 2, 1)
+    assert np.array_equal(got, f)
+
+
+def test_rescale_kernels_vs_oracle(emul, vm):
+    lib, h = emul
+    a = vm.random_ct(3, 1)
+    vm.ct_write(0, a)
+    vm.exec(asm.RESCALE, 1, 0)
+    exp = vm.ct_read(1)
+    got = np.zeros((2, 2, vm.N), dtype=np.uint64)
+    lib.emul_rescale(h, _p(a), _p(got), 3)
+    assert np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize("lvl", [1, 3])
+def test_mulcc_relin_kernels_vs_oracle(emul, vm, lvl):
+    lib, h = emul
+    a, b = vm.random_ct(lvl, 2), vm.random_ct(lvl, 3)
+    vm.ct_write(0, a)
+    vm.ct_write(1, b)
+    vm.exec(asm.MULCC, 2, 0, 1)
+    exp = vm.ct_read(2)
+    key = vm.key(2)
+    got = np.zeros_like(a)
+    lib.emul_keyswitch(h, 2, _p(a), _p(b), _p(got), lvl, _p(key), 0)
+    assert np.array_equal(got, exp)
+    # in place (dst aliases lhs), and squaring (lhs is rhs)
+    a2 = a.copy()
+    lib.emul_keyswitch(h, 2, _p(a2), _p(b), _p(a2), lvl, _p(key), 0)
+    assert np.array_equal(a2, exp)
+    vm.exec(asm.MULCC, 2, 0, 0)
+    a3 = a.copy()
+    lib.emul_keyswitch(h, 2, _p(a3), _p(a3), _p(a3), lvl, _p(key), 0)
+    assert np.array_equal(a3, vm.ct_read(2))
+
+
+@pytest.mark.parametrize("step", [1, -4])
+def test_rotate_kernels_vs_oracle(emul, vm, step):
+    lib, h = emul
+    lvl = 2
+    a = vm.random_ct(lvl, 4)
+    vm.ct_write(0, a)
+    vm.exec(asm.ROTATE, 1, 0, step)
+    exp = vm.ct_read(1)
+    elt = vm.lib.hevmx_galois_elt(vm.vm, step)
+    key = vm.key(3, elt)
+    got = a.copy()  # in place
+    lib.emul_keyswitch(h, 1, _p(got), None, _p(got), lvl, _p(key), elt)
+    assert np.array_equal(got, exp)
