@@ -1,0 +1,472 @@
+// sm_100a kernels of libB200_HEVM.so.
+//
+//  * NTT-based warp-job kernels: thin __global__ wrappers around ntt_bodies.cuh.  A CTA is
+//    8 independent warps (256 threads); each warp owns one job and a private padded
+//    shared-memory tile; there is no __syncthreads anywhere.
+//  * element-wise RNS kernels (256-bit vector loads/stores, one HBM pass)
+//  * samplers, key-generation / encryption helpers
+//  * fp64 CKKS encoder / decoder kernels (radix-2 special FFT, explicit *_rn intrinsics so that
+//    no FMA contraction changes bits w.r.t. the host restatement)
+#include "kernels.h"
+
+unsigned long long g_launch_count = 0;
+
+#define WARPS_PER_CTA 8
+#define CTA_THREADS (WARPS_PER_CTA * 32)
+
+template <int LD> __global__ void __launch_bounds__(CTA_THREADS) k_intt_B(ArgsInttB a, int njobs) {
+  __shared__ u64 sm[WARPS_PER_CTA][WARP_SMEM_WORDS];
+  const int warp = threadIdx.x >> 5, job = blockIdx.x * WARPS_PER_CTA + warp;
+  if (job >= njobs) return;
+  LaneB8 st[1];
+  body_intt_B<LD>(a, job, st, sm[warp]);
+}
+__global__ void __launch_bounds__(CTA_THREADS) k_intt_A(ArgsInttA a, int njobs) {
+  __shared__ u64 sm[WARPS_PER_CTA][WARP_SMEM_WORDS];
+  const int warp = threadIdx.x >> 5, job = blockIdx.x * WARPS_PER_CTA + warp;
+  if (job >= njobs) return;
+  LaneA st[1];
+  body_intt_A(a, job, st, sm[warp]);
+}
+template <int PRE> __global__ void __launch_bounds__(CTA_THREADS) k_fwd_A(ArgsFwdA a, int njobs) {
+  __shared__ u64 sm[WARPS_PER_CTA][WARP_SMEM_WORDS];
+  const int warp = threadIdx.x >> 5, job = blockIdx.x * WARPS_PER_CTA + warp;
+  if (job >= njobs) return;
+  LaneA st[1];
+  body_fwd_A<PRE>(a, job, st, sm[warp]);
+}
+template <int EPI> __global__ void __launch_bounds__(CTA_THREADS) k_fwd_B(ArgsFwdB a, int njobs) {
+  __shared__ u64 sm[WARPS_PER_CTA][WARP_SMEM_WORDS];
+  const int warp = threadIdx.x >> 5, job = blockIdx.x * WARPS_PER_CTA + warp;
+  if (job >= njobs) return;
+  LaneB8 st[1];
+  body_fwd_B<EPI>(a, job, st, sm[warp]);
+}
+
+static inline int ctas_for(int njobs) { return (njobs + WARPS_PER_CTA - 1) / WARPS_PER_CTA; }
+#define POST_LAUNCH()                                                                                                  \
+  do {                                                                                                                 \
+    g_launch_count++;                                                                                                  \
+    CUDA_CHECK(cudaGetLastError());                                                                                    \
+  } while (0)
+
+template <int LD> void GpuLauncher::intt_B(const ArgsInttB &a, int njobs) {
+  if (njobs <= 0) return;
+  k_intt_B<LD><<<ctas_for(njobs), CTA_THREADS, 0, stream>>>(a, njobs);
+  POST_LAUNCH();
+}
+void GpuLauncher::intt_A(const ArgsInttA &a, int njobs) {
+  if (njobs <= 0) return;
+  k_intt_A<<<ctas_for(njobs), CTA_THREADS, 0, stream>>>(a, njobs);
+  POST_LAUNCH();
+}
+template <int PRE> void GpuLauncher::fwd_A(const ArgsFwdA &a, int njobs) {
+  if (njobs <= 0) return;
+  k_fwd_A<PRE><<<ctas_for(njobs), CTA_THREADS, 0, stream>>>(a, njobs);
+  POST_LAUNCH();
+}
+template <int EPI> void GpuLauncher::fwd_B(const ArgsFwdB &a, int njobs) {
+  if (njobs <= 0) return;
+  k_fwd_B<EPI><<<ctas_for(njobs), CTA_THREADS, 0, stream>>>(a, njobs);
+  POST_LAUNCH();
+}
+template void GpuLauncher::intt_B<LD_PLAIN>(const ArgsInttB &, int);
+template void GpuLauncher::intt_B<LD_GALOIS>(const ArgsInttB &, int);
+template void GpuLauncher::intt_B<LD_PRODUCT>(const ArgsInttB &, int);
+template void GpuLauncher::fwd_A<PRE_NONE>(const ArgsFwdA &, int);
+template void GpuLauncher::fwd_A<PRE_MODUP>(const ArgsFwdA &, int);
+template void GpuLauncher::fwd_A<PRE_ROUND>(const ArgsFwdA &, int);
+template void GpuLauncher::fwd_B<EPI_CANON>(const ArgsFwdB &, int);
+template void GpuLauncher::fwd_B<EPI_MAC>(const ArgsFwdB &, int);
+template void GpuLauncher::fwd_B<EPI_MODDOWN_GALOIS>(const ArgsFwdB &, int);
+template void GpuLauncher::fwd_B<EPI_MODDOWN_RELIN>(const ArgsFwdB &, int);
+template void GpuLauncher::fwd_B<EPI_RESCALE>(const ArgsFwdB &, int);
+
+// =====================================================================================
+// element-wise kernels.  One thread = 4 consecutive coefficients (256-bit accesses).
+// =====================================================================================
+template <int OP>
+__global__ void __launch_bounds__(256) k_elementwise(const NttTables *T, int logN, u64 *out, const u64 *a, const u64 *b,
+                                                     const u64 *p, size_t pitch, int l, size_t nvec) {
+  const size_t polyw = (size_t)l << logN;
+  for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
+    const size_t w = v * 4;
+    const int K = w >= polyw;
+    const size_t rem = w - (K ? polyw : 0);
+    const int i = (int)(rem >> logN);
+    const size_t off = (size_t)K * pitch + rem;
+    const u64 q = T->mod[i].q;
+    u64 x[4], y[4], r[4];
+    ldg_stream4(a + off, x[0], x[1], x[2], x[3]);
+    if (OP == EW_ADD) {
+      ldg_stream4(b + off, y[0], y[1], y[2], y[3]);
+#pragma unroll
+      for (int e = 0; e < 4; e++) r[e] = csub(x[e] + y[e], q);
+    } else if (OP == EW_NEG) {
+#pragma unroll
+      for (int e = 0; e < 4; e++) r[e] = negmod(x[e], q);
+    } else if (OP == EW_ADDP) {
+      if (K == 0) {
+        ldg_stream4(p + rem, y[0], y[1], y[2], y[3]);
+#pragma unroll
+        for (int e = 0; e < 4; e++) r[e] = csub(x[e] + y[e], q);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; e++) r[e] = x[e];
+      }
+    } else if (OP == EW_MULP) {
+      const ModQ m = T->mod[i];
+      ldg_stream4(p + rem, y[0], y[1], y[2], y[3]);
+#pragma unroll
+      for (int e = 0; e < 4; e++) r[e] = mulmod(x[e], y[e], m);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; e++) r[e] = x[e];
+    }
+    stg4(out + off, r[0], r[1], r[2], r[3]);
+  }
+}
+static int ew_grid(size_t nthreads) {
+  size_t g = (nthreads + 255) / 256;
+  const size_t cap = 148 * 8; // 8 resident CTAs of 256 threads per SM, 148 SMs
+  return (int)(g < cap ? g : cap);
+}
+void launch_elementwise(cudaStream_t s, int op, const NttTables *T, int logN, u64 *out, const u64 *a, const u64 *b,
+                        const u64 *p, size_t pitch, int l) {
+  const size_t nvec = ((size_t)2 * l << logN) / 4;
+  const int g = ew_grid(nvec);
+  switch (op) {
+  case EW_ADD: k_elementwise<EW_ADD><<<g, 256, 0, s>>>(T, logN, out, a, b, p, pitch, l, nvec); break;
+  case EW_NEG: k_elementwise<EW_NEG><<<g, 256, 0, s>>>(T, logN, out, a, b, p, pitch, l, nvec); break;
+  case EW_ADDP: k_elementwise<EW_ADDP><<<g, 256, 0, s>>>(T, logN, out, a, b, p, pitch, l, nvec); break;
+  case EW_MULP: k_elementwise<EW_MULP><<<g, 256, 0, s>>>(T, logN, out, a, b, p, pitch, l, nvec); break;
+  default: k_elementwise<EW_COPY><<<g, 256, 0, s>>>(T, logN, out, a, b, p, pitch, l, nvec); break;
+  }
+  POST_LAUNCH();
+}
+
+// =====================================================================================
+// samplers: rnd(seed, stream, idx) = mix(mix(seed + G*(stream+1)) + G*(idx+1))
+// =====================================================================================
+__device__ __forceinline__ u64 mix64(u64 z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ u64 rnd64(u64 seed, u64 stream, u64 idx) {
+  const u64 G = 0x9E3779B97F4A7C15ull;
+  return mix64(mix64(seed + G * (stream + 1)) + G * (idx + 1));
+}
+template <int CBD>
+__global__ void k_sample_small(const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream) {
+  const size_t N = (size_t)1 << logN;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < N; k += (size_t)gridDim.x * blockDim.x) {
+    const u64 w = rnd64(seed, stream, k);
+    int t;
+    if (CBD)
+      t = __popcll(w & 0x1FFFFF) - __popcll((w >> 21) & 0x1FFFFF);
+    else
+      t = (int)(w % 3) - 1;
+    for (int i = 0; i < limbs; i++) out[(size_t)i * N + k] = t < 0 ? T->mod[i].q - (u64)(-t) : (u64)t;
+  }
+}
+__global__ void k_sample_uniform(const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream_base) {
+  const size_t N = (size_t)1 << logN, total = N * limbs;
+  for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < total; v += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(v >> logN);
+    const size_t k = v & (N - 1);
+    const u64 hi = rnd64(seed, stream_base + i, 2 * k), lo = rnd64(seed, stream_base + i, 2 * k + 1);
+    out[v] = reduce128(lo, hi, T->mod[i]);
+  }
+}
+void launch_sample_ternary(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream) {
+  k_sample_small<0><<<ew_grid((size_t)1 << logN), 256, 0, s>>>(T, logN, out, limbs, seed, stream);
+  POST_LAUNCH();
+}
+void launch_sample_cbd(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream) {
+  k_sample_small<1><<<ew_grid((size_t)1 << logN), 256, 0, s>>>(T, logN, out, limbs, seed, stream);
+  POST_LAUNCH();
+}
+void launch_sample_uniform(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream_base) {
+  k_sample_uniform<<<ew_grid((size_t)limbs << logN), 256, 0, s>>>(T, logN, out, limbs, seed, stream_base);
+  POST_LAUNCH();
+}
+
+// =====================================================================================
+// key generation / encryption helpers
+// =====================================================================================
+__global__ void k_ksk_finish(const NttTables *T, int logN, int L, u64 *c0, const u64 *c1, const u64 *sk, const u64 *e,
+                             const u64 *newkey, int digit) {
+  const size_t N = (size_t)1 << logN, total = N * L;
+  const u64 pspecial = T->mod[L - 1].q;
+  for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < total; v += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(v >> logN);
+    const ModQ m = T->mod[i];
+    u64 r = negmod(csub(mulmod(c1[v], sk[v], m) + e[v], m.q), m.q);
+    if (i == digit) r = csub(r + mulmod(newkey[v], reduce64(pspecial, m), m), m.q);
+    c0[v] = r;
+  }
+}
+void launch_ksk_finish(cudaStream_t s, const NttTables *T, int logN, int L, u64 *c0, const u64 *c1, const u64 *sk,
+                       const u64 *e, const u64 *newkey, int digit) {
+  k_ksk_finish<<<ew_grid((size_t)L << logN), 256, 0, s>>>(T, logN, L, c0, c1, sk, e, newkey, digit);
+  POST_LAUNCH();
+}
+__global__ void k_square(const NttTables *T, int logN, int L, u64 *out, const u64 *in) {
+  const size_t total = (size_t)L << logN;
+  for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < total; v += (size_t)gridDim.x * blockDim.x)
+    out[v] = mulmod(in[v], in[v], T->mod[v >> logN]);
+}
+void launch_square(cudaStream_t s, const NttTables *T, int logN, int L, u64 *out, const u64 *in) {
+  k_square<<<ew_grid((size_t)L << logN), 256, 0, s>>>(T, logN, L, out, in);
+  POST_LAUNCH();
+}
+__global__ void k_galois_gather(int logN, int L, u64 *out, const u64 *in, u32 elt) {
+  const size_t N = (size_t)1 << logN, total = N * L;
+  for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < total; v += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = v >> logN;
+    out[v] = in[i * N + galois_src_index((u32)(v & (N - 1)), elt, logN)];
+  }
+}
+void launch_galois_gather(cudaStream_t s, int logN, int L, u64 *out, const u64 *in, u32 elt) {
+  k_galois_gather<<<ew_grid((size_t)L << logN), 256, 0, s>>>(logN, L, out, in, elt);
+  POST_LAUNCH();
+}
+__global__ void k_enc_combine(const NttTables *T, int logN, int nl, u64 *c, const u64 *u, const u64 *pk, size_t pk_pitch,
+                              const u64 *e) {
+  const size_t polyw = (size_t)nl << logN, total = 2 * polyw;
+  for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < total; v += (size_t)gridDim.x * blockDim.x) {
+    const int j = v >= polyw;
+    const size_t rem = v - (j ? polyw : 0);
+    const ModQ m = T->mod[rem >> logN];
+    c[v] = csub(mulmod(u[rem], pk[(size_t)j * pk_pitch + rem], m) + e[v], m.q);
+  }
+}
+void launch_enc_combine(cudaStream_t s, const NttTables *T, int logN, int nl, u64 *c, const u64 *u, const u64 *pk,
+                        size_t pk_pitch, const u64 *e) {
+  k_enc_combine<<<ew_grid((size_t)2 * nl << logN), 256, 0, s>>>(T, logN, nl, c, u, pk, pk_pitch, e);
+  POST_LAUNCH();
+}
+__global__ void k_decrypt(const NttTables *T, int logN, int l, u64 *pt, const u64 *ct, size_t pitch, const u64 *sk) {
+  const size_t total = (size_t)l << logN;
+  for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < total; v += (size_t)gridDim.x * blockDim.x) {
+    const ModQ m = T->mod[v >> logN];
+    pt[v] = csub(ct[v] + mulmod(ct[pitch + v], sk[v], m), m.q);
+  }
+}
+void launch_decrypt(cudaStream_t s, const NttTables *T, int logN, int l, u64 *pt, const u64 *ct, size_t pitch, const u64 *sk) {
+  k_decrypt<<<ew_grid((size_t)l << logN), 256, 0, s>>>(T, logN, l, pt, ct, pitch, sk);
+  POST_LAUNCH();
+}
+
+// =====================================================================================
+// CKKS encoder / decoder (fp64).  Butterfly DAG and operation order of SEAL's
+// DWTHandler::transform_from_rev / transform_to_rev with complex<double> arithmetic
+// (SURVEY.md A.2.9); *_rn intrinsics are never contracted into FMAs.
+// =====================================================================================
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(__dadd_rn(a.x, b.x), __dadd_rn(a.y, b.y)); }
+__device__ __forceinline__ double2 csubc(double2 a, double2 b) { return make_double2(__dsub_rn(a.x, b.x), __dsub_rn(a.y, b.y)); }
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+  return make_double2(__dsub_rn(__dmul_rn(a.x, b.x), __dmul_rn(a.y, b.y)), __dadd_rn(__dmul_rn(a.x, b.y), __dmul_rn(a.y, b.x)));
+}
+__global__ void k_enc_scatter(int logN, const double *vals, int len, const u32 *slot_index, double2 *work,
+                              unsigned long long *maxbits) {
+  const size_t slots = (size_t)1 << (logN - 1);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *maxbits = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < slots; i += (size_t)gridDim.x * blockDim.x) {
+    const double v = vals[i % len];
+    work[slot_index[i]] = make_double2(v, 0.0);
+    work[slot_index[slots + i]] = make_double2(v, -0.0);
+  }
+}
+// Gentleman-Sande stage with m groups of gap = n/(2m); roots consumed at index (n - 2m) + 1 + group
+__global__ void k_fft_gs(int logN, double2 *v, const double2 *roots, int m, int gap, double fix, int last) {
+  const size_t half = (size_t)1 << (logN - 1), n = half * 2;
+  for (size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x; b < half; b += (size_t)gridDim.x * blockDim.x) {
+    const size_t g = b / gap, j = b - g * gap, off = 2 * g * gap + j;
+    const double2 r = roots[(n - 2 * (size_t)m) + 1 + g];
+    const double2 u = v[off], w = v[off + gap];
+    if (!last) {
+      v[off] = cadd(u, w);
+      v[off + gap] = cmul(csubc(u, w), r);
+    } else {
+      const double2 sr = make_double2(__dmul_rn(r.x, fix), __dmul_rn(r.y, fix));
+      const double2 s = cadd(u, w);
+      v[off] = make_double2(__dmul_rn(s.x, fix), __dmul_rn(s.y, fix));
+      v[off + gap] = cmul(csubc(u, w), sr);
+    }
+  }
+}
+// Cooley-Tukey stage with m groups; root index m + group
+__global__ void k_fft_ct(int logN, double2 *v, const double2 *roots, int m, int gap) {
+  const size_t half = (size_t)1 << (logN - 1);
+  for (size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x; b < half; b += (size_t)gridDim.x * blockDim.x) {
+    const size_t g = b / gap, j = b - g * gap, off = 2 * g * gap + j;
+    const double2 r = roots[(size_t)m + g];
+    const double2 u = v[off], w = cmul(v[off + gap], r);
+    v[off] = cadd(u, w);
+    v[off + gap] = csubc(u, w);
+  }
+}
+__global__ void k_enc_max(int logN, const double2 *work, unsigned long long *maxbits) {
+  const size_t n = (size_t)1 << logN;
+  double mx = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    mx = fmax(mx, fabs(work[i].x));
+  for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(maxbits, (unsigned long long)__double_as_longlong(mx)); // mx >= 0: bit order == value order
+}
+__global__ void k_enc_round(const NttTables *T, int logN, int level, const double2 *work, const unsigned long long *maxbits,
+                            u64 *out) {
+  const size_t n = (size_t)1 << logN;
+  // ceil(log2(max(maxc,1))) computed exactly from the exponent / mantissa
+  const double maxc = fmax(__longlong_as_double((long long)*maxbits), 1.0);
+  int ex;
+  const double mant = frexp(maxc, &ex); // maxc = mant * 2^ex, mant in [0.5,1)
+  const int bits = (mant == 0.5) ? ex - 1 : ex;
+  if (bits > 128) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) printf("[b200-hevm] fatal: encode: coefficient wider than 128 bits\n");
+    __trap();
+  }
+  const double two64 = 18446744073709551616.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double c = round(work[i].x);
+    const bool neg = signbit(c);
+    c = fabs(c);
+    if (bits <= 64) {
+      const u64 cu = (u64)c;
+      for (int j = 0; j < level; j++) {
+        const ModQ m = T->mod[j];
+        const u64 r = reduce64(cu, m);
+        out[(size_t)j * n + i] = neg ? negmod(r, m.q) : r;
+      }
+    } else {
+      const u64 lo = (u64)fmod(c, two64), hi = (u64)(c / two64);
+      for (int j = 0; j < level; j++) {
+        const ModQ m = T->mod[j];
+        const u64 r = reduce128(lo, hi, m);
+        out[(size_t)j * n + i] = neg ? negmod(r, m.q) : r;
+      }
+    }
+  }
+}
+void launch_encode(cudaStream_t s, const NttTables *T, const EncoderTables &E, int logN, const double *vals, int len,
+                   int level, double scale, double2 *work, unsigned long long *maxbits, u64 *out) {
+  const size_t n = (size_t)1 << logN;
+  k_enc_scatter<<<ew_grid(n / 2), 256, 0, s>>>(logN, vals, len, E.slot_index, work, maxbits);
+  POST_LAUNCH();
+  const double fix = scale / (double)n;
+  int gap = 1;
+  for (size_t m = n >> 1; m >= 1; m >>= 1, gap <<= 1) {
+    k_fft_gs<<<ew_grid(n / 2), 256, 0, s>>>(logN, work, E.inv_root, (int)m, gap, fix, m == 1);
+    POST_LAUNCH();
+  }
+  k_enc_max<<<ew_grid(n), 256, 0, s>>>(logN, work, maxbits);
+  POST_LAUNCH();
+  k_enc_round<<<ew_grid(n), 256, 0, s>>>(T, logN, level, work, maxbits, out);
+  POST_LAUNCH();
+}
+
+#define DEC_MAXW 33
+__global__ void k_dec_compose(const NttTables *T, int logN, int l, const u64 *coeff, DecodeTables D, double inv_scale,
+                              double2 *work) {
+  const size_t n = (size_t)1 << logN;
+  const double two64 = 18446744073709551616.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    u64 val[DEC_MAXW];
+    for (int k = 0; k <= l; k++) val[k] = 0;
+    for (int j = 0; j < l; j++) {
+      const ModQ m = T->mod[j];
+      const u64 t = mulmod(coeff[(size_t)j * n + i], D.invp[j], m);
+      // val += punct[j] * t   (< Q), then one conditional subtraction of Q
+      u64 carry = 0, cy = 0;
+      for (int k = 0; k < l; k++) {
+        const u64 pw = D.punct[(size_t)j * l + k];
+        u64 lo = pw * t, hi = __umul64hi(pw, t);
+        lo += carry;
+        hi += (lo < carry);
+        carry = hi;
+        u64 s1 = val[k] + lo;
+        u64 c1 = s1 < lo;
+        u64 s2 = s1 + cy;
+        u64 c2 = s2 < cy;
+        val[k] = s2;
+        cy = c1 + c2;
+      }
+      val[l] = carry + cy; // carry is 0 because punct[j]*t < Q
+      bool ge = val[l] != 0;
+      if (!ge) {
+        ge = true;
+        for (int k = l - 1; k >= 0; k--) {
+          const u64 qk = D.Q[k];
+          if (val[k] != qk) {
+            ge = val[k] > qk;
+            break;
+          }
+        }
+      }
+      if (ge) {
+        u64 borrow = 0;
+        for (int k = 0; k < l; k++) {
+          const u64 qk = D.Q[k];
+          const u64 d1 = val[k] - qk;
+          const u64 b1 = val[k] < qk;
+          const u64 d2 = d1 - borrow;
+          const u64 b2 = d1 < borrow;
+          val[k] = d2;
+          borrow = b1 + b2;
+        }
+        val[l] -= borrow;
+      }
+    }
+    bool upper = true; // val >= half ?
+    for (int k = l - 1; k >= 0; k--) {
+      const u64 hk = D.half[k];
+      if (val[k] != hk) {
+        upper = val[k] > hk;
+        break;
+      }
+    }
+    double r = 0.0, s64 = inv_scale;
+    if (upper) {
+      for (int j = 0; j < l; j++, s64 = __dmul_rn(s64, two64)) {
+        const u64 qj = D.Q[j];
+        if (val[j] > qj) {
+          const u64 diff = val[j] - qj;
+          r = __dadd_rn(r, diff ? __dmul_rn((double)diff, s64) : 0.0);
+        } else {
+          const u64 diff = qj - val[j];
+          r = __dsub_rn(r, diff ? __dmul_rn((double)diff, s64) : 0.0);
+        }
+      }
+    } else {
+      for (int j = 0; j < l; j++, s64 = __dmul_rn(s64, two64)) {
+        const u64 cc = val[j];
+        r = __dadd_rn(r, cc ? __dmul_rn((double)cc, s64) : 0.0);
+      }
+    }
+    work[i] = make_double2(r, 0.0);
+  }
+}
+__global__ void k_dec_gather(int logN, const double2 *work, const u32 *slot_index, double *out) {
+  const size_t slots = (size_t)1 << (logN - 1);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < slots; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = work[slot_index[i]].x;
+}
+void launch_decode(cudaStream_t s, const NttTables *T, const EncoderTables &E, const DecodeTables &D, int logN, int l,
+                   const u64 *coeff, double scale, double2 *work, double *out) {
+  const size_t n = (size_t)1 << logN;
+  if (l + 1 > DEC_MAXW) {
+    std::fprintf(stderr, "[b200-hevm] fatal: decode supports at most %d limbs\n", DEC_MAXW - 1);
+    std::abort();
+  }
+  k_dec_compose<<<ew_grid(n), 256, 0, s>>>(T, logN, l, coeff, D, 1.0 / scale, work);
+  POST_LAUNCH();
+  int gap = (int)(n >> 1);
+  for (size_t m = 1; m < n; m <<= 1, gap >>= 1) {
+    k_fft_ct<<<ew_grid(n / 2), 256, 0, s>>>(logN, work, E.fwd_root, (int)m, gap);
+    POST_LAUNCH();
+  }
+  k_dec_gather<<<ew_grid(n / 2), 256, 0, s>>>(logN, work, E.slot_index, out);
+  POST_LAUNCH();
+}

@@ -1,0 +1,69 @@
+// Launch interface of the sm_100a kernels (kernels.cu) used by the HEVM host code (vm.cu).
+#pragma once
+#include "ops.hpp"
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+
+#define CUDA_CHECK(x)                                                                                                  \
+  do {                                                                                                                 \
+    cudaError_t e_ = (x);                                                                                              \
+    if (e_ != cudaSuccess) {                                                                                           \
+      std::fprintf(stderr, "[b200-hevm] fatal: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e_), __FILE__, __LINE__, \
+                   cudaGetErrorString(e_));                                                                            \
+      std::abort();                                                                                                    \
+    }                                                                                                                  \
+  } while (0)
+
+// counts every kernel this library launches (bench.py reports it as gpu_launches)
+extern unsigned long long g_launch_count;
+
+struct GpuLauncher {
+  cudaStream_t stream = nullptr;
+  template <int LD> void intt_B(const ArgsInttB &a, int njobs);
+  void intt_A(const ArgsInttA &a, int njobs);
+  template <int PRE> void fwd_A(const ArgsFwdA &a, int njobs);
+  template <int EPI> void fwd_B(const ArgsFwdB &a, int njobs);
+};
+
+// ---- element-wise ciphertext kernels (SEAL add/negate/add_plain/multiply_plain, limb drop) ----
+enum { EW_ADD = 0, EW_NEG = 1, EW_ADDP = 2, EW_MULP = 3, EW_COPY = 4 };
+// out[K][i][n] = op(a[K][i][n], b...) for K<2, i<l ; ct poly pitch = `pitch` words; plaintext `p` is [l][N]
+void launch_elementwise(cudaStream_t s, int op, const NttTables *T, int logN, u64 *out, const u64 *a, const u64 *b,
+                        const u64 *p, size_t pitch, int l);
+
+// ---- samplers (specification shared with the oracle: oracle/ckks_oracle.hpp "sampler") ----
+void launch_sample_ternary(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream);
+void launch_sample_cbd(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream);
+void launch_sample_uniform(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream_base);
+
+// ---- key generation / encryption helpers ----
+// c0[i] = -(c1[i]*sk[i] + e[i]); if (digit >= 0 && i == digit) c0[i] += (p mod q_i) * newkey[i]
+void launch_ksk_finish(cudaStream_t s, const NttTables *T, int logN, int L, u64 *c0, const u64 *c1, const u64 *sk,
+                       const u64 *e, const u64 *newkey, int digit);
+void launch_square(cudaStream_t s, const NttTables *T, int logN, int L, u64 *out, const u64 *in);
+void launch_galois_gather(cudaStream_t s, int logN, int L, u64 *out, const u64 *in, u32 elt);
+// c[j][i] = u[i]*pk[j][i] + e[j][i]   (limbs i < nl; pk poly pitch pk_pitch; c/e poly pitch nl*N)
+void launch_enc_combine(cudaStream_t s, const NttTables *T, int logN, int nl, u64 *c, const u64 *u, const u64 *pk,
+                        size_t pk_pitch, const u64 *e);
+// pt[i] = c0[i] + c1[i]*sk[i]
+void launch_decrypt(cudaStream_t s, const NttTables *T, int logN, int l, u64 *pt, const u64 *ct, size_t pitch, const u64 *sk);
+
+// ---- CKKS encoder (fp64; SEAL CKKSEncoder::encode_internal / decode_internal) ----
+struct EncoderTables {
+  const u32 *slot_index;   // [N]  matrix_reps_index_map
+  const double2 *fwd_root; // [N]  root_powers_
+  const double2 *inv_root; // [N]  inv_root_powers_
+};
+// values (device, `len` doubles, tiled to N/2 slots) -> coefficient-form RNS limbs [level][N] (not yet NTT'd)
+void launch_encode(cudaStream_t s, const NttTables *T, const EncoderTables &E, int logN, const double *vals, int len,
+                   int level, double scale, double2 *work, unsigned long long *maxbits, u64 *out);
+struct DecodeTables { // per level, device
+  const u64 *punct;   // [l][l]  Q/q_j
+  const u64 *invp;    // [l]     (Q/q_j)^-1 mod q_j
+  const u64 *Q;       // [l]
+  const u64 *half;    // [l]     (Q+1)/2
+};
+// coeff: [l][N] coefficient-form canonical limbs -> out: N/2 doubles (device)
+void launch_decode(cudaStream_t s, const NttTables *T, const EncoderTables &E, const DecodeTables &D, int logN, int l,
+                   const u64 *coeff, double scale, double2 *work, double *out);

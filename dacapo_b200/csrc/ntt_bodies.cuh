@@ -55,7 +55,7 @@ template <int LD> HD void body_intt_B(const ArgsInttB &a, int job, LaneB8 *st, u
       const u64 *c0 = a.c0 + (size_t)limb * N;
       u64 *pc0 = a.pc0 + (size_t)limb * N;
       u64 v[8];
-#pragma unroll
+_Pragma("unroll")
       for (int e = 0; e < 8; e++) {
         u32 si = galois_src_index((u32)(base + e), a.elt, T.logN);
         S.x[e] = ldg_stream(src + si);
@@ -70,14 +70,14 @@ template <int LD> HD void body_intt_B(const ArgsInttB &a, int job, LaneB8 *st, u
       ldg_stream4(src + base + 4, u[4], u[5], u[6], u[7]);
       ldg_stream4(b + base, v[0], v[1], v[2], v[3]);
       ldg_stream4(b + base + 4, v[4], v[5], v[6], v[7]);
-#pragma unroll
+_Pragma("unroll")
       for (int e = 0; e < 8; e++) S.x[e] = mulmod(u[e], v[e], m);
     }
   });
   warp_invB8_regs(st, sm, r, T.itw + (size_t)p * N, m.q);
   u64 *dst = a.dst + (size_t)limb * N + r * 256;
   FOR_LANES(S, st, {
-#pragma unroll
+_Pragma("unroll")
     for (int e = 0; e < 8; e++) dst[idxH(lane, e)] = S.x[e];
   });
 }
@@ -103,7 +103,7 @@ HD void body_intt_A(const ArgsInttA &a, int job, LaneA *st, u64 *sm) {
   const u64 half = q >> 1;
   LANE_DECL;
   FOR_LANES(S, st, {
-#pragma unroll
+_Pragma("unroll")
     for (int e = 0; e < 16; e++) {
       u64 v = S.x[e];
       if (a.round) v = csub(v + half, q);
@@ -153,7 +153,7 @@ template <int PRE> HD void body_fwd_A(const ArgsFwdA &a, int job, LaneA *st, u64
   if (PRE == PRE_ROUND) fix = m.q - reduce64(T.mod[ps].q >> 1, m);
   LANE_DECL;
   FOR_LANES(S, st, {
-#pragma unroll
+_Pragma("unroll")
     for (int e = 0; e < 16; e++) {
       u64 v = ldg_stream(src + ((size_t)rowR(lane, e) << LOGB8) + (lane & 3));
       if (PRE != PRE_NONE && ps > pd) v = reduce64(v, m);
@@ -201,7 +201,7 @@ template <int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, LaneB8 *st, u6
     FOR_LANES(S, st, {
       (void)S;
       const int li = (NLANE_STATE == 1) ? 0 : lane;
-#pragma unroll
+_Pragma("unroll")
       for (int e = 0; e < 8; e++) lo0[li][e] = hi0[li][e] = lo1[li][e] = hi1[li][e] = 0;
     });
     for (int J = 0; J < a.l; J++) {
@@ -215,7 +215,7 @@ template <int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, LaneB8 *st, u6
             ldg_stream4(t + 4, S.x[4], S.x[5], S.x[6], S.x[7]);
           } else if (a.ld == LD_GALOIS) {
             const u64 *t = a.tgt + (size_t)J * N;
-#pragma unroll
+_Pragma("unroll")
             for (int e = 0; e < 8; e++) S.x[e] = ldg_stream(t + galois_src_index((u32)(base + e), a.elt, T.logN));
           } else {
             const u64 *t = a.tgt + (size_t)J * N + base;
@@ -225,14 +225,14 @@ template <int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, LaneB8 *st, u6
             ldg_stream4(t + 4, u[4], u[5], u[6], u[7]);
             ldg_stream4(t2, v[0], v[1], v[2], v[3]);
             ldg_stream4(t2 + 4, v[4], v[5], v[6], v[7]);
-#pragma unroll
+_Pragma("unroll")
             for (int e = 0; e < 8; e++) S.x[e] = mulmod(u[e], v[e], m);
           }
         });
       } else {
         const u64 *src = a.src + ((size_t)Iidx * a.l + J) * N + r * 256;
         FOR_LANES(S, st, {
-#pragma unroll
+_Pragma("unroll")
           for (int e = 0; e < 8; e++) S.x[e] = ldg_stream(src + idxH(lane, e));
         });
         warp_fwdB8_regs(st, sm, r, tw, m.q);
@@ -246,7 +246,7 @@ template <int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, LaneB8 *st, u6
         ldg_stream4(k0 + lane * 8 + 4, ka[4], ka[5], ka[6], ka[7]);
         ldg_stream4(k1 + lane * 8, kb[0], kb[1], kb[2], kb[3]);
         ldg_stream4(k1 + lane * 8 + 4, kb[4], kb[5], kb[6], kb[7]);
-#pragma unroll
+_Pragma("unroll")
         for (int e = 0; e < 8; e++) {
           mac128(lo0[li][e], hi0[li][e], S.x[e], ka[e]);
           mac128(lo1[li][e], hi1[li][e], S.x[e], kb[e]);
@@ -259,7 +259,7 @@ template <int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, LaneB8 *st, u6
       (void)S;
       const int li = (NLANE_STATE == 1) ? 0 : lane;
       u64 v0[8], v1[8];
-#pragma unroll
+_Pragma("unroll")
       for (int e = 0; e < 8; e++) {
         v0[e] = reduce128(lo0[li][e], hi0[li][e], m);
         v1[e] = reduce128(lo1[li][e], hi1[li][e], m);
@@ -279,14 +279,14 @@ template <int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, LaneB8 *st, u6
     const u64 q = m.q, q2 = 2 * m.q;
     const u64 *src = a.src + (size_t)d * N + r * 256;
     FOR_LANES(S, st, {
-#pragma unroll
+_Pragma("unroll")
       for (int e = 0; e < 8; e++) S.x[e] = ldg_stream(src + idxH(lane, e));
     });
     warp_fwdB8_regs(st, sm, r, T.tw + (size_t)p * N, q);
     u64 *o = a.dst + (size_t)d * N + r * 256;
     FOR_LANES(S, st, {
       u64 v[8];
-#pragma unroll
+_Pragma("unroll")
       for (int e = 0; e < 8; e++) v[e] = csub(csub(S.x[e], q2), q);
       stg4(o + lane * 8, v[0], v[1], v[2], v[3]);
       stg4(o + lane * 8 + 4, v[4], v[5], v[6], v[7]);
@@ -305,10 +305,10 @@ template <int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, LaneB8 *st, u6
       const u64 *src = a.src + ((size_t)K * a.l + i) * N + r * 256;
       FOR_LANES(S, st, {
         if (K == 1) {
-#pragma unroll
+_Pragma("unroll")
           for (int e = 0; e < 8; e++) S.z[e] = S.x[e];
         }
-#pragma unroll
+_Pragma("unroll")
         for (int e = 0; e < 8; e++) S.x[e] = ldg_stream(src + idxH(lane, e));
       });
       warp_fwdB8_regs(st, sm, r, T.tw + (size_t)i * N, q);
@@ -332,7 +332,7 @@ template <int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, LaneB8 *st, u6
       ldg_stream4(pb0 + 4, b0[4], b0[5], b0[6], b0[7]);
       ldg_stream4(pb1, b1[0], b1[1], b1[2], b1[3]);
       ldg_stream4(pb1 + 4, b1[4], b1[5], b1[6], b1[7]);
-#pragma unroll
+_Pragma("unroll")
       for (int e = 0; e < 8; e++) {
         u64 u0 = csub(csub(S.z[e], q2), q), u1 = csub(csub(S.x[e], q2), q);
         u64 t0 = shoup_mul(c0[e] + q - u0, inv, q);
@@ -359,7 +359,7 @@ template <int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, LaneB8 *st, u6
     const u64 q = m.q, q2 = 2 * m.q;
     const u64 *src = a.src + (size_t)d * N + r * 256;
     FOR_LANES(S, st, {
-#pragma unroll
+_Pragma("unroll")
       for (int e = 0; e < 8; e++) S.x[e] = ldg_stream(src + idxH(lane, e));
     });
     warp_fwdB8_regs(st, sm, r, T.tw + (size_t)i * N, q);
@@ -373,7 +373,7 @@ template <int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, LaneB8 *st, u6
                                             : a.acc + ((size_t)K * (a.l + 1) + i) * N + r * 256 + b;
       ldg_stream4(cin, c[0], c[1], c[2], c[3]);
       ldg_stream4(cin + 4, c[4], c[5], c[6], c[7]);
-#pragma unroll
+_Pragma("unroll")
       for (int e = 0; e < 8; e++) {
         u64 u = csub(csub(S.x[e], q2), q);      // canonical NTT of the rounding term
         v[e] = shoup_mul(c[e] + q - u, inv, q); // (c - u) * plast^-1 mod q
@@ -383,7 +383,7 @@ template <int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, LaneB8 *st, u6
         u64 w[8];
         ldg_stream4(p0, w[0], w[1], w[2], w[3]);
         ldg_stream4(p0 + 4, w[4], w[5], w[6], w[7]);
-#pragma unroll
+_Pragma("unroll")
         for (int e = 0; e < 8; e++) v[e] = csub(v[e] + w[e], q);
       }
       stg4(o + b, v[0], v[1], v[2], v[3]);

@@ -97,23 +97,23 @@ HD int idxR(int lane, int e) { return e * 32 + lane; }
 HD int idxS(int lane, int e) { return (lane >> 2) * 64 + e * 4 + (lane & 3); }
 
 HD void fwdA_stages_R(u64 (&x)[16], const Tw *tw, u64 q, u64 q2) {
-#pragma unroll
+_Pragma("unroll")
   for (int s = 0; s < 4; s++) {
     const int half = 8 >> s;
     Tw t[8];
-#pragma unroll
+_Pragma("unroll")
     for (int g = 0; g < (1 << s); g++) t[g] = ldtw(tw + (1 << s) + g);
-#pragma unroll
+_Pragma("unroll")
     for (int e = 0; e < 16; e++)
       if (!(e & half)) ct_bfly(x[e], x[e + half], t[e >> (4 - s)], q, q2);
   }
 }
 HD void fwdA_stages_S(u64 (&x)[16], int lane, const Tw *tw, u64 q, u64 q2) {
   const int rbase = (lane >> 2) * 16;
-#pragma unroll
+_Pragma("unroll")
   for (int s = 4; s < 7; s++) {
     const int half = 1 << (6 - s);
-#pragma unroll
+_Pragma("unroll")
     for (int e = 0; e < 16; e++)
       if (!(e & half)) {
         Tw t = ldtw(tw + (1 << s) + ((rbase + e) >> (7 - s)));
@@ -124,10 +124,10 @@ HD void fwdA_stages_S(u64 (&x)[16], int lane, const Tw *tw, u64 q, u64 q2) {
 // inverse, layout S: row gaps 1,2,4  (m = 64,32,16 groups)
 HD void invA_stages_S(u64 (&x)[16], int lane, const Tw *itw, u64 q, u64 q2) {
   const int rbase = (lane >> 2) * 16;
-#pragma unroll
+_Pragma("unroll")
   for (int j = 0; j < 3; j++) {
     const int half = 1 << j;
-#pragma unroll
+_Pragma("unroll")
     for (int e = 0; e < 16; e++)
       if (!(e & half)) {
         Tw t = ldtw(itw + (64 >> j) + ((rbase + e) >> (j + 1)));
@@ -137,17 +137,17 @@ HD void invA_stages_S(u64 (&x)[16], int lane, const Tw *itw, u64 q, u64 q2) {
 }
 // inverse, layout R: row gaps 8,16,32,64 (m = 8,4,2,1); the last stage applies N^-1; output canonical
 HD void invA_stages_R(u64 (&x)[16], const Tw *itw, u64 q, u64 q2, Tw invn, Tw invn_w) {
-#pragma unroll
+_Pragma("unroll")
   for (int j = 3; j < 6; j++) {
     const int half = 1 << (j - 3);
     Tw t[8];
-#pragma unroll
+_Pragma("unroll")
     for (int g = 0; g < (64 >> j); g++) t[g] = ldtw(itw + (64 >> j) + g);
-#pragma unroll
+_Pragma("unroll")
     for (int e = 0; e < 16; e++)
       if (!(e & half)) gs_bfly(x[e], x[e + half], t[e >> (j - 2)], q, q2);
   }
-#pragma unroll
+_Pragma("unroll")
   for (int e = 0; e < 8; e++) {
     u64 u = x[e], v = x[e + 8];
     x[e] = csub(shoup_lazy(u + v, invn, q), q);
@@ -169,23 +169,23 @@ HD int idxM8(int lane, int e) { return ((((lane >> 2) & 3) * 2 + (lane >> 4)) <<
 HD int idxC8(int lane, int e) { return lane * 8 + e; }
 
 HD void fwdB8_stages_H(u64 (&x)[8], int r, const Tw *tw, u64 q, u64 q2) {
-#pragma unroll
+_Pragma("unroll")
   for (int k = 0; k < 3; k++) {
     const int half = 4 >> k;
     Tw t[4];
-#pragma unroll
+_Pragma("unroll")
     for (int g = 0; g < (1 << k); g++) t[g] = ldtw(tw + (128 << k) + (r << k) + g);
-#pragma unroll
+_Pragma("unroll")
     for (int e = 0; e < 8; e++)
       if (!(e & half)) ct_bfly(x[e], x[e + half], t[e >> (3 - k)], q, q2);
   }
 }
 HD void fwdB8_stages_M(u64 (&x)[8], int lane, int r, const Tw *tw, u64 q, u64 q2) {
   const int base = idxM8(lane, 0);
-#pragma unroll
+_Pragma("unroll")
   for (int k = 3; k < 6; k++) {
     const int half = 4 >> (k - 3);
-#pragma unroll
+_Pragma("unroll")
     for (int e = 0; e < 8; e++)
       if (!(e & half)) {
         Tw t = ldtw(tw + (128 << k) + (r << k) + ((base + e * 4) >> (8 - k)));
@@ -195,10 +195,10 @@ HD void fwdB8_stages_M(u64 (&x)[8], int lane, int r, const Tw *tw, u64 q, u64 q2
 }
 HD void fwdB8_stages_C(u64 (&x)[8], int lane, int r, const Tw *tw, u64 q, u64 q2) {
   const int base = lane * 8;
-#pragma unroll
+_Pragma("unroll")
   for (int k = 6; k < 8; k++) {
     const int half = 2 >> (k - 6);
-#pragma unroll
+_Pragma("unroll")
     for (int e = 0; e < 8; e++)
       if (!(e & half)) {
         Tw t = ldtw(tw + (128 << k) + (r << k) + ((base + e) >> (8 - k)));
@@ -209,10 +209,10 @@ HD void fwdB8_stages_C(u64 (&x)[8], int lane, int r, const Tw *tw, u64 q, u64 q2
 // inverse: gap 2^j, m_loc = 128>>j, twiddle itw[128*m_loc + r*m_loc + (idx >> (j+1))]
 HD void invB8_stages_C(u64 (&x)[8], int lane, int r, const Tw *itw, u64 q, u64 q2) {
   const int base = lane * 8;
-#pragma unroll
+_Pragma("unroll")
   for (int j = 0; j < 2; j++) {
     const int half = 1 << j, ml = 128 >> j;
-#pragma unroll
+_Pragma("unroll")
     for (int e = 0; e < 8; e++)
       if (!(e & half)) {
         Tw t = ldtw(itw + 128 * ml + r * ml + ((base + e) >> (j + 1)));
@@ -222,10 +222,10 @@ HD void invB8_stages_C(u64 (&x)[8], int lane, int r, const Tw *itw, u64 q, u64 q
 }
 HD void invB8_stages_M(u64 (&x)[8], int lane, int r, const Tw *itw, u64 q, u64 q2) {
   const int base = idxM8(lane, 0);
-#pragma unroll
+_Pragma("unroll")
   for (int j = 2; j < 5; j++) {
     const int half = 1 << (j - 2), ml = 128 >> j;
-#pragma unroll
+_Pragma("unroll")
     for (int e = 0; e < 8; e++)
       if (!(e & half)) {
         Tw t = ldtw(itw + 128 * ml + r * ml + ((base + e * 4) >> (j + 1)));
@@ -234,13 +234,13 @@ HD void invB8_stages_M(u64 (&x)[8], int lane, int r, const Tw *itw, u64 q, u64 q
   }
 }
 HD void invB8_stages_H(u64 (&x)[8], int r, const Tw *itw, u64 q, u64 q2) {
-#pragma unroll
+_Pragma("unroll")
   for (int j = 5; j < 8; j++) {
     const int half = 1 << (j - 5), ml = 128 >> j;
     Tw t[4];
-#pragma unroll
+_Pragma("unroll")
     for (int g = 0; g < ml; g++) t[g] = ldtw(itw + 128 * ml + r * ml + g);
-#pragma unroll
+_Pragma("unroll")
     for (int e = 0; e < 8; e++)
       if (!(e & half)) gs_bfly(x[e], x[e + half], t[e >> (j - 4)], q, q2);
   }
@@ -268,14 +268,14 @@ HD void warp_fwdA_from_regs(LaneA *st, u64 *sm, u64 *dst, int c0, const Tw *tw, 
   LANE_DECL;
   FOR_LANES(S, st, {
     fwdA_stages_R(S.y, tw, q, q2);
-#pragma unroll
+_Pragma("unroll")
     for (int e = 0; e < 16; e++) sm[padx(idxR(lane, e))] = S.y[e];
   });
   FOR_LANES(S, st, {
-#pragma unroll
+_Pragma("unroll")
     for (int e = 0; e < 16; e++) S.y[e] = sm[padx(idxS(lane, e))];
     fwdA_stages_S(S.y, lane, tw, q, q2);
-#pragma unroll
+_Pragma("unroll")
     for (int e = 0; e < 16; e++) dst[((size_t)rowS(lane, e) << LOGB) + c0 + (lane & 3)] = S.y[e];
   });
 }
@@ -286,14 +286,14 @@ HD void warp_invA_to_regs(LaneA *st, u64 *sm, const u64 *src, int c0, const Tw *
   const u64 q2 = 2 * q;
   LANE_DECL;
   FOR_LANES(S, st, {
-#pragma unroll
+_Pragma("unroll")
     for (int e = 0; e < 16; e++) S.x[e] = ldg_stream(src + ((size_t)rowS(lane, e) << LOGB) + c0 + (lane & 3));
     invA_stages_S(S.x, lane, itw, q, q2);
-#pragma unroll
+_Pragma("unroll")
     for (int e = 0; e < 16; e++) sm[padx(idxS(lane, e))] = S.x[e];
   });
   FOR_LANES(S, st, {
-#pragma unroll
+_Pragma("unroll")
     for (int e = 0; e < 16; e++) S.x[e] = sm[padx(idxR(lane, e))];
     invA_stages_R(S.x, itw, q, q2, invn, invn_w);
   });
@@ -305,18 +305,18 @@ HD void warp_fwdB8_regs(LaneB8 *st, u64 *sm, int r, const Tw *tw, u64 q) {
   LANE_DECL;
   FOR_LANES(S, st, {
     fwdB8_stages_H(S.x, r, tw, q, q2);
-#pragma unroll
+_Pragma("unroll")
     for (int e = 0; e < 8; e++) sm[padx(idxH(lane, e))] = S.x[e];
   });
   FOR_LANES(S, st, {
-#pragma unroll
+_Pragma("unroll")
     for (int e = 0; e < 8; e++) S.x[e] = sm[padx(idxM8(lane, e))];
     fwdB8_stages_M(S.x, lane, r, tw, q, q2);
-#pragma unroll
+_Pragma("unroll")
     for (int e = 0; e < 8; e++) sm[padx(idxM8(lane, e))] = S.x[e];
   });
   FOR_LANES(S, st, {
-#pragma unroll
+_Pragma("unroll")
     for (int e = 0; e < 8; e++) S.x[e] = sm[padx(idxC8(lane, e))];
     fwdB8_stages_C(S.x, lane, r, tw, q, q2);
   });
@@ -327,18 +327,18 @@ HD void warp_invB8_regs(LaneB8 *st, u64 *sm, int r, const Tw *itw, u64 q) {
   LANE_DECL;
   FOR_LANES(S, st, {
     invB8_stages_C(S.x, lane, r, itw, q, q2);
-#pragma unroll
+_Pragma("unroll")
     for (int e = 0; e < 8; e++) sm[padx(idxC8(lane, e))] = S.x[e];
   });
   FOR_LANES(S, st, {
-#pragma unroll
+_Pragma("unroll")
     for (int e = 0; e < 8; e++) S.x[e] = sm[padx(idxM8(lane, e))];
     invB8_stages_M(S.x, lane, r, itw, q, q2);
-#pragma unroll
+_Pragma("unroll")
     for (int e = 0; e < 8; e++) sm[padx(idxM8(lane, e))] = S.x[e];
   });
   FOR_LANES(S, st, {
-#pragma unroll
+_Pragma("unroll")
     for (int e = 0; e < 8; e++) S.x[e] = sm[padx(idxH(lane, e))];
     invB8_stages_H(S.x, r, itw, q, q2);
   });

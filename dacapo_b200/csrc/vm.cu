@@ -1,0 +1,704 @@
+// libB200_HEVM.so -- the HEVM interpreter on B200 and its C ABI.
+//
+// Drop-in for the reference runtime (reference: lib/Runtime/SEAL_HEVM.cpp:15-504): same 18
+// exported symbols (include/hevm_abi.h), same .hevm / .cst files, same opcode semantics
+// including the wrapper quirks of SURVEY.md A.3.  Ciphertext / plaintext registers, the
+// secret / public / relinearisation / Galois keys and every table live in HBM for the life of
+// the VM; host<->device traffic happens only in load/preprocess (constants), encrypt (input
+// slots) and decrypt (output slots) -- nothing crosses during run().
+//
+// There is no CPU execution path: without a CUDA device every entry point aborts.
+#include "host_params.hpp"
+#include "kernels.h"
+#include <cmath>
+#include <complex>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <map>
+#include <random>
+#include <string>
+#include <vector>
+
+namespace {
+
+[[noreturn]] void die(const char *msg) {
+  std::fprintf(stderr, "[b200-hevm] fatal: %s\n", msg);
+  std::abort();
+}
+
+// ---- on-disk formats ---------------------------------------------------------------------
+// HEVM container (reference: include/hecate/Support/HEVMHeader.h:9-34; writer EmitHEVM.cpp:31-119)
+#pragma pack(push, 1)
+struct HevmHead {
+  uint32_t magic, head_size;
+  uint64_t n_args, n_res;
+};
+struct HevmConfig {
+  uint64_t body_len, n_ops, n_ct, n_pt, init_level;
+};
+struct HevmOp {
+  uint16_t opcode, dst, lhs, rhs;
+};
+#pragma pack(pop)
+struct ParamFile { // <dir>/hevm_params.bin : ring geometry + key seed (own format; SURVEY 8b "Files consumed")
+  uint64_t magic, logN, L, bits, seed;
+};
+const uint64_t PARAM_MAGIC = 0x3030324D56454842ull;
+
+// sampler stream ids (specification shared with the oracle)
+inline u64 ksk_stream(u64 key_id, u64 digit, u64 kind, u64 limb) { return (((key_id * 64 + digit) * 2 + kind) * 64 + limb) + (16ull << 20); }
+inline u64 enc_stream(u64 counter, u64 which) { return (1ull << 40) + counter * 4 + which; }
+
+struct CtReg {
+  u64 *d = nullptr; // [2][L-1][N] (poly pitch fixed), NTT form
+  int level = 0;
+  double scale = 1.0;
+};
+struct PtReg {
+  u64 *d = nullptr; // [level][N]
+  int level = 0, cap = 0;
+  double scale = 1.0;
+};
+
+template <class T> T *dalloc(size_t n) {
+  T *p = nullptr;
+  CUDA_CHECK(cudaMalloc(&p, n * sizeof(T)));
+  return p;
+}
+template <class T> T *upload(const std::vector<T> &v) {
+  T *p = dalloc<T>(v.size());
+  CUDA_CHECK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return p;
+}
+
+struct DecTabs {
+  u64 *punct, *invp, *Q, *half;
+};
+
+struct VM {
+  hp::HostParams P;
+  int logN = 0, L = 0;
+  size_t N = 0, pitch = 0;
+  u64 seed = 0, enc_counter = 0;
+  cudaStream_t stream = nullptr;
+  GpuLauncher la;
+  HeOps<GpuLauncher> *ops = nullptr;
+  NttTables *dT = nullptr;
+  // encoder
+  EncoderTables E{};
+  double2 *d_work = nullptr;
+  unsigned long long *d_maxbits = nullptr;
+  double *d_vals = nullptr, *d_vals_in = nullptr;
+  std::map<int, DecTabs> dec;
+  // keys
+  u64 *d_sk = nullptr, *d_pk = nullptr, *d_relin = nullptr;
+  std::map<u64, u64 *> d_gal;
+  // temporaries
+  u64 *d_u = nullptr, *d_e = nullptr, *d_tmpct = nullptr, *d_coef = nullptr;
+  PtReg boot_pt;
+  // program
+  std::vector<std::vector<double>> consts;
+  HevmHead head{};
+  HevmConfig cfg{};
+  std::vector<HevmOp> prog;
+  std::vector<uint64_t> arg_scale, arg_level, res_scale, res_level, res_dst;
+  std::vector<CtReg> ct;
+  std::vector<PtReg> pt;
+  bool debug = false;
+  size_t bytes_allocated = 0;
+
+  // ---------------------------------------------------------------- setup
+  void init(const ParamFile &pf) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) die("no CUDA device visible: libB200_HEVM.so has no CPU path");
+    if (const char *e = std::getenv("HEVM_DEVICE")) CUDA_CHECK(cudaSetDevice(std::atoi(e)));
+    if (pf.logN != 15) die("this build supports N = 2^15 only (HEVM_LOGN=15); other ring sizes are planned (DESIGN.md)");
+    if (pf.L < 2 || pf.L > HEVM_MAXL) die("number of primes out of range");
+    logN = (int)pf.logN, L = (int)pf.L, N = (size_t)1 << logN, seed = pf.seed;
+    pitch = (size_t)(L - 1) * N;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    la.stream = stream;
+    P.build(logN, L, (int)pf.bits);
+    Tw *d_tw = upload(P.tw), *d_itw = upload(P.itw);
+    P.tab.tw = d_tw, P.tab.itw = d_itw;
+    dT = dalloc<NttTables>(1);
+    CUDA_CHECK(cudaMemcpy(dT, &P.tab, sizeof(NttTables), cudaMemcpyHostToDevice));
+    ops = new HeOps<GpuLauncher>(la, dT, logN, L);
+    ops->sc.carve(dalloc<u64>(Scratch::words(L, N)), L, N);
+    init_encoder();
+    d_u = dalloc<u64>((size_t)L * N);
+    d_e = dalloc<u64>((size_t)2 * L * N);
+    d_tmpct = dalloc<u64>((size_t)2 * L * N);
+    d_coef = dalloc<u64>((size_t)L * N);
+    keygen();
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+  }
+
+  // CKKSEncoder tables (SEAL ckks.cpp constructor): slot index map through powers of 3,
+  // complex 2N-th roots from the first octant (std::polar) + 8-fold symmetry.
+  void init_encoder() {
+    const size_t m = 2 * N, slots = N / 2;
+    std::vector<u32> idx(N);
+    u64 pos = 1;
+    for (size_t i = 0; i < slots; i++, pos = (pos * 3) & (m - 1)) {
+      idx[i] = hp::revbits((u32)((pos - 1) >> 1), logN);
+      idx[slots + i] = hp::revbits((u32)((m - pos - 1) >> 1), logN);
+    }
+    const double PI = 3.1415926535897932384626433832795028842;
+    std::vector<std::complex<double>> oct(m / 8 + 1);
+    for (size_t i = 0; i <= m / 8; i++) oct[i] = std::polar<double>(1.0, 2 * PI * (double)i / (double)m);
+    // ComplexRoots::get_root: first octant table + 8-fold symmetry (same case order as SEAL's util/croots.cpp)
+    std::function<std::complex<double>(size_t)> root = [&](size_t k) -> std::complex<double> {
+      k &= m - 1;
+      if (k <= m / 8) return oct[k];
+      if (k <= m / 4) return std::complex<double>(oct[m / 4 - k].imag(), oct[m / 4 - k].real());
+      if (k <= m / 2) return -std::conj(root(m / 2 - k));
+      if (k <= 3 * m / 4) return -root(k - m / 2);
+      return std::conj(root(m - k));
+    };
+    std::vector<double2> fr(N), ir(N);
+    fr[0] = ir[0] = make_double2(0, 0);
+    for (size_t i = 1; i < N; i++) {
+      auto f = root(hp::revbits((u32)i, logN));
+      auto b = std::conj(root((size_t)hp::revbits((u32)(i - 1), logN) + 1));
+      fr[i] = make_double2(f.real(), f.imag());
+      ir[i] = make_double2(b.real(), b.imag());
+    }
+    E.slot_index = upload(idx);
+    E.fwd_root = upload(fr);
+    E.inv_root = upload(ir);
+    d_work = dalloc<double2>(N);
+    d_maxbits = dalloc<unsigned long long>(1);
+    d_vals = dalloc<double>(slots);
+    d_vals_in = dalloc<double>(slots);
+  }
+
+  // per-level CRT tables for decode (SEAL RNSBase punctured products; multi-precision, little endian)
+  const DecTabs &dec_tabs(int l) {
+    auto it = dec.find(l);
+    if (it != dec.end()) return it->second;
+    auto mulw = [](std::vector<u64> &a, u64 w) {
+      u64 c = 0;
+      for (auto &x : a) {
+        unsigned __int128 p = (unsigned __int128)x * w + c;
+        x = (u64)p, c = (u64)(p >> 64);
+      }
+    };
+    std::vector<u64> Q(l, 0), punct((size_t)l * l, 0), invp(l), half(l);
+    Q[0] = 1;
+    for (int j = 0; j < l; j++) mulw(Q, P.q[j]);
+    for (int j = 0; j < l; j++) {
+      std::vector<u64> a(l, 0);
+      a[0] = 1;
+      u64 r = 1;
+      for (int k = 0; k < l; k++)
+        if (k != j) mulw(a, P.q[k]), r = hp::mul(r, P.q[k] % P.q[j], P.q[j]);
+      std::copy(a.begin(), a.end(), punct.begin() + (size_t)j * l);
+      invp[j] = hp::inv(r, P.q[j]);
+    }
+    { // (Q+1) >> 1
+      std::vector<u64> t(Q);
+      u64 c = 1;
+      for (int k = 0; k < l && c; k++) c = (++t[k] == 0);
+      for (int k = 0; k < l; k++) half[k] = (t[k] >> 1) | ((k + 1 < l ? t[k + 1] : c) << 63);
+    }
+    DecTabs d{upload(punct), upload(invp), upload(Q), upload(half)};
+    return dec[l] = d;
+  }
+
+  // ---------------------------------------------------------------- keys (on device, from the seed)
+  void enc_zero_sym(u64 a_stream_base, u64 e_stream, u64 *c0, u64 *c1, const u64 *newkey, int digit) {
+    launch_sample_uniform(stream, dT, logN, c1, L, seed, a_stream_base); // a: sampled directly in NTT form
+    launch_sample_cbd(stream, dT, logN, d_e, L, seed, e_stream);
+    ops->ntt_fwd(d_e, d_e, L, 0, 1);
+    launch_ksk_finish(stream, dT, logN, L, c0, c1, d_sk, d_e, newkey, digit);
+  }
+  u64 *make_ksk(u64 key_id, const u64 *newkey) {
+    u64 *key = dalloc<u64>((size_t)(L - 1) * 2 * L * N);
+    for (int J = 0; J < L - 1; J++) {
+      u64 *c0 = key + ((size_t)J * 2 + 0) * L * N, *c1 = key + ((size_t)J * 2 + 1) * L * N;
+      enc_zero_sym(ksk_stream(key_id, J, 0, 0), ksk_stream(key_id, J, 1, 0), c0, c1, newkey, J);
+    }
+    return key;
+  }
+  u64 galois_elt_from_step(int step) const {
+    const u64 m = 2 * N;
+    if (step == 0) return m - 1;
+    const u64 pos = (u64)std::abs(step);
+    if (pos >= N / 2) die("rotation step count too large");
+    u64 s = step < 0 ? N / 2 - pos : pos, elt = 1;
+    for (u64 i = 0; i < s; i++) elt = (elt * 3) & (m - 1);
+    return elt;
+  }
+  void keygen() {
+    d_sk = dalloc<u64>((size_t)L * N);
+    launch_sample_ternary(stream, dT, logN, d_sk, L, seed, 1ull << 20);
+    ops->ntt_fwd(d_sk, d_sk, L, 0, 1);
+    d_pk = dalloc<u64>((size_t)2 * L * N);
+    enc_zero_sym(2ull << 20, 3ull << 20, d_pk, d_pk + (size_t)L * N, nullptr, -1);
+    u64 *nk = dalloc<u64>((size_t)L * N);
+    launch_square(stream, dT, logN, L, nk, d_sk);
+    d_relin = make_ksk(0, nk);
+    // default Galois key set (SEAL GaloisTool::get_elts_all): conjugation + 3^(+-2^i)
+    const u64 m = 2 * N;
+    std::vector<u64> elts{m - 1};
+    u64 posp = 3, negp = 0;
+    for (u64 x = 1; x < m; x += 2)
+      if (((x * 3) & (m - 1)) == 1) {
+        negp = x;
+        break;
+      }
+    for (int i = 0; i < logN - 1; i++) {
+      elts.push_back(posp), posp = (posp * posp) & (m - 1);
+      elts.push_back(negp), negp = (negp * negp) & (m - 1);
+    }
+    for (u64 elt : elts) {
+      if (d_gal.count(elt)) continue;
+      launch_galois_gather(stream, logN, L, nk, d_sk, (u32)elt);
+      d_gal[elt] = make_ksk(1 + ((elt - 1) >> 1), nk);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    CUDA_CHECK(cudaFree(nk));
+  }
+
+  // ---------------------------------------------------------------- registers
+  CtReg &ctr(size_t r) {
+    if (r >= ct.size()) die("ciphertext register index out of range");
+    CtReg &c = ct[r];
+    if (!c.d) c.d = dalloc<u64>(2 * pitch);
+    return c;
+  }
+  PtReg &ptr(size_t r) {
+    if (r >= pt.size()) die("plaintext register index out of range");
+    return pt[r];
+  }
+  void pt_reserve(PtReg &p, int level) {
+    if (p.cap < level) {
+      if (p.d) CUDA_CHECK(cudaFree(p.d));
+      p.d = dalloc<u64>((size_t)level * N);
+      p.cap = level;
+    }
+  }
+  void resize_regs(size_t nct, size_t npt) {
+    for (auto &c : ct)
+      if (c.d) CUDA_CHECK(cudaFree(c.d));
+    for (auto &p : pt)
+      if (p.d) CUDA_CHECK(cudaFree(p.d));
+    ct.assign(nct, CtReg());
+    pt.assign(npt, PtReg());
+  }
+
+  // ---------------------------------------------------------------- encode / encrypt / decrypt
+  // SEAL_HEVM.cpp:256-267 : tile to N/2 slots, encode at 2^scale_bits, keep `level` limbs
+  void encode_internal(PtReg &dst, const double *d_src, int len, int64_t level, int64_t scale_bits) {
+    if (level < 1 || level > L - 1) die("encode: level out of range");
+    pt_reserve(dst, (int)level);
+    dst.level = (int)level;
+    dst.scale = std::pow(2.0, (double)scale_bits);
+    launch_encode(stream, dT, E, logN, d_src, len, (int)level, dst.scale, d_work, d_maxbits, dst.d);
+    ops->ntt_fwd(dst.d, dst.d, (int)level, 0, 1);
+  }
+  void stage_host_values(const double *h, size_t len) {
+    if (len == 0) die("empty value vector");
+    CUDA_CHECK(cudaMemcpyAsync(d_vals_in, h, std::min(len, N / 2) * sizeof(double), cudaMemcpyHostToDevice, stream));
+  }
+  // Encryptor::encrypt (public key): zero-encrypt on level+1 limbs, divide-and-round by the extra
+  // prime, add the plaintext.  Reference call sites SEAL_HEVM.cpp:333,444.
+  void encrypt_pt(const PtReg &p, CtReg &out) {
+    const int l = p.level, nl = l + 1;
+    const u64 counter = enc_counter++;
+    launch_sample_ternary(stream, dT, logN, d_u, nl, seed, enc_stream(counter, 0));
+    ops->ntt_fwd(d_u, d_u, nl, 0, 1);
+    for (int j = 0; j < 2; j++) {
+      u64 *e = d_e + (size_t)j * nl * N;
+      launch_sample_cbd(stream, dT, logN, e, nl, seed, enc_stream(counter, 1 + j));
+      ops->ntt_fwd(e, e, nl, 0, 1);
+    }
+    launch_enc_combine(stream, dT, logN, nl, d_tmpct, d_u, d_pk, (size_t)L * N, d_e);
+    ops->rescale(d_tmpct, (size_t)nl * N, out.d, pitch, nl);
+    launch_elementwise(stream, EW_ADDP, dT, logN, out.d, out.d, nullptr, p.d, pitch, l);
+    out.level = l;
+    out.scale = p.scale;
+  }
+  void decrypt_to_pt(const CtReg &c, PtReg &p) {
+    pt_reserve(p, c.level);
+    p.level = c.level;
+    p.scale = c.scale;
+    launch_decrypt(stream, dT, logN, c.level, p.d, c.d, pitch, d_sk);
+  }
+  void decode_pt(const PtReg &p, double *d_out) {
+    ops->ntt_inv(p.d, d_coef, p.level, 0, 1);
+    const DecTabs &t = dec_tabs(p.level);
+    DecodeTables D{t.punct, t.invp, t.Q, t.half};
+    launch_decode(stream, dT, E, D, logN, p.level, d_coef, p.scale, d_work, d_out);
+  }
+
+  // ---------------------------------------------------------------- the opcodes (SEAL_HEVM.cpp:269-334)
+  static std::vector<int> naf(int value) {
+    std::vector<int> res;
+    const bool sign = value < 0;
+    value = std::abs(value);
+    for (int i = 0; value; i++) {
+      int zi = (value & 1) ? 2 - (value & 3) : 0;
+      value = (value - zi) >> 1;
+      if (zi) res.push_back((sign ? -zi : zi) * (1 << i));
+    }
+    return res;
+  }
+  void rotate_steps(int steps, std::vector<int> &out) const { // Evaluator::rotate_internal
+    if (steps == 0) return;
+    if (d_gal.count(galois_elt_from_step(steps))) {
+      out.push_back(steps);
+      return;
+    }
+    auto terms = naf(steps);
+    if (terms.size() == 1) die("Galois key not present");
+    for (int t : terms)
+      if ((size_t)std::abs(t) != N / 2) rotate_steps(t, out);
+  }
+  void copy_ct(const CtReg &s, CtReg &d) {
+    if (s.d != d.d) launch_elementwise(stream, EW_COPY, dT, logN, d.d, s.d, nullptr, nullptr, pitch, s.level);
+    d.level = s.level, d.scale = s.scale;
+  }
+  void exec(const HevmOp &op) {
+    switch (op.opcode) {
+    case 1: { // rotate
+      CtReg &s = ctr(op.lhs), &d = ctr(op.dst);
+      if (s.level < 1) die("rotate: empty source register");
+      std::vector<int> steps;
+      rotate_steps((int16_t)op.rhs, steps);
+      if (steps.empty()) {
+        copy_ct(s, d);
+        break;
+      }
+      const u64 *cur = s.d;
+      for (int st : steps) {
+        const u64 elt = galois_elt_from_step(st);
+        ops->keyswitch(LD_GALOIS, cur, nullptr, d.d, pitch, s.level, d_gal.at(elt), (u32)elt);
+        cur = d.d;
+      }
+      d.level = s.level, d.scale = s.scale;
+      break;
+    }
+    case 2: { // negate
+      CtReg &s = ctr(op.lhs), &d = ctr(op.dst);
+      launch_elementwise(stream, EW_NEG, dT, logN, d.d, s.d, nullptr, nullptr, pitch, s.level);
+      d.level = s.level, d.scale = s.scale;
+      break;
+    }
+    case 3: { // rescale
+      CtReg &s = ctr(op.lhs), &d = ctr(op.dst);
+      if (s.level < 2) die("rescale: already at the last level");
+      ops->rescale(s.d, pitch, d.d, pitch, s.level);
+      const int l = s.level;
+      const double sc = s.scale / (double)P.q[l - 1];
+      d.level = l - 1, d.scale = sc;
+      break;
+    }
+    case 4: { // modswitch by downFactor limbs
+      const int down = (int16_t)op.rhs;
+      if (down <= 0) break; // reference: nothing happens (SEAL_HEVM.cpp:288-292)
+      CtReg &s = ctr(op.lhs), &d = ctr(op.dst);
+      if (s.level - down < 1) die("modswitch: already at the last level");
+      const int nl = s.level - down;
+      const double sc = s.scale;
+      if (s.d != d.d) launch_elementwise(stream, EW_COPY, dT, logN, d.d, s.d, nullptr, nullptr, pitch, nl);
+      d.level = nl, d.scale = sc;
+      break;
+    }
+    case 5: die("This VM does not support native upscale op");
+    case 6: { // addcc
+      CtReg &a = ctr(op.lhs), &b = ctr(op.rhs), &d = ctr(op.dst);
+      a.scale = b.scale; // SEAL_HEVM.cpp:301
+      if (a.level != b.level) die("addcc: level mismatch");
+      const int l = a.level;
+      const double sc = a.scale;
+      launch_elementwise(stream, EW_ADD, dT, logN, d.d, a.d, b.d, nullptr, pitch, l);
+      d.level = l, d.scale = sc;
+      break;
+    }
+    case 7: { // addcp
+      CtReg &a = ctr(op.lhs), &d = ctr(op.dst);
+      PtReg &p = ptr(op.rhs);
+      a.scale = p.scale; // SEAL_HEVM.cpp:308
+      if (a.level != p.level) die("addcp: level mismatch");
+      const int l = a.level;
+      const double sc = a.scale;
+      launch_elementwise(stream, EW_ADDP, dT, logN, d.d, a.d, nullptr, p.d, pitch, l);
+      d.level = l, d.scale = sc;
+      break;
+    }
+    case 8: { // mulcc = multiply + relinearize, one fused key-switch pipeline
+      CtReg &a = ctr(op.lhs), &b = ctr(op.rhs), &d = ctr(op.dst);
+      if (a.level != b.level || a.level < 1) die("mulcc: level mismatch");
+      const int l = a.level;
+      const double sc = a.scale * b.scale;
+      ops->keyswitch(LD_PRODUCT, a.d, b.d, d.d, pitch, l, d_relin, 0);
+      d.level = l, d.scale = sc;
+      break;
+    }
+    case 9: { // mulcp
+      CtReg &a = ctr(op.lhs), &d = ctr(op.dst);
+      PtReg &p = ptr(op.rhs);
+      if (a.level != p.level) die("mulcp: level mismatch");
+      const int l = a.level;
+      const double sc = a.scale * p.scale;
+      launch_elementwise(stream, EW_MULP, dT, logN, d.d, a.d, nullptr, p.d, pitch, l);
+      d.level = l, d.scale = sc;
+      break;
+    }
+    case 10: { // "bootstrap" = decrypt + re-encrypt at the target level, entirely on device
+      CtReg &s = ctr(op.lhs), &d = ctr(op.dst);
+      decrypt_to_pt(s, boot_pt);
+      decode_pt(boot_pt, d_vals);
+      const int64_t sb = (int64_t)std::log2(s.scale); // SEAL_HEVM.cpp:332 truncation
+      encode_internal(boot_pt, d_vals, (int)(N / 2), op.rhs, sb);
+      encrypt_pt(boot_pt, d);
+      break;
+    }
+    default: break; // 0 = encode (done in preprocess), 0xFFFF = tensor.empty placeholder
+    }
+  }
+};
+
+VM *V(void *h) { return static_cast<VM *>(h); }
+
+void read_params(const char *dir, ParamFile &pf) {
+  std::ifstream f(std::string(dir) + "/hevm_params.bin", std::ios::binary);
+  if (!f) die("cannot open <dir>/hevm_params.bin (call create_context first)");
+  f.read((char *)&pf, sizeof pf);
+  if (pf.magic != PARAM_MAGIC) die("bad hevm_params.bin");
+}
+
+} // namespace
+
+extern "C" {
+
+// ================= the reference's 18 symbols (include/hevm_abi.h) =========================
+void create_context(char *dir) {
+  ParamFile pf{};
+  pf.magic = PARAM_MAGIC;
+  const char *e;
+  pf.logN = (e = std::getenv("HEVM_LOGN")) ? std::strtoull(e, nullptr, 10) : 15;
+  pf.L = (e = std::getenv("HEVM_NUM_PRIMES")) ? std::strtoull(e, nullptr, 10) : 14;
+  pf.bits = (e = std::getenv("HEVM_PRIME_BITS")) ? std::strtoull(e, nullptr, 10) : 60;
+  if ((e = std::getenv("HEVM_SEED")))
+    pf.seed = std::strtoull(e, nullptr, 0);
+  else {
+    std::random_device rd;
+    pf.seed = ((uint64_t)rd() << 32) ^ rd();
+  }
+  std::ofstream f(std::string(dir) + "/hevm_params.bin", std::ios::binary);
+  if (!f) die("create_context: cannot write hevm_params.bin");
+  f.write((const char *)&pf, sizeof pf);
+}
+void *initFullVM(char *dir, bool /*device: always the GPU*/) {
+  ParamFile pf;
+  read_params(dir, pf);
+  auto vm = new VM();
+  vm->init(pf);
+  return vm;
+}
+void *initClientVM(char *dir) { return initFullVM(dir, true); }
+void *initServerVM(char *dir) { return initFullVM(dir, true); }
+
+void load(void *h, char *cst, char *hevm) {
+  VM *vm = V(h);
+  {
+    std::ifstream f(cst, std::ios::binary);
+    if (!f) die("cannot open constants file");
+    int64_t n = 0;
+    f.read((char *)&n, 8);
+    vm->consts.assign((size_t)n, {});
+    for (auto &c : vm->consts) {
+      int64_t len = 0;
+      f.read((char *)&len, 8);
+      c.resize((size_t)len);
+      f.read((char *)c.data(), len * 8);
+    }
+  }
+  std::ifstream f(hevm, std::ios::binary);
+  if (!f) die("cannot open hevm file");
+  f.read((char *)&vm->head, sizeof(HevmHead));
+  if (vm->head.magic != 0x4845564D) die("bad HEVM magic");
+  f.read((char *)&vm->cfg, sizeof(HevmConfig));
+  auto rd = [&](std::vector<uint64_t> &v, size_t n) {
+    v.resize(n);
+    f.read((char *)v.data(), n * 8);
+  };
+  rd(vm->arg_scale, vm->head.n_args), rd(vm->arg_level, vm->head.n_args);
+  rd(vm->res_scale, vm->head.n_res), rd(vm->res_level, vm->head.n_res), rd(vm->res_dst, vm->head.n_res);
+  vm->prog.resize(vm->cfg.n_ops);
+  f.read((char *)vm->prog.data(), vm->prog.size() * sizeof(HevmOp));
+  vm->resize_regs(vm->cfg.n_ct, vm->cfg.n_pt);
+}
+void loadClient(void *, void *) { die("client/server split is vestigial in the reference (SURVEY A.3); use initFullVM"); }
+
+void preprocess(void *h) { // SEAL_HEVM.cpp:242-254: encode every opcode-0 constant into its plaintext register
+  VM *vm = V(h);
+  static const double one = 1.0;
+  for (auto &op : vm->prog)
+    if (op.opcode == 0) {
+      const double *src = &one;
+      size_t len = 1;
+      if (op.lhs != 0xFFFF) {
+        if (op.lhs >= vm->consts.size()) die("encode: constant index out of range");
+        src = vm->consts[op.lhs].data(), len = vm->consts[op.lhs].size();
+      }
+      vm->stage_host_values(src, len);
+      vm->encode_internal(vm->ptr(op.dst), vm->d_vals_in, (int)std::min(len, vm->N / 2), op.rhs >> 10, op.rhs & 0x3FF);
+    }
+  CUDA_CHECK(cudaStreamSynchronize(vm->stream));
+}
+void encrypt(void *h, int64_t i, double *dat, int len) {
+  VM *vm = V(h);
+  if ((size_t)i >= vm->arg_level.size()) die("encrypt: argument index out of range");
+  vm->stage_host_values(dat, (size_t)len);
+  vm->encode_internal(vm->boot_pt, vm->d_vals_in, (int)std::min((size_t)len, vm->N / 2), (int64_t)vm->arg_level[i], (int64_t)vm->arg_scale[i]);
+  vm->encrypt_pt(vm->boot_pt, vm->ctr((size_t)i));
+  CUDA_CHECK(cudaStreamSynchronize(vm->stream));
+}
+void decrypt(void *h, int64_t i, double *dat) {
+  VM *vm = V(h);
+  CtReg &c = vm->ctr((size_t)i);
+  if (c.level < 1) die("decrypt: empty register");
+  vm->decrypt_to_pt(c, vm->boot_pt);
+  vm->decode_pt(vm->boot_pt, vm->d_vals);
+  CUDA_CHECK(cudaMemcpyAsync(dat, vm->d_vals, (vm->N / 2) * sizeof(double), cudaMemcpyDeviceToHost, vm->stream));
+  CUDA_CHECK(cudaStreamSynchronize(vm->stream));
+}
+void decrypt_result(void *h, int64_t i, double *dat) { decrypt(h, (int64_t)V(h)->res_dst.at((size_t)i), dat); }
+int64_t getResIdx(void *h, int64_t i) { return (int64_t)V(h)->res_dst.at((size_t)i); }
+void *getCtxt(void *h, int64_t id) { return &V(h)->ctr((size_t)id); }
+void run(void *h) { // SEAL_HEVM.cpp:336-401; returns only when the results are complete
+  VM *vm = V(h);
+  for (auto &op : vm->prog) vm->exec(op);
+  CUDA_CHECK(cudaStreamSynchronize(vm->stream));
+}
+int64_t getArgLen(void *h) { return (int64_t)V(h)->head.n_args; }
+int64_t getResLen(void *h) { return (int64_t)V(h)->head.n_res; }
+void setDebug(void *h, bool e) { V(h)->debug = e; }
+void setToGPU(void *, bool) {} // always resident on the GPU
+void printMem(void *h) {
+  if (!V(h)->debug) return;
+  size_t fr = 0, tot = 0;
+  CUDA_CHECK(cudaMemGetInfo(&fr, &tot));
+  std::printf("MemUsage: %.2fGB (%.1f%%)\n", (tot - fr) / 1e9, 100.0 * (tot - fr) / tot);
+}
+
+// ================= hevmx_* hooks (include/hevm_ext.h) =========================================
+int64_t hevmx_param(void *h, int what) {
+  VM *vm = V(h);
+  switch (what) {
+  case 0: return vm->logN;
+  case 1: return vm->L;
+  case 2: return (int64_t)vm->seed;
+  case 3: return (int64_t)vm->ct.size();
+  case 4: return (int64_t)vm->pt.size();
+  case 5: return (int64_t)vm->d_gal.size();
+  case 6: return (int64_t)g_launch_count;
+  }
+  return -1;
+}
+void hevmx_primes(void *h, uint64_t *out) {
+  for (int i = 0; i < V(h)->L; i++) out[i] = V(h)->P.q[i];
+}
+void hevmx_roots(void *h, uint64_t *out) {
+  for (int i = 0; i < V(h)->L; i++) out[i] = V(h)->P.psi[i];
+}
+void hevmx_resize(void *h, int64_t nct, int64_t npt) { V(h)->resize_regs((size_t)nct, (size_t)npt); }
+void hevmx_ct_info(void *h, int64_t r, int64_t *level, double *scale) {
+  CtReg &c = V(h)->ctr((size_t)r);
+  *level = c.level, *scale = c.scale;
+}
+void hevmx_ct_read(void *h, int64_t r, uint64_t *out) {
+  VM *vm = V(h);
+  CtReg &c = vm->ctr((size_t)r);
+  CUDA_CHECK(cudaStreamSynchronize(vm->stream));
+  const size_t w = (size_t)c.level * vm->N;
+  for (int K = 0; K < 2; K++) CUDA_CHECK(cudaMemcpy(out + K * w, c.d + K * vm->pitch, w * 8, cudaMemcpyDeviceToHost));
+}
+void hevmx_ct_write(void *h, int64_t r, const uint64_t *in, int64_t level, double scale) {
+  VM *vm = V(h);
+  CtReg &c = vm->ctr((size_t)r);
+  if (level < 1 || level > vm->L - 1) die("ct_write: level out of range");
+  CUDA_CHECK(cudaStreamSynchronize(vm->stream));
+  const size_t w = (size_t)level * vm->N;
+  for (int K = 0; K < 2; K++) CUDA_CHECK(cudaMemcpy(c.d + K * vm->pitch, in + K * w, w * 8, cudaMemcpyHostToDevice));
+  c.level = (int)level, c.scale = scale;
+}
+void hevmx_pt_info(void *h, int64_t r, int64_t *level, double *scale) {
+  PtReg &p = V(h)->ptr((size_t)r);
+  *level = p.level, *scale = p.scale;
+}
+void hevmx_pt_read(void *h, int64_t r, uint64_t *out) {
+  VM *vm = V(h);
+  PtReg &p = vm->ptr((size_t)r);
+  CUDA_CHECK(cudaStreamSynchronize(vm->stream));
+  CUDA_CHECK(cudaMemcpy(out, p.d, (size_t)p.level * vm->N * 8, cudaMemcpyDeviceToHost));
+}
+void hevmx_pt_write(void *h, int64_t r, const uint64_t *in, int64_t level, double scale) {
+  VM *vm = V(h);
+  PtReg &p = vm->ptr((size_t)r);
+  CUDA_CHECK(cudaStreamSynchronize(vm->stream));
+  vm->pt_reserve(p, (int)level);
+  CUDA_CHECK(cudaMemcpy(p.d, in, (size_t)level * vm->N * 8, cudaMemcpyHostToDevice));
+  p.level = (int)level, p.scale = scale;
+}
+void hevmx_exec(void *h, int64_t opcode, int64_t dst, int64_t lhs, int64_t rhs) {
+  HevmOp op{(uint16_t)opcode, (uint16_t)dst, (uint16_t)lhs, (uint16_t)rhs};
+  V(h)->exec(op);
+}
+void hevmx_sync(void *h) { CUDA_CHECK(cudaStreamSynchronize(V(h)->stream)); }
+void hevmx_ntt(void *h, uint64_t *data, int64_t prime_idx, int64_t count, int inverse) {
+  VM *vm = V(h);
+  const size_t w = (size_t)count * vm->N;
+  u64 *d = dalloc<u64>(w);
+  CUDA_CHECK(cudaMemcpy(d, data, w * 8, cudaMemcpyHostToDevice));
+  if (inverse)
+    vm->ops->ntt_inv(d, d, (int)count, (int)prime_idx, 0);
+  else
+    vm->ops->ntt_fwd(d, d, (int)count, (int)prime_idx, 0);
+  CUDA_CHECK(cudaStreamSynchronize(vm->stream));
+  CUDA_CHECK(cudaMemcpy(data, d, w * 8, cudaMemcpyDeviceToHost));
+  CUDA_CHECK(cudaFree(d));
+}
+void hevmx_encode(void *h, int64_t ptreg, const double *vals, int64_t len, int64_t level, int64_t scale_bits) {
+  VM *vm = V(h);
+  vm->stage_host_values(vals, (size_t)len);
+  vm->encode_internal(vm->ptr((size_t)ptreg), vm->d_vals_in, (int)std::min((size_t)len, vm->N / 2), level, scale_bits);
+  CUDA_CHECK(cudaStreamSynchronize(vm->stream));
+}
+void hevmx_decode(void *h, int64_t ptreg, double *out) {
+  VM *vm = V(h);
+  vm->decode_pt(vm->ptr((size_t)ptreg), vm->d_vals);
+  CUDA_CHECK(cudaMemcpyAsync(out, vm->d_vals, (vm->N / 2) * sizeof(double), cudaMemcpyDeviceToHost, vm->stream));
+  CUDA_CHECK(cudaStreamSynchronize(vm->stream));
+}
+void hevmx_decrypt_to_pt(void *h, int64_t ctreg, int64_t ptreg) { V(h)->decrypt_to_pt(V(h)->ctr((size_t)ctreg), V(h)->ptr((size_t)ptreg)); }
+void hevmx_encrypt_pt(void *h, int64_t ptreg, int64_t ctreg) { V(h)->encrypt_pt(V(h)->ptr((size_t)ptreg), V(h)->ctr((size_t)ctreg)); }
+void hevmx_set_enc_counter(void *h, uint64_t c) { V(h)->enc_counter = c; }
+int64_t hevmx_key_read(void *h, int which, uint64_t elt, uint64_t *out) {
+  VM *vm = V(h);
+  const u64 *src = nullptr;
+  size_t w = 0;
+  const size_t kw = (size_t)(vm->L - 1) * 2 * vm->L * vm->N;
+  if (which == 0) src = vm->d_sk, w = (size_t)vm->L * vm->N;
+  if (which == 1) src = vm->d_pk, w = (size_t)2 * vm->L * vm->N;
+  if (which == 2) src = vm->d_relin, w = kw;
+  if (which == 3) {
+    auto it = vm->d_gal.find(elt);
+    if (it == vm->d_gal.end()) return -1;
+    src = it->second, w = kw;
+  }
+  if (!src) return -1;
+  if (out) {
+    CUDA_CHECK(cudaStreamSynchronize(vm->stream));
+    CUDA_CHECK(cudaMemcpy(out, src, w * 8, cudaMemcpyDeviceToHost));
+  }
+  return (int64_t)w;
+}
+int64_t hevmx_galois_elt(void *h, int64_t step) { return (int64_t)V(h)->galois_elt_from_step((int)step); }
+const char *hevmx_backend(void) { return "b200-cuda-sm_100a"; }
+}

@@ -1,0 +1,255 @@
+"""GPU tier (-m gpu): libB200_HEVM.so vs the CPU oracle, bit-exact, through the C ABI.
+
+Full reference geometry: N = 2^15, 14 x 60-bit primes (SEAL_HEVM.cpp:39-53).  Both libraries
+are initialised from the same parameter/seed file, so keys, encryptions and every opcode's
+output residues must be identical words.  Floating-point (encode/decode) parity is also
+required bit-exact; the tolerance for end-to-end decrypted values against plain numpy maths
+is 1e-5 (the reference reports RMS ~1e-3 on ResNet, README.md:187).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from dacapo_b200 import hevm_asm as asm
+from util import VM
+
+pytestmark = pytest.mark.gpu
+LOGN, NPR = 15, 14
+
+
+@pytest.fixture(scope="module")
+def pair(oracle_lib, b200_lib, tmp_path_factory):
+    d = str(tmp_path_factory.mktemp("keys"))
+    g = VM(b200_lib, LOGN, NPR, keydir=d, nct=8, npt=4)
+    o = VM(oracle_lib, LOGN, NPR, keydir=d, nct=8, npt=4)
+    assert b200_lib.hevmx_backend() == b"b200-cuda-sm_100a"
+    return g, o
+
+
+def both(pair, fn):
+    g, o = pair
+    return fn(g), fn(o)
+
+
+def test_parameters(pair):
+    g, o = pair
+    assert g.primes == o.primes and g.roots == o.roots
+    assert g.primes[13] == 0xFFFFFFFFFFC0001
+
+
+def test_keys_bit_exact(pair):
+    g, o = pair
+    for which in (0, 1, 2):
+        assert np.array_equal(g.key(which), o.key(which)), f"key kind {which}"
+    for step in (1, -1, 64, -8192):
+        elt = o.lib.hevmx_galois_elt(o.vm, step)
+        assert g.lib.hevmx_galois_elt(g.vm, step) == elt
+        assert np.array_equal(g.key(3, elt), o.key(3, elt)), f"galois key step {step}"
+    assert g.lib.hevmx_param(g.vm, 5) == o.lib.hevmx_param(o.vm, 5) == 28
+
+
+@pytest.mark.parametrize("prime", [0, 5, 13])
+def test_ntt_bit_exact(pair, prime):
+    g, o = pair
+    rng = np.random.default_rng(prime)
+    q = o.primes[prime]
+    f = rng.integers(0, q, size=(3, o.N), dtype=np.uint64)
+    f[0, :6] = [0, 1, q - 1, q - 2, 2, q // 2]
+    f[2, :] = q - 1
+    F = o.ntt(f, prime)
+    assert np.array_equal(g.ntt(f, prime), F)
+    assert np.array_equal(g.ntt(F, prime, inverse=True), f)
+
+
+@pytest.mark.parametrize("lvl", [1, 2, 7, 13])
+def test_elementwise_ops(pair, lvl):
+    g, o = pair
+    a, b, p = o.random_ct(lvl, lvl), o.random_ct(lvl, 100 + lvl), o.random_pt(lvl, 200 + lvl)
+    for vm in pair:
+        vm.ct_write(0, a, 2.0 ** 40)
+        vm.ct_write(1, b, 2.0 ** 41)
+        vm.pt_write(0, p, 2.0 ** 30)
+    for op, args in ((asm.ADDCC, (0, 1)), (asm.NEGATE, (0, 0)), (asm.ADDCP, (0, 0)), (asm.MULCP, (0, 0))):
+        for vm in pair:
+            vm.exec(op, 2, *args)
+        assert np.array_equal(g.ct_read(2), o.ct_read(2)), asm.OP_NAMES[op]
+        assert g.ct_info(2) == o.ct_info(2)
+        assert g.ct_info(0) == o.ct_info(0)  # addcc/addcp overwrite the lhs scale (SEAL_HEVM.cpp:301,308)
+    if lvl > 2:
+        for vm in pair:
+            vm.exec(asm.MODSWITCH, 3, 0, 2)
+            vm.exec(asm.MODSWITCH, 0, 0, 1)  # in place
+        assert np.array_equal(g.ct_read(3), o.ct_read(3)) and g.ct_info(3) == o.ct_info(3) == (lvl - 2, 2.0 ** 30)
+        assert np.array_equal(g.ct_read(0), o.ct_read(0)) and g.ct_info(0)[0] == lvl - 1
+
+
+@pytest.mark.parametrize("lvl", [2, 3, 8, 13])
+def test_rescale(pair, lvl):
+    g, o = pair
+    a = o.random_ct(lvl, 300 + lvl)
+    for dst in (1, 0):  # out of place, in place
+        for vm in pair:
+            vm.ct_write(0, a, 2.0 ** 100)
+            vm.exec(asm.RESCALE, dst, 0)
+        assert np.array_equal(g.ct_read(dst), o.ct_read(dst))
+        assert g.ct_info(dst) == o.ct_info(dst)
+
+
+@pytest.mark.parametrize("lvl", [1, 2, 6, 13])
+def test_mulcc_relin(pair, lvl):
+    g, o = pair
+    a, b = o.random_ct(lvl, 400 + lvl), o.random_ct(lvl, 500 + lvl)
+    for dst, lhs, rhs in ((2, 0, 1), (0, 0, 1), (1, 0, 1), (2, 0, 0), (0, 0, 0)):
+        for vm in pair:
+            vm.ct_write(0, a, 2.0 ** 40)
+            vm.ct_write(1, b, 2.0 ** 40)
+            vm.exec(asm.MULCC, dst, lhs, rhs)
+        assert np.array_equal(g.ct_read(dst), o.ct_read(dst)), (dst, lhs, rhs)
+        assert g.ct_info(dst) == o.ct_info(dst)
+
+
+@pytest.mark.parametrize("lvl,step", [(1, 1), (2, -1), (5, 128), (13, 1), (13, -8192), (4, 12285), (3, -15360), (2, 0), (13, 16383)])
+def test_rotate(pair, lvl, step):
+    g, o = pair
+    a = o.random_ct(lvl, 600 + lvl)
+    for dst in (1, 0):
+        for vm in pair:
+            vm.ct_write(0, a, 2.0 ** 40)
+            vm.exec(asm.ROTATE, dst, 0, step)
+        assert np.array_equal(g.ct_read(dst), o.ct_read(dst)), (lvl, step, dst)
+
+
+def test_encode_decode_bit_exact(pair):
+    g, o = pair
+    rng = np.random.default_rng(7)
+    n = o.N // 2
+    cases = [(rng.uniform(-1, 1, n), 13, 40), (rng.uniform(-8, 8, 3), 5, 40), (np.array([1.0]), 2, 20),
+             (rng.uniform(-1, 1, n), 4, 90), (np.zeros(n), 1, 40), (rng.uniform(-1e3, 1e3, 100), 13, 59)]
+    for vals, lvl, sb in cases:
+        for vm in pair:
+            vm.encode(0, vals, lvl, sb)
+        assert np.array_equal(g.pt_read(0), o.pt_read(0)), (lvl, sb)
+        assert g.pt_info(0) == o.pt_info(0)
+        dg, do = g.decode(0), o.decode(0)
+        assert np.array_equal(dg, do), (lvl, sb)
+        assert np.max(np.abs(do - np.resize(vals, n))) < 1e-6 * max(1.0, np.max(np.abs(vals)))
+
+
+def test_encrypt_decrypt_bit_exact(pair):
+    g, o = pair
+    rng = np.random.default_rng(8)
+    x = rng.uniform(-1, 1, o.N // 2)
+    for lvl in (13, 3, 1):
+        for vm in pair:
+            vm.encode(0, x, lvl, 40)
+            vm.encrypt_pt(0, 0, counter=1000 + lvl)
+        assert np.array_equal(g.ct_read(0), o.ct_read(0)), lvl
+        for vm in pair:
+            vm.decrypt_to_pt(0, 1)
+        assert np.array_equal(g.pt_read(1), o.pt_read(1))
+        assert np.max(np.abs(g.decode(1) - x)) < 1e-7
+
+
+def test_bootstrap_op_bit_exact(pair):
+    g, o = pair
+    rng = np.random.default_rng(9)
+    x = rng.uniform(-1, 1, o.N // 2)
+    for vm in pair:
+        vm.encode(0, x, 2, 40)
+        vm.encrypt_pt(0, 0, counter=77)
+        vm.lib.hevmx_set_enc_counter(vm.vm, 78)
+        vm.exec(asm.BOOTSTRAP, 1, 0, 13)
+    assert np.array_equal(g.ct_read(1), o.ct_read(1))
+    assert g.ct_info(1) == o.ct_info(1) == (13, 2.0 ** 40)
+    assert np.max(np.abs(g.decrypt_decode(1, 1) - x)) < 1e-6
+
+
+def _program():
+    """A small program touching every opcode the compiler emits, incl. placeholders and aliasing."""
+    p = asm.Program(init_level=13)
+    x = p.arg(50, 4)
+    y = p.arg(50, 4)
+    t, u, v = p.new_ct(), p.new_ct(), p.new_ct()
+    c = p.const(np.linspace(0.1, 0.9, 37))
+    pt, ones, bias = p.new_pt(), p.new_pt(), p.new_pt()
+    p.encode(pt, c, 4, 50)
+    p.encode(ones, -1, 3, 20)
+    p.emit(asm.PLACEHOLDER, 0xBEEF, 0xDEAD, 0xF00D)
+    p.emit(asm.MULCP, t, x, pt)          # t = x*w            scale 100, level 4
+    p.emit(asm.MULCC, u, x, y)           # u = x*y            scale 100
+    p.emit(asm.ADDCC, t, t, u)           # t = x*w + x*y
+    p.emit(asm.RESCALE, t, t)            # scale ~40, level 3
+    p.encode(bias, p.const([0.25]), 3, 40)
+    p.emit(asm.ADDCP, t, t, bias)
+    p.rotate(v, t, 5)
+    p.rotate(v, v, -12285)
+    p.emit(asm.NEGATE, u, v)
+    p.emit(asm.ADDCC, v, u, t)           # v = t - rot(t)
+    p.emit(asm.MULCP, v, v, ones)        # upscale lowering (UpscaleToMulcp.cpp:52-72)
+    p.emit(asm.MODSWITCH, v, v, 1)       # level 2
+    p.emit(asm.BOOTSTRAP, u, v, 6)       # decrypt + re-encrypt at level 6
+    p.emit(asm.MULCC, u, u, u)
+    p.emit(asm.RESCALE, u, u)
+    p.result(u, 60, 5)
+    p.result(t, 40, 3)
+    return p
+
+
+def test_program_through_c_abi(pair, tmp_path):
+    g, o = pair
+    p = _program()
+    cst, hv = tmp_path / "p.cst", tmp_path / "p.hevm"
+    p.save(cst, hv)
+    n = o.N // 2
+    rng = np.random.default_rng(10)
+    x, y = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    outs = []
+    for vm in pair:
+        lib = vm.lib
+        lib.load(vm.vm, str(cst).encode(), str(hv).encode())
+        lib.preprocess(vm.vm)
+        lib.hevmx_set_enc_counter(vm.vm, 5)
+        assert lib.getArgLen(vm.vm) == 2 and lib.getResLen(vm.vm) == 2
+        for i, d in enumerate((x, y)):
+            lib.encrypt(vm.vm, i, d.ctypes.data_as(C.POINTER(C.c_double)), n)
+        lib.run(vm.vm)
+        res = np.zeros((2, n))
+        for i in range(2):
+            lib.decrypt_result(vm.vm, i, res[i].ctypes.data_as(C.POINTER(C.c_double)))
+        outs.append((res, vm.ct_read(lib.getResIdx(vm.vm, 0)), vm.ct_read(lib.getResIdx(vm.vm, 1))))
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
+    assert np.array_equal(outs[0][0], outs[1][0])
+    w = np.resize(np.linspace(0.1, 0.9, 37), n)
+    t = x * w + x * y + 0.25
+    v = t - np.roll(np.roll(t, -5), 12285)
+    assert np.max(np.abs(outs[0][0][1] - t)) < 1e-5
+    assert np.max(np.abs(outs[0][0][0] - v * v)) < 1e-4
+    for vm in pair:
+        vm.lib.hevmx_resize(vm.vm, 8, 4)
+
+
+def test_full_size_properties(pair):
+    """Size-independent properties on the device alone (no oracle): add/negate cancel exactly,
+    rotate(k) o rotate(-k) = id up to noise, rotate and multiply commute with decryption."""
+    g, _ = pair
+    rng = np.random.default_rng(11)
+    n = g.N // 2
+    x = rng.uniform(-1, 1, n)
+    g.encode(0, x, 13, 40)
+    g.encrypt_pt(0, 0)
+    g.exec(asm.NEGATE, 1, 0)
+    g.exec(asm.ADDCC, 2, 0, 1)
+    assert not g.ct_read(2).any()
+    g.exec(asm.ROTATE, 3, 0, 4097)
+    g.exec(asm.ROTATE, 3, 3, -4097)
+    assert np.max(np.abs(g.decrypt_decode(3, 1) - x)) < 1e-6
+    y = rng.uniform(-1, 1, n)
+    g.encode(1, y, 13, 40)
+    g.encrypt_pt(1, 4)
+    g.exec(asm.ADDCC, 5, 0, 4)
+    g.exec(asm.ROTATE, 5, 5, -300)
+    assert np.max(np.abs(g.decrypt_decode(5, 1) - np.roll(x + y, 300))) < 1e-6
+    g.exec(asm.MULCC, 6, 0, 4)
+    g.exec(asm.RESCALE, 6, 6)
+    assert np.max(np.abs(g.decrypt_decode(6, 1) - x * y)) < 1e-4  # scale 2^80/q ~ 2^20 after rescale
