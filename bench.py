@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py -- HEVM op micro-benchmark on B200 (BASELINE.json configs[1]).
+
+Workload ("step"): one run() of a compiled-style HEVM program over a batch of independent
+ciphertexts at the reference geometry (N = 2^15, 14 x 60-bit primes, SEAL_HEVM.cpp:39-53).
+Every ciphertext walks the FULL modulus chain: for level l = 13 .. 1:
+rotate (one key-switch, a different Galois key per ciphertext), multiply + relinearize,
+rescale.  That is 13 rotates + 13 HMult+relin + 12 rescales (+1 register copy) per ciphertext.
+
+  value : HEVM ops/s, run() only, inputs already encrypted and resident in HBM (what hc-test times)
+  e2e   : same metric through the reference-facing C ABI with HOST buffers: encrypt() of the
+          inputs (host doubles -> H2D -> encode -> public-key encrypt), run(), decrypt_result()
+          (decode -> D2H) all inside the timed region
+  --impl reference : the CPU restatement of the reference path (oracle/), one chain per host
+          core, timed on the box's host cores (SEAL itself is not installable here)
+
+One process per GPU; ranks are independent replicas over different ciphertexts (weak scaling,
+no data-path collective: SURVEY.md 8e "independent ciphertexts").
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+from dacapo_b200 import _binding, hevm_asm as asm  # noqa: E402
+
+LOGN, NPRIMES, TOP = 15, 14, 13
+N = 1 << LOGN
+SLOTS = N // 2
+BYTES_LIMB = 8 * N
+SEED = 0xDACA90
+f64p = C.POINTER(C.c_double)
+
+
+# ------------------------------------------------------------------------------------------------
+def build_program(batch, top=TOP, check_after=3):
+    """args 0..batch-1 stay pristine (encrypt() writes them); chains run in registers batch..2*batch-1."""
+    p = asm.Program(init_level=top)
+    args = [p.arg(60, top) for _ in range(batch)]
+    work = [p.new_ct() for _ in range(batch)]
+    mid = p.new_ct()
+    steps = []
+    for b in range(batch):
+        k = b % 14
+        steps.append((1 << k) if (b // 14) % 2 == 0 else -(1 << k))
+    for b in range(batch):
+        p.rotate(work[b], args[b], 0)  # register copy (rotate by 0)
+    nks = 0
+    for i, l in enumerate(range(top, 0, -1)):
+        for b in range(batch):
+            p.rotate(work[b], work[b], steps[b])
+            p.emit(asm.MULCC, work[b], work[b], work[b])
+            nks += 2
+            if l > 1:
+                p.emit(asm.RESCALE, work[b], work[b])
+        if i + 1 == check_after:
+            p.rotate(mid, work[0], 0)
+    for b in range(batch):
+        p.result(work[b], 60, 1)
+    p.result(mid, 60, top - check_after)
+    return p, steps, nks
+
+
+def expected_mid(x, step, rounds):
+    v = x.copy()
+    for _ in range(rounds):
+        v = np.roll(v, -step)
+        v = v * v
+    return v
+
+
+def make_vm(lib, keydir):
+    if not os.path.isfile(os.path.join(keydir, "hevm_params.bin")):
+        os.environ.update(HEVM_LOGN=str(LOGN), HEVM_NUM_PRIMES=str(NPRIMES), HEVM_SEED=str(SEED), HEVM_PRIME_BITS="60")
+        lib.create_context(keydir.encode())
+    return lib.initFullVM(keydir.encode(), True)
+
+
+def load_program(lib, vm, prog, tmp):
+    cst, hv = os.path.join(tmp, "bench.cst"), os.path.join(tmp, "bench.hevm")
+    prog.save(cst, hv)
+    lib.load(vm, cst.encode(), hv.encode())
+    lib.preprocess(vm)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path).read().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def measured_peak():
+    try:
+        return float(json.loads((REPO / "MEASURED_PEAKS.json").read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_chain_rate(nthreads, reps, keydirs):
+    """Oracle (CPU port of the reference path): `nthreads` independent VMs, each runs one full chain per rep."""
+    olib = _binding.bind(_binding.ORACLE_LIB)
+    prog, steps, _ = build_program(1)
+    nops = len(prog.ops)
+    tmp = tempfile.mkdtemp(prefix="hevm_cpu_")
+    vms = [None] * nthreads
+
+    def init(i):
+        vms[i] = make_vm(olib, keydirs[i])
+        load_program(olib, vms[i], prog, tempfile.mkdtemp(prefix=f"hevm_cpu{i}_", dir=tmp))
+        x = np.random.default_rng(i).uniform(-0.5, 0.5, SLOTS)
+        olib.encrypt(vms[i], 0, x.ctypes.data_as(f64p), SLOTS)
+
+    ts = [threading.Thread(target=init, args=(i,)) for i in range(nthreads)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+
+    def one_step():
+        th = [threading.Thread(target=olib.run, args=(vms[i],)) for i in range(nthreads)]
+        t0 = time.perf_counter()
+        [t.start() for t in th]
+        [t.join() for t in th]
+        return time.perf_counter() - t0
+
+    return one_step, nops * nthreads
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = max(1, min(os.cpu_count() or 1, 8))
+    subprocess.run(["make", "-s", "-C", str(REPO / "oracle")], check=True)
+    base = tempfile.mkdtemp(prefix="hevm_ref_keys_")
+    keydirs = []
+    for i in range(cores):
+        d = os.path.join(base, str(i))
+        os.makedirs(d)
+        keydirs.append(d)
+    one_step, ops_per_step = cpu_chain_rate(cores, 1, keydirs)
+    for _ in range(args.warmup):
+        one_step()
+    t = [one_step() for _ in range(args.steps)]
+    total = sum(t)
+    val = ops_per_step * args.steps / total
+    line = {
+        "impl": "reference", "metric": "hevm_ops_per_s", "value": val, "unit": "ops/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(cores, note="CPU restatement of SEAL 4.0 evaluator (oracle/); SEAL not installable offline"),
+        "cpu_baseline": {"value": val, "unit": "ops/s", "cores": cores, "kind": "port",
+                         "sample": f"{cores} independent ciphertext chains (one per core, {ops_per_step // cores} HEVM ops each) per step"},
+        "e2e": {"value": val, "unit": "ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(batch, note=None):
+    c = {"workload": "HEVM op microbench: per ciphertext, levels 13..1: rotate(1 key-switch) + HMult+relin + rescale "
+                     "(N=2^15, 14x60-bit primes, full modulus chain)",
+         "batch_ciphertexts_per_gpu": batch, "poly_degree": N, "num_primes": NPRIMES,
+         "l2": "working set per step (>= 1.3 GB of distinct key-switch keys) exceeds the 126 MB L2; no explicit flush"}
+    if note:
+        c["note"] = note
+    return c
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=28, help="independent ciphertexts per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--op-table", action="store_true", help="also measure the per-op/per-level table and emit profiled_B200_GPU.json")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libB200_HEVM.so has no CPU path")
+    torch.cuda.set_device(local_rank)
+    os.environ["HEVM_DEVICE"] = str(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    lib = _binding.bind(_binding.B200_LIB)  # raises if the CUDA library is missing
+    keydir = tempfile.mkdtemp(prefix=f"hevm_bench_keys_r{rank}_")
+    vm = make_vm(lib, keydir)
+    prog, steps, nks = build_program(args.batch)
+    nops = len(prog.ops)
+    tmp = tempfile.mkdtemp(prefix="hevm_bench_")
+    load_program(lib, vm, prog, tmp)
+
+    # inputs / outputs in pinned host memory
+    nres = args.batch + 1
+    xin = torch.empty((args.batch, SLOTS), dtype=torch.float64).pin_memory()
+    xout = torch.empty((nres, SLOTS), dtype=torch.float64).pin_memory()
+    rng = np.random.default_rng(1 + rank)
+    xin.numpy()[:] = rng.uniform(-0.5, 0.5, (args.batch, SLOTS))
+    xin_np, xout_np = xin.numpy(), xout.numpy()
+
+    def encrypt_all():
+        for b in range(args.batch):
+            lib.encrypt(vm, b, xin_np[b].ctypes.data_as(f64p), SLOTS)
+
+    def decrypt_all():
+        for r in range(nres):
+            lib.decrypt_result(vm, r, xout_np[r].ctypes.data_as(f64p))
+
+    # ---- correctness gate: the check register must match plain numpy ----
+    encrypt_all()
+    lib.run(vm)
+    decrypt_all()
+    exp = expected_mid(xin_np[0], steps[0], 3)
+    err = float(np.max(np.abs(xout_np[args.batch] - exp)))
+    if not err < 1e-4:
+        raise SystemExit(f"bench: decrypted check value differs from plain maths (max err {err})")
+
+    # ---- value: run() only, inputs resident in HBM; CUDA events on the VM stream ----
+    for _ in range(args.warmup):
+        lib.run(vm)
+    launches0 = lib.hevmx_param(vm, 6)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    lib.hevmx_timer(vm, 0)
+    for _ in range(args.steps):
+        lib.run(vm)
+    ms = lib.hevmx_timer(vm, 1)
+    barrier()
+    clocks = sampler.stop()
+    launches = lib.hevmx_param(vm, 6) - launches0
+    ms = max_over_ranks(ms)
+    value = nops * world * args.steps / (ms / 1e3)
+
+    # ---- e2e: encrypt (H2D) + run + decrypt (D2H) through the C ABI, wall clock, max over ranks ----
+    for _ in range(2):
+        encrypt_all(), lib.run(vm), decrypt_all()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        encrypt_all()
+        lib.run(vm)
+        decrypt_all()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = nops * world * args.steps / e2e_s
+
+    # ---- roofline of the dominant kernel: per-class CUDA-event timing over one more step ----
+    lib.hevmx_profile(vm, 1)
+    lib.run(vm)
+    lib.hevmx_profile(vm, 0)
+    kern = {}
+    cls = 0
+    while True:
+        t, c = C.c_double(), C.c_int64()
+        name = lib.hevmx_profile_read(vm, cls, C.byref(t), C.byref(c))
+        if name is None:
+            break
+        if c.value:
+            kern[name.decode()] = {"ms": t.value, "launches": c.value}
+        cls += 1
+    total_kernel_ms = sum(k["ms"] for k in kern.values())
+    dom = max(kern, key=lambda k: kern[k]["ms"])
+    peak, peak_src = measured_peak()
+    # algorithmic bytes of one fwd_B_mac launch at level l: digits l(l+1) + key 2l(l+1) + out 2(l+1) limbs
+    alg = {"fwd_B_mac": lambda l: (3 * l * l + 5 * l + 2) * BYTES_LIMB,
+           "fwd_A_modup": lambda l: (l + l * l) * BYTES_LIMB}
+    roof = None
+    if dom in alg:
+        launches_per_level = 2 * args.batch  # rotate + mulcc per ciphertext per level
+        tot_bytes = sum(alg[dom](l) for l in range(1, TOP + 1)) * launches_per_level
+        ach = tot_bytes / (kern[dom]["ms"] / 1e3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_src, "share_of_step": kern[dom]["ms"] / total_kernel_ms,
+                "avg_launch_us": 1e3 * kern[dom]["ms"] / kern[dom]["launches"]}
+    # op-level roofline per SURVEY 8(d): key-switch bytes (2l^2+6l)B (rotate) / (2l^2+8l)B (HMult+relin), rescale (4l-2)B
+    op_bytes = args.batch * sum((2 * l * l + 6 * l) + (2 * l * l + 8 * l) + ((4 * l - 2) if l > 1 else 0) for l in range(1, TOP + 1)) * BYTES_LIMB
+    op_roof = {"algorithmic_GB_per_step": op_bytes / 1e9, "achieved_GBps": op_bytes * args.steps / (ms / 1e3) / 1e9 / 1.0,
+               "frac_of_peak": op_bytes * args.steps / (ms / 1e3) / 1e9 / peak}
+
+    line = {
+        "metric": "hevm_ops_per_s", "value": value, "unit": "ops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic", "config": workload_config(args.batch),
+        "e2e": {"value": e2e, "unit": "ops/s", "h2d_bytes_per_step": args.batch * SLOTS * 8, "d2h_bytes_per_step": nres * SLOTS * 8,
+                "ms_per_step": 1e3 * e2e_s / args.steps},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "op_roofline": op_roof,
+        "keyswitch_per_s": nks * world * args.steps / (ms / 1e3), "hevm_ops_per_step": nops, "check_max_err": err,
+        "kernels": kern,
+    }
+
+    if args.op_table and rank == 0:
+        from dacapo_b200 import profile
+        table, prof = profile.emit_profile(str(REPO / "profiled_B200_GPU.json"), lib, vm)
+        line["op_table_us"] = {op: {str(l): round(v, 2) for l, v in lv.items()} for op, lv in table.items()}
+        line["op_roofline_l13"] = {op: {"us": table[op][13], "frac": profile.algorithmic_bytes(op, 13) / (table[op][13] * 1e-6) / 1e9 / peak}
+                                   for op in ("rotate", "mulcc", "rescale", "addcc", "mulcp")}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        subprocess.run(["make", "-s", "-C", str(REPO / "oracle")], check=True)
+        kd = tempfile.mkdtemp(prefix="hevm_cpu_keys_")
+        one_step, ops = cpu_chain_rate(1, 1, [kd])
+        one_step()
+        reps = 3
+        t = sum(one_step() for _ in range(reps))
+        line["cpu_baseline"] = {"value": ops * reps / t, "unit": "ops/s", "cores": 1, "kind": "port",
+                                "sample": f"1 ciphertext chain ({ops} HEVM ops, levels 13..1) x {reps} repetitions on one host core "
+                                          f"(the reference's SEAL evaluator is single-threaded); host has {os.cpu_count()} cores"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -10,6 +10,45 @@
 #include "kernels.h"
 
 unsigned long long g_launch_count = 0;
+KProfiler g_prof;
+const char *const g_kernel_class_names[KC_COUNT] = {
+    "intt_B_plain", "intt_B_galois", "intt_B_product", "intt_A", "fwd_A_plain", "fwd_A_modup", "fwd_A_round",
+    "fwd_B_canon", "fwd_B_mac", "fwd_B_moddown_galois", "fwd_B_moddown_relin", "fwd_B_rescale", "elementwise", "other"};
+cudaEvent_t KProfiler::ev() {
+  if (used == pool.size()) {
+    cudaEvent_t e;
+    CUDA_CHECK(cudaEventCreate(&e));
+    pool.push_back(e);
+  }
+  return pool[used++];
+}
+void KProfiler::begin(cudaStream_t s, int cls) {
+  if (!on) return;
+  Rec r{cls, ev(), ev()};
+  CUDA_CHECK(cudaEventRecord(r.a, s));
+  recs.push_back(r);
+  pending = true;
+}
+void KProfiler::end(cudaStream_t s) {
+  if (!on || !pending) return;
+  pending = false;
+  CUDA_CHECK(cudaEventRecord(recs.back().b, s));
+}
+void KProfiler::collect() {
+  for (auto &r : recs) {
+    CUDA_CHECK(cudaEventSynchronize(r.b));
+    float t = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.cls] += t;
+    cnt[r.cls]++;
+  }
+  recs.clear();
+  used = 0;
+}
+void KProfiler::reset() {
+  collect();
+  for (int i = 0; i < KC_COUNT; i++) ms[i] = 0, cnt[i] = 0;
+}
 
 #define WARPS_PER_CTA 8
 #define CTA_THREADS (WARPS_PER_CTA * 32)
@@ -44,31 +83,37 @@ template <int EPI> __global__ void __launch_bounds__(CTA_THREADS) k_fwd_B(ArgsFw
 }
 
 static inline int ctas_for(int njobs) { return (njobs + WARPS_PER_CTA - 1) / WARPS_PER_CTA; }
-#define POST_LAUNCH()                                                                                                  \
+#define PRE_LAUNCH(s, cls) g_prof.begin(s, cls)
+#define POST_LAUNCH_S(s)                                                                                               \
   do {                                                                                                                 \
+    g_prof.end(s);                                                                                                     \
     g_launch_count++;                                                                                                  \
     CUDA_CHECK(cudaGetLastError());                                                                                    \
   } while (0)
 
 template <int LD> void GpuLauncher::intt_B(const ArgsInttB &a, int njobs) {
   if (njobs <= 0) return;
+  PRE_LAUNCH(stream, KC_INTT_B_PLAIN + LD);
   k_intt_B<LD><<<ctas_for(njobs), CTA_THREADS, 0, stream>>>(a, njobs);
-  POST_LAUNCH();
+  POST_LAUNCH_S(stream);
 }
 void GpuLauncher::intt_A(const ArgsInttA &a, int njobs) {
   if (njobs <= 0) return;
+  PRE_LAUNCH(stream, KC_INTT_A);
   k_intt_A<<<ctas_for(njobs), CTA_THREADS, 0, stream>>>(a, njobs);
-  POST_LAUNCH();
+  POST_LAUNCH_S(stream);
 }
 template <int PRE> void GpuLauncher::fwd_A(const ArgsFwdA &a, int njobs) {
   if (njobs <= 0) return;
+  PRE_LAUNCH(stream, KC_FWD_A_NONE + PRE);
   k_fwd_A<PRE><<<ctas_for(njobs), CTA_THREADS, 0, stream>>>(a, njobs);
-  POST_LAUNCH();
+  POST_LAUNCH_S(stream);
 }
 template <int EPI> void GpuLauncher::fwd_B(const ArgsFwdB &a, int njobs) {
   if (njobs <= 0) return;
+  PRE_LAUNCH(stream, KC_FWD_B_CANON + EPI);
   k_fwd_B<EPI><<<ctas_for(njobs), CTA_THREADS, 0, stream>>>(a, njobs);
-  POST_LAUNCH();
+  POST_LAUNCH_S(stream);
 }
 template void GpuLauncher::intt_B<LD_PLAIN>(const ArgsInttB &, int);
 template void GpuLauncher::intt_B<LD_GALOIS>(const ArgsInttB &, int);
@@ -135,6 +180,7 @@ void launch_elementwise(cudaStream_t s, int op, const NttTables *T, int logN, u6
                         const u64 *p, size_t pitch, int l) {
   const size_t nvec = ((size_t)2 * l << logN) / 4;
   const int g = ew_grid(nvec);
+  PRE_LAUNCH(s, KC_ELEMENTWISE);
   switch (op) {
   case EW_ADD: k_elementwise<EW_ADD><<<g, 256, 0, s>>>(T, logN, out, a, b, p, pitch, l, nvec); break;
   case EW_NEG: k_elementwise<EW_NEG><<<g, 256, 0, s>>>(T, logN, out, a, b, p, pitch, l, nvec); break;
@@ -142,7 +188,7 @@ void launch_elementwise(cudaStream_t s, int op, const NttTables *T, int logN, u6
   case EW_MULP: k_elementwise<EW_MULP><<<g, 256, 0, s>>>(T, logN, out, a, b, p, pitch, l, nvec); break;
   default: k_elementwise<EW_COPY><<<g, 256, 0, s>>>(T, logN, out, a, b, p, pitch, l, nvec); break;
   }
-  POST_LAUNCH();
+  POST_LAUNCH_S(s);
 }
 
 // =====================================================================================
@@ -181,15 +227,15 @@ __global__ void k_sample_uniform(const NttTables *T, int logN, u64 *out, int lim
 }
 void launch_sample_ternary(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream) {
   k_sample_small<0><<<ew_grid((size_t)1 << logN), 256, 0, s>>>(T, logN, out, limbs, seed, stream);
-  POST_LAUNCH();
+  POST_LAUNCH_S(s);
 }
 void launch_sample_cbd(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream) {
   k_sample_small<1><<<ew_grid((size_t)1 << logN), 256, 0, s>>>(T, logN, out, limbs, seed, stream);
-  POST_LAUNCH();
+  POST_LAUNCH_S(s);
 }
 void launch_sample_uniform(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream_base) {
   k_sample_uniform<<<ew_grid((size_t)limbs << logN), 256, 0, s>>>(T, logN, out, limbs, seed, stream_base);
-  POST_LAUNCH();
+  POST_LAUNCH_S(s);
 }
 
 // =====================================================================================
@@ -210,7 +256,7 @@ __global__ void k_ksk_finish(const NttTables *T, int logN, int L, u64 *c0, const
 void launch_ksk_finish(cudaStream_t s, const NttTables *T, int logN, int L, u64 *c0, const u64 *c1, const u64 *sk,
                        const u64 *e, const u64 *newkey, int digit) {
   k_ksk_finish<<<ew_grid((size_t)L << logN), 256, 0, s>>>(T, logN, L, c0, c1, sk, e, newkey, digit);
-  POST_LAUNCH();
+  POST_LAUNCH_S(s);
 }
 __global__ void k_square(const NttTables *T, int logN, int L, u64 *out, const u64 *in) {
   const size_t total = (size_t)L << logN;
@@ -219,7 +265,7 @@ __global__ void k_square(const NttTables *T, int logN, int L, u64 *out, const u6
 }
 void launch_square(cudaStream_t s, const NttTables *T, int logN, int L, u64 *out, const u64 *in) {
   k_square<<<ew_grid((size_t)L << logN), 256, 0, s>>>(T, logN, L, out, in);
-  POST_LAUNCH();
+  POST_LAUNCH_S(s);
 }
 __global__ void k_galois_gather(int logN, int L, u64 *out, const u64 *in, u32 elt) {
   const size_t N = (size_t)1 << logN, total = N * L;
@@ -230,7 +276,7 @@ __global__ void k_galois_gather(int logN, int L, u64 *out, const u64 *in, u32 el
 }
 void launch_galois_gather(cudaStream_t s, int logN, int L, u64 *out, const u64 *in, u32 elt) {
   k_galois_gather<<<ew_grid((size_t)L << logN), 256, 0, s>>>(logN, L, out, in, elt);
-  POST_LAUNCH();
+  POST_LAUNCH_S(s);
 }
 __global__ void k_enc_combine(const NttTables *T, int logN, int nl, u64 *c, const u64 *u, const u64 *pk, size_t pk_pitch,
                               const u64 *e) {
@@ -245,7 +291,7 @@ __global__ void k_enc_combine(const NttTables *T, int logN, int nl, u64 *c, cons
 void launch_enc_combine(cudaStream_t s, const NttTables *T, int logN, int nl, u64 *c, const u64 *u, const u64 *pk,
                         size_t pk_pitch, const u64 *e) {
   k_enc_combine<<<ew_grid((size_t)2 * nl << logN), 256, 0, s>>>(T, logN, nl, c, u, pk, pk_pitch, e);
-  POST_LAUNCH();
+  POST_LAUNCH_S(s);
 }
 __global__ void k_decrypt(const NttTables *T, int logN, int l, u64 *pt, const u64 *ct, size_t pitch, const u64 *sk) {
   const size_t total = (size_t)l << logN;
@@ -256,7 +302,7 @@ __global__ void k_decrypt(const NttTables *T, int logN, int l, u64 *pt, const u6
 }
 void launch_decrypt(cudaStream_t s, const NttTables *T, int logN, int l, u64 *pt, const u64 *ct, size_t pitch, const u64 *sk) {
   k_decrypt<<<ew_grid((size_t)l << logN), 256, 0, s>>>(T, logN, l, pt, ct, pitch, sk);
-  POST_LAUNCH();
+  POST_LAUNCH_S(s);
 }
 
 // =====================================================================================
@@ -354,17 +400,17 @@ void launch_encode(cudaStream_t s, const NttTables *T, const EncoderTables &E, i
                    int level, double scale, double2 *work, unsigned long long *maxbits, u64 *out) {
   const size_t n = (size_t)1 << logN;
   k_enc_scatter<<<ew_grid(n / 2), 256, 0, s>>>(logN, vals, len, E.slot_index, work, maxbits);
-  POST_LAUNCH();
+  POST_LAUNCH_S(s);
   const double fix = scale / (double)n;
   int gap = 1;
   for (size_t m = n >> 1; m >= 1; m >>= 1, gap <<= 1) {
     k_fft_gs<<<ew_grid(n / 2), 256, 0, s>>>(logN, work, E.inv_root, (int)m, gap, fix, m == 1);
-    POST_LAUNCH();
+    POST_LAUNCH_S(s);
   }
   k_enc_max<<<ew_grid(n), 256, 0, s>>>(logN, work, maxbits);
-  POST_LAUNCH();
+  POST_LAUNCH_S(s);
   k_enc_round<<<ew_grid(n), 256, 0, s>>>(T, logN, level, work, maxbits, out);
-  POST_LAUNCH();
+  POST_LAUNCH_S(s);
 }
 
 #define DEC_MAXW 33
@@ -461,12 +507,12 @@ void launch_decode(cudaStream_t s, const NttTables *T, const EncoderTables &E, c
     std::abort();
   }
   k_dec_compose<<<ew_grid(n), 256, 0, s>>>(T, logN, l, coeff, D, 1.0 / scale, work);
-  POST_LAUNCH();
+  POST_LAUNCH_S(s);
   int gap = (int)(n >> 1);
   for (size_t m = 1; m < n; m <<= 1, gap >>= 1) {
     k_fft_ct<<<ew_grid(n / 2), 256, 0, s>>>(logN, work, E.fwd_root, (int)m, gap);
-    POST_LAUNCH();
+    POST_LAUNCH_S(s);
   }
   k_dec_gather<<<ew_grid(n / 2), 256, 0, s>>>(logN, work, E.slot_index, out);
-  POST_LAUNCH();
+  POST_LAUNCH_S(s);
 }

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
+#include <vector>
 
 #define CUDA_CHECK(x)                                                                                                  \
   do {                                                                                                                 \
@@ -17,6 +18,29 @@
 
 // counts every kernel this library launches (bench.py reports it as gpu_launches)
 extern unsigned long long g_launch_count;
+
+// Optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline).
+enum {
+  KC_INTT_B_PLAIN = 0, KC_INTT_B_GALOIS, KC_INTT_B_PRODUCT, KC_INTT_A, KC_FWD_A_NONE, KC_FWD_A_MODUP, KC_FWD_A_ROUND,
+  KC_FWD_B_CANON, KC_FWD_B_MAC, KC_FWD_B_MODDOWN_GALOIS, KC_FWD_B_MODDOWN_RELIN, KC_FWD_B_RESCALE, KC_ELEMENTWISE,
+  KC_OTHER, KC_COUNT
+};
+extern const char *const g_kernel_class_names[KC_COUNT];
+struct KProfiler {
+  bool on = false, pending = false;
+  struct Rec { int cls; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  double ms[KC_COUNT] = {0};
+  long long cnt[KC_COUNT] = {0};
+  cudaEvent_t ev();
+  void begin(cudaStream_t s, int cls);
+  void end(cudaStream_t s);
+  void collect(); // synchronises the recorded events and accumulates ms / cnt
+  void reset();
+};
+extern KProfiler g_prof;
 
 struct GpuLauncher {
   cudaStream_t stream = nullptr;

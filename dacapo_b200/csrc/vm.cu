@@ -106,7 +106,7 @@ struct VM {
   std::vector<CtReg> ct;
   std::vector<PtReg> pt;
   bool debug = false;
-  size_t bytes_allocated = 0;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
 
   // ---------------------------------------------------------------- setup
   void init(const ParamFile &pf) {
@@ -701,4 +701,37 @@ int64_t hevmx_key_read(void *h, int which, uint64_t elt, uint64_t *out) {
 }
 int64_t hevmx_galois_elt(void *h, int64_t step) { return (int64_t)V(h)->galois_elt_from_step((int)step); }
 const char *hevmx_backend(void) { return "b200-cuda-sm_100a"; }
+// CUDA-event stopwatch on the VM's own stream: which=0 start, which=1 stop -> elapsed milliseconds
+double hevmx_timer(void *h, int which) {
+  VM *vm = V(h);
+  if (!vm->ev_start) {
+    CUDA_CHECK(cudaEventCreate(&vm->ev_start));
+    CUDA_CHECK(cudaEventCreate(&vm->ev_stop));
+  }
+  if (which == 0) {
+    CUDA_CHECK(cudaEventRecord(vm->ev_start, vm->stream));
+    return 0.0;
+  }
+  CUDA_CHECK(cudaEventRecord(vm->ev_stop, vm->stream));
+  CUDA_CHECK(cudaEventSynchronize(vm->ev_stop));
+  float ms = 0;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, vm->ev_start, vm->ev_stop));
+  return (double)ms;
+}
+// per-kernel-class CUDA-event timing: on=1 reset+enable, on=0 collect+disable
+void hevmx_profile(void *h, int on) {
+  CUDA_CHECK(cudaStreamSynchronize(V(h)->stream));
+  if (on) {
+    g_prof.reset();
+    g_prof.on = true;
+  } else {
+    g_prof.on = false;
+    g_prof.collect();
+  }
+}
+const char *hevmx_profile_read(void *, int cls, double *ms, int64_t *count) {
+  if (cls < 0 || cls >= KC_COUNT) return nullptr;
+  *ms = g_prof.ms[cls], *count = g_prof.cnt[cls];
+  return g_kernel_class_names[cls];
+}
 }

@@ -1,0 +1,130 @@
+"""Measured B200 cost profile for the DaCapo / PARS planners.
+
+Emits `profiled_B200_GPU.json` with the schema the reference compiler loads
+(reference: lib/Dialect/Earth/IR/EarthDialect.cpp:130-180; sample profiled_SEAL_CPU.json):
+scalars rescalingFactor / polynomialDegree / level bounds, and `latencyTable` lists of
+INTEGER microseconds indexed by ciphertext level (entry k <=> level k+1).  Sub-microsecond
+GPU ops are rounded up to >= 1 us (the loader sums int64 microseconds); the
+exact float microseconds are kept beside them under "latencyTableExact" (ignored by the loader).
+Unlike profiled_SEAL_CPU.json this table also prices `bootstrap_single` (the wrapper's
+decrypt + re-encrypt) and `negate_single`, which the SEAL profile leaves at 0.
+"""
+import json
+import math
+
+import numpy as np
+
+from . import hevm_asm as asm
+
+_u64 = np.uint64
+
+
+def _rand_ct(vm_primes, level, N, seed):
+    rng = np.random.default_rng(seed)
+    a = np.zeros((2, level, N), dtype=np.uint64)
+    for i in range(level):
+        a[:, i, :] = rng.integers(0, vm_primes[i], size=(2, N), dtype=np.uint64)
+    return a
+
+
+def time_op(lib, vm, opcode, dst, lhs, rhs, reps, warmup=2):
+    """Median-free mean device time (us) of `reps` back-to-back executions, CUDA events on the VM stream."""
+    for _ in range(warmup):
+        lib.hevmx_exec(vm, opcode, dst, lhs, rhs & 0xFFFF)
+    lib.hevmx_sync(vm)
+    lib.hevmx_timer(vm, 0)
+    for _ in range(reps):
+        lib.hevmx_exec(vm, opcode, dst, lhs, rhs & 0xFFFF)
+    return lib.hevmx_timer(vm, 1) * 1e3 / reps
+
+
+def measure_op_table(lib, vm, levels=None, reps=20, rotate_steps=(1, -2, 4, -8, 16, -32, 64, -128)):
+    """Per-op, per-level device latency in microseconds.  Register file is resized (program state is lost).
+
+    rotate cycles through several Galois keys so that consecutive repetitions do not find their
+    95 MB key in L2; every other op alternates between register pairs for the same reason."""
+    import ctypes as C
+    logN = lib.hevmx_param(vm, 0)
+    L = lib.hevmx_param(vm, 1)
+    N = 1 << logN
+    primes = np.zeros(L, dtype=_u64)
+    lib.hevmx_primes(vm, primes.ctypes.data_as(C.POINTER(C.c_uint64)))
+    primes = [int(x) for x in primes]
+    levels = list(levels or range(1, L))
+    nreg = 18
+    lib.hevmx_resize(vm, nreg, 2)
+    table = {k: {} for k in ("rotate", "mulcc", "rescale", "modswitch", "addcc", "addcp", "mulcp", "negate", "bootstrap")}
+    for l in levels:
+        for r in range(8):
+            a = _rand_ct(primes, l, N, 1000 * l + r)
+            lib.hevmx_ct_write(vm, r, a.ctypes.data_as(C.POINTER(C.c_uint64)), l, 2.0 ** 40)
+        p = _rand_ct(primes, l, N, 7)[0]
+        lib.hevmx_pt_write(vm, 0, p.ctypes.data_as(C.POINTER(C.c_uint64)), l, 2.0 ** 40)
+
+        def cyc(opcode, rhs_fn, n=reps):
+            # warm-up + timed loop over rotating register pairs
+            for i in range(2):
+                lib.hevmx_exec(vm, opcode, 8 + i % 8, i % 8, rhs_fn(i) & 0xFFFF)
+            lib.hevmx_sync(vm)
+            lib.hevmx_timer(vm, 0)
+            for i in range(n):
+                lib.hevmx_exec(vm, opcode, 8 + i % 8, i % 8, rhs_fn(i) & 0xFFFF)
+            return lib.hevmx_timer(vm, 1) * 1e3 / n
+
+        table["rotate"][l] = cyc(asm.ROTATE, lambda i: rotate_steps[i % len(rotate_steps)])
+        table["mulcc"][l] = cyc(asm.MULCC, lambda i: (i + 1) % 8)
+        table["addcc"][l] = cyc(asm.ADDCC, lambda i: (i + 1) % 8)
+        table["addcp"][l] = cyc(asm.ADDCP, lambda i: 0)
+        table["mulcp"][l] = cyc(asm.MULCP, lambda i: 0)
+        table["negate"][l] = cyc(asm.NEGATE, lambda i: 0)
+        if l >= 2:
+            table["rescale"][l] = cyc(asm.RESCALE, lambda i: 0)
+            table["modswitch"][l] = cyc(asm.MODSWITCH, lambda i: 1)
+        # bootstrap = decrypt + decode + encode + encrypt from a low level up to level l
+        src_l = min(2, l)
+        a = _rand_ct(primes, src_l, N, 5)
+        lib.hevmx_ct_write(vm, 16, a.ctypes.data_as(C.POINTER(C.c_uint64)), src_l, 2.0 ** 40)
+        table["bootstrap"][l] = time_op(lib, vm, asm.BOOTSTRAP, 17, 16, l, max(3, reps // 4))
+    return table
+
+
+def algorithmic_bytes(op, l, N=1 << 15):
+    """Compulsory HBM bytes of one op at level l, B = 8N."""
+    B = 8 * N
+    return {"rotate": (2 * l * l + 6 * l) * B, "mulcc": (2 * l * l + 8 * l) * B, "rescale": (4 * l - 2) * B,
+            "addcc": 6 * l * B, "addcp": 5 * l * B, "mulcp": 5 * l * B, "negate": 4 * l * B,
+            "modswitch": 4 * (l - 1) * B}.get(op)
+
+
+def profile_json(table, logN=15, L=14):
+    top = L - 1
+
+    def lst(op, lo=1, hi=None):
+        hi = hi or top
+        return [table[op][l] for l in range(lo, hi + 1) if l in table[op]]
+
+    exact = {
+        "earth.rotate_single": lst("rotate"), "earth.rescale_single": lst("rescale", 2),
+        "earth.modswitch_single": lst("modswitch", 2), "earth.add_single": lst("addcp"),
+        "earth.add_double": lst("addcc"), "earth.mul_single": lst("mulcp"), "earth.mul_double": lst("mulcc"),
+        "earth.negate_single": lst("negate"), "earth.bootstrap_single": lst("bootstrap"),
+    }
+    # rescale / modswitch entry k is the cost at level k+1; level 1 cannot be rescaled: repeat the level-2 cost
+    for k in ("earth.rescale_single", "earth.modswitch_single"):
+        if exact[k]:
+            exact[k] = [exact[k][0]] + exact[k]
+    return {
+        "runtime": "B200-HEVM", "rescalingFactor": 60, "polynomialDegree": 1 << logN,
+        "levelLowerBound": 2, "levelUpperBound": top, "bootstrapLevelLowerBound": 2, "bootstrapLevelUpperBound": top,
+        "latencyTable": {k: [max(1, int(math.ceil(v))) for v in vs] for k, vs in exact.items()},
+        "latencyTableExact": {k: [round(v, 3) for v in vs] for k, vs in exact.items()},
+        "noiseTable": {},
+    }
+
+
+def emit_profile(path, lib, vm, reps=20):
+    table = measure_op_table(lib, vm, reps=reps)
+    prof = profile_json(table, lib.hevmx_param(vm, 0), lib.hevmx_param(vm, 1))
+    with open(path, "w") as f:
+        json.dump(prof, f, indent=1)
+    return table, prof

@@ -39,6 +39,10 @@ void hevmx_set_enc_counter(void *vm, uint64_t counter);
 int64_t hevmx_key_read(void *vm, int which, uint64_t elt, uint64_t *out);
 int64_t hevmx_galois_elt(void *vm, int64_t step);
 const char *hevmx_backend(void);
+/* --- libB200_HEVM.so only (measurement; not part of the oracle) --- */
+double hevmx_timer(void *vm, int which);        /* CUDA events on the VM stream: 0 start, 1 stop -> ms */
+void hevmx_profile(void *vm, int on);           /* per-kernel-class CUDA-event timing */
+const char *hevmx_profile_read(void *vm, int cls, double *ms, int64_t *count); /* NULL past the last class */
 
 #ifdef __cplusplus
 }

@@ -395,8 +395,12 @@ struct Context {
     return r;
   }
   // apply_galois_ntt permutation table: out[i] = in[table[i]]
-  std::vector<uint32_t> galois_table(u64 elt) const {
-    std::vector<uint32_t> t(N);
+  mutable std::map<u64, std::vector<uint32_t>> galois_table_cache; // GaloisTool keeps its tables too
+  const std::vector<uint32_t> &galois_table(u64 elt) const {
+    auto it = galois_table_cache.find(elt);
+    if (it != galois_table_cache.end()) return it->second;
+    std::vector<uint32_t> &t = galois_table_cache[elt];
+    t.resize(N);
     for (size_t i = 0; i < N; i++) {
       u64 rev = 2 * (u64)bitrev((uint32_t)i, logN) + 1;
       u64 raw = ((elt * rev) >> 1) & (N - 1);
@@ -499,7 +503,7 @@ struct Context {
   }
   void make_galois_key(u64 elt) {
     if (gal.count(elt)) return;
-    auto tab = galois_table(elt);
+    const auto &tab = galois_table(elt);
     std::vector<u64> rs((size_t)L * N);
     for (int i = 0; i < L; i++)
       for (size_t k = 0; k < N; k++) rs[(size_t)i * N + k] = sk[(size_t)i * N + tab[k]];
@@ -945,7 +949,7 @@ struct Context {
   void apply_galois(Ct &c, u64 elt) {
     int l = c.level;
     if (!gal.count(elt)) die("Galois key not present");
-    auto tab = galois_table(elt);
+    const auto &tab = galois_table(elt);
     std::vector<u64> t0((size_t)l * N), t1((size_t)l * N);
     for (int i = 0; i < l; i++)
       for (size_t k = 0; k < N; k++) {
