@@ -23,7 +23,7 @@ EXT_SYMBOLS = [
     "hevmx_set_enc_counter", "hevmx_key_read", "hevmx_galois_elt", "hevmx_backend",
 ]
 
-B200_ONLY_SYMBOLS = ["hevmx_timer", "hevmx_profile", "hevmx_profile_read"]
+B200_ONLY_SYMBOLS = ["hevmx_timer", "hevmx_profile", "hevmx_profile_read", "hevmx_profiler_range"]
 
 _u64p = C.POINTER(C.c_uint64)
 _f64p = C.POINTER(C.c_double)
@@ -92,6 +92,7 @@ def bind(path):
         lw.hevmx_timer.argtypes = [C.c_void_p, C.c_int]
         lw.hevmx_timer.restype = C.c_double
         lw.hevmx_profile.argtypes = [C.c_void_p, C.c_int]
+        lw.hevmx_profiler_range.argtypes = [C.c_void_p, C.c_int]
         lw.hevmx_profile_read.argtypes = [C.c_void_p, C.c_int, _f64p, _i64p]
         lw.hevmx_profile_read.restype = C.c_char_p
     return lw

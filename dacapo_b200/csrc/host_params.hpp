@@ -94,8 +94,17 @@ struct HostParams {
       std::fprintf(stderr, "[b200-hevm] fatal: at most %d primes supported\n", HEVM_MAXL);
       std::abort();
     }
+    if (bits != 60) {
+      std::fprintf(stderr, "[b200-hevm] fatal: the kernels assume 60-bit primes (SEAL_HEVM.cpp:48-53)\n");
+      std::abort();
+    }
     logN = logn, L = nprimes, N = (size_t)1 << logn;
     q = prime_chain(logn, bits, nprimes);
+    for (u64 p : q)
+      if ((((u64)1 << 60) - p) >> 32) {
+        std::fprintf(stderr, "[b200-hevm] fatal: prime too far below 2^60 for lazy folding\n");
+        std::abort();
+      }
     psi.resize(L);
     tw.resize((size_t)L * N);
     itw.resize((size_t)L * N);
@@ -117,6 +126,7 @@ struct HostParams {
       tab.mod[i].q = p;
       tab.mod[i].ratio_lo = (u64)ratio;
       tab.mod[i].ratio_hi = (u64)(ratio >> 64);
+      tab.mod[i].delta = ((u64)1 << 60) - p; // lazy-range folding needs p = 2^60 - delta, delta < 2^32
       u64 ninv = inv((u64)N % p, p);
       tab.invn[i] = shoup(ninv, p);
       tab.invn_w[i] = shoup(mul(ninv, itw[(size_t)i * N + 1].w, p), p);

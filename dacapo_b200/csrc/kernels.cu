@@ -50,36 +50,46 @@ void KProfiler::reset() {
   for (int i = 0; i < KC_COUNT; i++) ms[i] = 0, cnt[i] = 0;
 }
 
-#define WARPS_PER_CTA 8
+#define WARPS_PER_CTA 4
 #define CTA_THREADS (WARPS_PER_CTA * 32)
 
+// Every NTT kernel: a CTA is WARPS_PER_CTA independent warps; warp = one job; per-warp shared region =
+// padded value tile + staged twiddles.  No __syncthreads (except the MAC kernel's two CTA barriers).
+#define WARP_KERNEL_PROLOGUE(LaneT)                                                                                    \
+  __shared__ __align__(16) u64 sm[WARPS_PER_CTA][WARP_SMEM_WORDS];                                                     \
+  const int warp = threadIdx.x >> 5, job = blockIdx.x * WARPS_PER_CTA + warp;                                          \
+  if (job >= njobs) return;                                                                                            \
+  LaneT st[1];
+
 template <int LD> __global__ void __launch_bounds__(CTA_THREADS) k_intt_B(ArgsInttB a, int njobs) {
-  __shared__ u64 sm[WARPS_PER_CTA][WARP_SMEM_WORDS];
-  const int warp = threadIdx.x >> 5, job = blockIdx.x * WARPS_PER_CTA + warp;
-  if (job >= njobs) return;
-  LaneB8 st[1];
+  WARP_KERNEL_PROLOGUE(LaneB8)
   body_intt_B<LD>(a, job, st, sm[warp]);
 }
 __global__ void __launch_bounds__(CTA_THREADS) k_intt_A(ArgsInttA a, int njobs) {
-  __shared__ u64 sm[WARPS_PER_CTA][WARP_SMEM_WORDS];
-  const int warp = threadIdx.x >> 5, job = blockIdx.x * WARPS_PER_CTA + warp;
-  if (job >= njobs) return;
-  LaneA st[1];
+  WARP_KERNEL_PROLOGUE(LaneA)
   body_intt_A(a, job, st, sm[warp]);
 }
 template <int PRE> __global__ void __launch_bounds__(CTA_THREADS) k_fwd_A(ArgsFwdA a, int njobs) {
-  __shared__ u64 sm[WARPS_PER_CTA][WARP_SMEM_WORDS];
-  const int warp = threadIdx.x >> 5, job = blockIdx.x * WARPS_PER_CTA + warp;
-  if (job >= njobs) return;
-  LaneA st[1];
+  WARP_KERNEL_PROLOGUE(LaneA)
   body_fwd_A<PRE>(a, job, st, sm[warp]);
 }
 template <int EPI> __global__ void __launch_bounds__(CTA_THREADS) k_fwd_B(ArgsFwdB a, int njobs) {
-  __shared__ u64 sm[WARPS_PER_CTA][WARP_SMEM_WORDS];
-  const int warp = threadIdx.x >> 5, job = blockIdx.x * WARPS_PER_CTA + warp;
-  if (job >= njobs) return;
-  LaneB8 st[1];
+  WARP_KERNEL_PROLOGUE(LaneB8)
   body_fwd_B<EPI>(a, job, st, sm[warp]);
+}
+// key-switch inner product: CTA = one (output prime, row) job, its MAC_WARPS warps split the digits
+__global__ void __launch_bounds__(MAC_WARPS * 32, 3) k_mac(ArgsFwdB a) {
+  __shared__ __align__(16) u64 sm[MAC_SMEM_WORDS];
+  Tw *tw_s = reinterpret_cast<Tw *>(sm);
+  u64 *tiles = sm + 2 * WARP_TW_ENTRIES;
+  u64 *parts = tiles + MAC_WARPS * TILE_B_WORDS;
+  const int job = blockIdx.x, warp = threadIdx.x >> 5;
+  body_mac_stage(a, job, threadIdx.x, tw_s);
+  __syncthreads();
+  LaneB8 st[1];
+  body_mac_warp(a, job, warp, st, tiles + warp * TILE_B_WORDS, tw_s, parts + warp * MAC_PART_WORDS);
+  __syncthreads();
+  body_mac_reduce(a, job, threadIdx.x, parts);
 }
 
 static inline int ctas_for(int njobs) { return (njobs + WARPS_PER_CTA - 1) / WARPS_PER_CTA; }
@@ -115,6 +125,12 @@ template <int EPI> void GpuLauncher::fwd_B(const ArgsFwdB &a, int njobs) {
   k_fwd_B<EPI><<<ctas_for(njobs), CTA_THREADS, 0, stream>>>(a, njobs);
   POST_LAUNCH_S(stream);
 }
+void GpuLauncher::mac(const ArgsFwdB &a, int njobs) {
+  if (njobs <= 0) return;
+  PRE_LAUNCH(stream, KC_FWD_B_MAC);
+  k_mac<<<njobs, MAC_WARPS * 32, 0, stream>>>(a);
+  POST_LAUNCH_S(stream);
+}
 template void GpuLauncher::intt_B<LD_PLAIN>(const ArgsInttB &, int);
 template void GpuLauncher::intt_B<LD_GALOIS>(const ArgsInttB &, int);
 template void GpuLauncher::intt_B<LD_PRODUCT>(const ArgsInttB &, int);
@@ -122,7 +138,6 @@ template void GpuLauncher::fwd_A<PRE_NONE>(const ArgsFwdA &, int);
 template void GpuLauncher::fwd_A<PRE_MODUP>(const ArgsFwdA &, int);
 template void GpuLauncher::fwd_A<PRE_ROUND>(const ArgsFwdA &, int);
 template void GpuLauncher::fwd_B<EPI_CANON>(const ArgsFwdB &, int);
-template void GpuLauncher::fwd_B<EPI_MAC>(const ArgsFwdB &, int);
 template void GpuLauncher::fwd_B<EPI_MODDOWN_GALOIS>(const ArgsFwdB &, int);
 template void GpuLauncher::fwd_B<EPI_MODDOWN_RELIN>(const ArgsFwdB &, int);
 template void GpuLauncher::fwd_B<EPI_RESCALE>(const ArgsFwdB &, int);

@@ -48,6 +48,7 @@ struct GpuLauncher {
   void intt_A(const ArgsInttA &a, int njobs);
   template <int PRE> void fwd_A(const ArgsFwdA &a, int njobs);
   template <int EPI> void fwd_B(const ArgsFwdB &a, int njobs);
+  void mac(const ArgsFwdB &a, int njobs); // one 4-warp CTA per job
 };
 
 // ---- element-wise ciphertext kernels (SEAL add/negate/add_plain/multiply_plain, limb drop) ----

@@ -24,8 +24,9 @@ struct Tw { // Shoup operand: value and floor(value * 2^64 / q)   (SEAL Multiply
   u64 w, wq;
 };
 
-struct ModQ { // one RNS prime with its Barrett ratio floor(2^128 / q)
+struct ModQ { // one RNS prime q = 2^60 - delta (SEAL-style 60-bit prime) with its Barrett ratio floor(2^128 / q)
   u64 q, ratio_lo, ratio_hi;
+  u64 delta; // 2^60 - q  (< 2^32)
 };
 
 HD u64 mulhi64(u64 a, u64 b) {
@@ -43,6 +44,30 @@ HD u64 csub(u64 x, u64 m) { // x in [0,2m) -> [0,m)
   return y < x ? y : x; // unsigned wrap: x < m  =>  y > x
 }
 HD u64 shoup_mul(u64 x, Tw t, u64 q) { return csub(shoup_lazy(x, t, q), q); }
+
+// Lazy range control for q = 2^60 - delta, delta < 2^32:  v = k*2^60 + r  ==  r + k*delta (mod q).
+// Any 64-bit v (k <= 15) is mapped into [0, 2^60 + 15*delta) which is inside [0, 2q): three integer
+// instructions (shift, mask, 32x32->64 multiply-add) instead of a 6-instruction 64-bit compare/select.
+HD u64 fold60(u64 v, u64 delta) {
+  const u32 k = (u32)(v >> 60);
+  return (v & 0x0FFFFFFFFFFFFFFFull) + (u64)k * (u32)delta;
+}
+// Cooley-Tukey butterfly without range correction: x' = x + w*y, y' = x - w*y + 2q.
+// Each application grows the bound of its outputs by 2q; callers fold60() before 16q is reached.
+HD void ct_bfly_lazy(u64 &x, u64 &y, Tw t, u64 q, u64 q2) {
+  const u64 v = shoup_lazy(y, t, q);
+  const u64 u = x;
+  x = u + v;
+  y = u + q2 - v;
+}
+// Gentleman-Sande butterfly, inputs in [0,2q): x' = fold(x + y) in [0,2q), y' = w*(x - y) in [0,2q)
+HD void gs_bfly_fold(u64 &x, u64 &y, Tw t, u64 q, u64 q2, u64 delta) {
+  const u64 u = x, v = y;
+  x = fold60(u + v, delta);
+  y = shoup_lazy(u + q2 - v, t, q);
+}
+// canonical representative of a lazily bounded value (any 64-bit input)
+HD u64 canon60(u64 v, u64 q, u64 delta) { return csub(fold60(v, delta), q); }
 
 // Harvey forward (Cooley-Tukey) butterfly: x,y in [0,4q) -> [0,4q)
 HD void ct_bfly(u64 &x, u64 &y, Tw t, u64 q, u64 q2) {

@@ -1,6 +1,7 @@
-// Warp-job bodies of the NTT-based kernels (N = 2^15: 128 rows x 256 cols, LOGB = 8).
-// One warp executes one job; a job is a (limb, tile) or (limb, row) pair.  See ntt_core.cuh
-// for the schedule, and kernels.cu for the __global__ wrappers and the launch geometry.
+// Warp-job bodies of the NTT-based kernels (N = 2^15: 128 rows x 256 cols).
+// One warp executes one job (a (limb, tile) or (limb, row) pair); the key-switch inner-product
+// kernel uses one 4-warp CTA per (output prime, row) and splits the digit loop over its warps.
+// See ntt_core.cuh for the schedule, kernels.cu for the __global__ wrappers.
 //
 // Fusions (reference call sites SEAL_HEVM.cpp:273,283,315-316):
 //   body_intt_B  : [Galois gather | ct x ct product d2 = a1*b1 | plain load] + inverse pass B
@@ -8,10 +9,12 @@
 //   body_fwd_A   : [mod-up reduction "t_J mod q_I" | rounding fix-up] + forward pass A
 //   body_fwd_B   : forward pass B + one of
 //        CANON    canonical store (plain NTT)
-//        MAC      key-switch inner product over all digits J (128-bit lazy accumulators in
-//                 registers, Barrett at the end) -- the l x (l+1) digit matrix never exists in HBM
 //        MODDOWN  (acc - u) * p^-1 + addend   with addend = permuted c0 | tensor product d0/d1
 //        RESCALE  (c - u) * q_last^-1
+//   body_mac_*   : forward pass B of every digit + key-switch inner product with the key
+//                  (128-bit lazy accumulators in registers, per-warp partial sums combined through
+//                  shared memory, one Barrett at the end): the l x (l+1) matrix of NTT'd digits
+//                  never exists in HBM.
 #pragma once
 #include "ntt_core.cuh"
 
@@ -22,6 +25,22 @@ enum { EPI_CANON = 0, EPI_MAC = 1, EPI_MODDOWN_GALOIS = 2, EPI_MODDOWN_RELIN = 3
 #define LOGB8 8
 #define ROWS 128
 #define TILES_A 64 // 256 cols / 4
+#define MAC_WARPS 4
+#define MAC_PART_WORDS 1024 // per warp: 2 keys x 256 values x (lo,hi)
+// shared memory of one MAC CTA (words): staged twiddles | MAC_WARPS tiles | MAC_WARPS partial-sum blocks
+#define TILE_B_WORDS 272 // 256 values + 256/16 padding
+#define MAC_SMEM_WORDS (2 * WARP_TW_ENTRIES + MAC_WARPS * TILE_B_WORDS + MAC_WARPS * MAC_PART_WORDS)
+
+HD Tw *warp_tw(u64 *sm) { return reinterpret_cast<Tw *>(sm + WARP_TILE_WORDS); }
+
+HD void load8_stream(const u64 *p, u64 (&v)[8]) {
+  ldg_stream4(p, v[0], v[1], v[2], v[3]);
+  ldg_stream4(p + 4, v[4], v[5], v[6], v[7]);
+}
+HD void store8(u64 *p, const u64 (&v)[8]) {
+  stg4(p, v[0], v[1], v[2], v[3]);
+  stg4(p + 4, v[4], v[5], v[6], v[7]);
+}
 
 // ---------------------------------------------------------------------------------------------
 // inverse pass B.  limbs: `nl` limbs, limb k uses prime (prime0 + k*pstep); src limb pitch = N.
@@ -45,39 +64,36 @@ template <int LD> HD void body_intt_B(const ArgsInttB &a, int job, LaneB8 *st, u
   const int p = a.prime0 + limb * a.pstep;
   const ModQ m = T.mod[p];
   const u64 *src = a.src + (size_t)limb * N;
+  Tw *tw = warp_tw(sm);
   LANE_DECL;
   FOR_LANES(S, st, {
+    stage_tw_B(tw, T.itw + (size_t)p * N, r, lane);
     const int base = r * 256 + lane * 8;
     if (LD == LD_PLAIN) {
-      ldg_stream4(src + base, S.x[0], S.x[1], S.x[2], S.x[3]);
-      ldg_stream4(src + base + 4, S.x[4], S.x[5], S.x[6], S.x[7]);
+      load8_stream(src + base, S.x);
     } else if (LD == LD_GALOIS) {
       const u64 *c0 = a.c0 + (size_t)limb * N;
-      u64 *pc0 = a.pc0 + (size_t)limb * N;
       u64 v[8];
-_Pragma("unroll")
+      _Pragma("unroll")
       for (int e = 0; e < 8; e++) {
         u32 si = galois_src_index((u32)(base + e), a.elt, T.logN);
         S.x[e] = ldg_stream(src + si);
         v[e] = ldg_stream(c0 + si);
       }
-      stg4(pc0 + base, v[0], v[1], v[2], v[3]);
-      stg4(pc0 + base + 4, v[4], v[5], v[6], v[7]);
+      store8(a.pc0 + (size_t)limb * N + base, v);
     } else {
-      const u64 *b = a.src2 + (size_t)limb * N;
       u64 u[8], v[8];
-      ldg_stream4(src + base, u[0], u[1], u[2], u[3]);
-      ldg_stream4(src + base + 4, u[4], u[5], u[6], u[7]);
-      ldg_stream4(b + base, v[0], v[1], v[2], v[3]);
-      ldg_stream4(b + base + 4, v[4], v[5], v[6], v[7]);
-_Pragma("unroll")
+      load8_stream(src + base, u);
+      load8_stream(a.src2 + (size_t)limb * N + base, v);
+      _Pragma("unroll")
       for (int e = 0; e < 8; e++) S.x[e] = mulmod(u[e], v[e], m);
     }
+    cp_async_wait();
   });
-  warp_invB8_regs(st, sm, r, T.itw + (size_t)p * N, m.q);
+  warp_invB8_regs(st, sm, tw, m);
   u64 *dst = a.dst + (size_t)limb * N + r * 256;
   FOR_LANES(S, st, {
-_Pragma("unroll")
+    _Pragma("unroll")
     for (int e = 0; e < 8; e++) dst[idxH(lane, e)] = S.x[e];
   });
 }
@@ -97,13 +113,20 @@ HD void body_intt_A(const ArgsInttA &a, int job, LaneA *st, u64 *sm) {
   const int N = 1 << T.logN;
   const int limb = job >> 6, tile = job & 63;
   const int p = a.prime0 + limb * a.pstep;
-  const u64 q = T.mod[p].q;
-  warp_invA_to_regs<LOGB8>(st, sm, a.src + (size_t)limb * N, tile * 4, T.itw + (size_t)p * N, q, T.invn[p], T.invn_w[p]);
-  u64 *dst = a.dst + (size_t)limb * N + tile * 4;
-  const u64 half = q >> 1;
+  const ModQ m = T.mod[p];
+  const u64 q = m.q;
+  Tw *tw = warp_tw(sm);
   LANE_DECL;
   FOR_LANES(S, st, {
-_Pragma("unroll")
+    (void)S;
+    stage_tw_A(tw, T.itw + (size_t)p * N, lane);
+    cp_async_wait();
+  });
+  warp_invA_to_regs<LOGB8>(st, sm, a.src + (size_t)limb * N, tile * 4, tw, m, T.invn[p], T.invn_w[p]);
+  u64 *dst = a.dst + (size_t)limb * N + tile * 4;
+  const u64 half = q >> 1;
+  FOR_LANES(S, st, {
+    _Pragma("unroll")
     for (int e = 0; e < 16; e++) {
       u64 v = S.x[e];
       if (a.round) v = csub(v + half, q);
@@ -113,7 +136,7 @@ _Pragma("unroll")
 }
 
 // ---------------------------------------------------------------------------------------------
-// forward pass A with optional pre-processing.
+// forward pass A with optional pre-processing (output values are lazy, < 8q).
 //   PRE_NONE : dst limb d <- src limb d, prime prime0 + d*pstep                       (nd limbs)
 //   PRE_MODUP: d = Iidx*l + J : dst s2[Iidx][J] <- (t[J] mod q_I), I = Iidx<l ? Iidx : sp; skip I==J
 //   PRE_ROUND: d = K*nlim + i : dst s4[K][i]  <- (r[K] mod q_i) + q_i - (half mod q_i), half = q_plast/2
@@ -151,16 +174,21 @@ template <int PRE> HD void body_fwd_A(const ArgsFwdA &a, int job, LaneA *st, u64
   const u64 *src = a.src + (size_t)sl * N + tile * 4;
   u64 fix = 0;
   if (PRE == PRE_ROUND) fix = m.q - reduce64(T.mod[ps].q >> 1, m);
+  Tw *tw = warp_tw(sm);
   LANE_DECL;
   FOR_LANES(S, st, {
-_Pragma("unroll")
+    stage_tw_A(tw, T.tw + (size_t)pd * N, lane);
+    _Pragma("unroll")
+    for (int e = 0; e < 16; e++) S.y[e] = ldg_stream(src + ((size_t)rowR(lane, e) << LOGB8) + (lane & 3));
+    _Pragma("unroll")
     for (int e = 0; e < 16; e++) {
-      u64 v = ldg_stream(src + ((size_t)rowR(lane, e) << LOGB8) + (lane & 3));
+      u64 v = S.y[e];
       if (PRE != PRE_NONE && ps > pd) v = reduce64(v, m);
       S.y[e] = v + fix;
     }
+    cp_async_wait();
   });
-  warp_fwdA_from_regs<LOGB8>(st, sm, a.dst + (size_t)d * N, tile * 4, T.tw + (size_t)pd * N, m.q);
+  warp_fwdA_from_regs<LOGB8>(st, sm, a.dst + (size_t)d * N, tile * 4, tw, m);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -187,109 +215,131 @@ struct ArgsFwdB {
   int plast;         // prime divided out (sp for MODDOWN, l_in-1 for RESCALE)
 };
 
+// ---- key-switch inner product: one CTA of MAC_WARPS warps per (Iidx, row) ----------------------
+// phase 0 (all threads of the CTA): stage the row's twiddles of prime I
+HD void body_mac_stage(const ArgsFwdB &a, int job, int tid, Tw *tw_s) {
+  const NttTables &T = *a.T;
+  const int N = 1 << T.logN;
+  const int r = job & 127, Iidx = job >> 7, I = (Iidx == a.l) ? a.sp : Iidx;
+  stage_tw_B(tw_s, T.tw + (size_t)I * N, r, tid, MAC_WARPS * 32);
+  cp_async_wait();
+}
+// phase 1 (per warp): digits J = w, w + MAC_WARPS, ...; partial sums -> part[(K*256 + e*32 + lane)*2 + {lo,hi}]
+HD void body_mac_warp(const ArgsFwdB &a, int job, int w, LaneB8 *st, u64 *tile, const Tw *tw_s, u64 *part) {
+  const NttTables &T = *a.T;
+  const int N = 1 << T.logN;
+  const int r = job & 127, Iidx = job >> 7, I = (Iidx == a.l) ? a.sp : Iidx;
+  const ModQ m = T.mod[I];
+  LANE_DECL;
+  u64 lo0[NLANE_STATE][8], hi0[NLANE_STATE][8], lo1[NLANE_STATE][8], hi1[NLANE_STATE][8];
+  FOR_LANES(S, st, {
+    (void)S;
+    const int li = (NLANE_STATE == 1) ? 0 : lane;
+    _Pragma("unroll")
+    for (int e = 0; e < 8; e++) lo0[li][e] = hi0[li][e] = lo1[li][e] = hi1[li][e] = 0;
+  });
+  for (int J = w; J < a.l; J += MAC_WARPS) {
+    const u64 *k0 = a.key + (((size_t)J * 2 + 0) * a.Ltot + I) * N + r * 256;
+    const u64 *k1 = a.key + (((size_t)J * 2 + 1) * a.Ltot + I) * N + r * 256;
+    if (J == I) {
+      // diagonal: NTT-form target limb J, layout C, canonical
+      FOR_LANES(S, st, {
+        const int base = r * 256 + lane * 8;
+        if (a.ld == LD_PLAIN) {
+          load8_stream(a.tgt + (size_t)J * N + base, S.x);
+        } else if (a.ld == LD_GALOIS) {
+          const u64 *t = a.tgt + (size_t)J * N;
+          _Pragma("unroll")
+          for (int e = 0; e < 8; e++) S.x[e] = ldg_stream(t + galois_src_index((u32)(base + e), a.elt, T.logN));
+        } else {
+          u64 u[8], v[8];
+          load8_stream(a.tgt + (size_t)J * N + base, u);
+          load8_stream(a.tgt2 + (size_t)J * N + base, v);
+          _Pragma("unroll")
+          for (int e = 0; e < 8; e++) S.x[e] = mulmod(u[e], v[e], m);
+        }
+      });
+    } else {
+      const u64 *src = a.src + ((size_t)Iidx * a.l + J) * N + r * 256;
+      FOR_LANES(S, st, {
+        _Pragma("unroll")
+        for (int e = 0; e < 8; e++) S.x[e] = ldg_stream(src + idxH(lane, e));
+      });
+      warp_fwdB8_regs(st, tile, tw_s, m);
+      FOR_LANES(S, st, {
+        _Pragma("unroll")
+        for (int e = 0; e < 8; e++) S.x[e] = fold60(S.x[e], m.delta);
+      });
+    }
+    FOR_LANES(S, st, {
+      const int li = (NLANE_STATE == 1) ? 0 : lane;
+      u64 ka[8], kb[8];
+      load8_stream(k0 + lane * 8, ka);
+      load8_stream(k1 + lane * 8, kb);
+      _Pragma("unroll")
+      for (int e = 0; e < 8; e++) {
+        mac128(lo0[li][e], hi0[li][e], S.x[e], ka[e]);
+        mac128(lo1[li][e], hi1[li][e], S.x[e], kb[e]);
+      }
+    });
+  }
+  FOR_LANES(S, st, {
+    (void)S;
+    const int li = (NLANE_STATE == 1) ? 0 : lane;
+    _Pragma("unroll")
+    for (int e = 0; e < 8; e++) {
+      u64 *p0 = part + (size_t)(0 * 256 + e * 32 + lane) * 2;
+      u64 *p1 = part + (size_t)(1 * 256 + e * 32 + lane) * 2;
+      p0[0] = lo0[li][e], p0[1] = hi0[li][e];
+      p1[0] = lo1[li][e], p1[1] = hi1[li][e];
+    }
+  });
+}
+// phase 2 (all threads, after a CTA barrier): sum the per-warp partials, Barrett, store acc[K][Iidx][row]
+HD void body_mac_reduce(const ArgsFwdB &a, int job, int tid, const u64 *parts) {
+  const NttTables &T = *a.T;
+  const int N = 1 << T.logN;
+  const int r = job & 127, Iidx = job >> 7, I = (Iidx == a.l) ? a.sp : Iidx;
+  const ModQ m = T.mod[I];
+  const int nw = a.l < MAC_WARPS ? a.l : MAC_WARPS; // warps that own at least one digit
+  _Pragma("unroll")
+  for (int it = 0; it < 512 / (MAC_WARPS * 32); it++) {
+    const int slot = tid + it * MAC_WARPS * 32; // K*256 + e*32 + lane
+    u64 lo = 0, hi = 0;
+    for (int w = 0; w < nw; w++) {
+      const u64 *p = parts + (size_t)w * MAC_PART_WORDS + (size_t)slot * 2;
+      const u64 pl = p[0], ph = p[1];
+      lo += pl;
+      hi += ph + (lo < pl ? 1 : 0);
+    }
+    const int K = slot >> 8, e = (slot >> 5) & 7, lane = slot & 31;
+    a.dst[((size_t)K * (a.l + 1) + Iidx) * N + r * 256 + lane * 8 + e] = reduce128(lo, hi, m);
+  }
+}
+
 template <int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, LaneB8 *st, u64 *sm) {
   const NttTables &T = *a.T;
   const int N = 1 << T.logN;
   const int r = job & 127, d = job >> 7;
+  Tw *tw = warp_tw(sm);
   LANE_DECL;
-  if (EPI == EPI_MAC) {
-    // d = Iidx in [0, l]; loop over digits J
-    const int Iidx = d, I = (Iidx == a.l) ? a.sp : Iidx;
-    const ModQ m = T.mod[I];
-    const Tw *tw = T.tw + (size_t)I * N;
-    u64 lo0[NLANE_STATE][8], hi0[NLANE_STATE][8], lo1[NLANE_STATE][8], hi1[NLANE_STATE][8];
-    FOR_LANES(S, st, {
-      (void)S;
-      const int li = (NLANE_STATE == 1) ? 0 : lane;
-_Pragma("unroll")
-      for (int e = 0; e < 8; e++) lo0[li][e] = hi0[li][e] = lo1[li][e] = hi1[li][e] = 0;
-    });
-    for (int J = 0; J < a.l; J++) {
-      if (J == I) {
-        // diagonal: NTT-form target limb J, layout C
-        FOR_LANES(S, st, {
-          const int base = r * 256 + lane * 8;
-          if (a.ld == LD_PLAIN) {
-            const u64 *t = a.tgt + (size_t)J * N + base;
-            ldg_stream4(t, S.x[0], S.x[1], S.x[2], S.x[3]);
-            ldg_stream4(t + 4, S.x[4], S.x[5], S.x[6], S.x[7]);
-          } else if (a.ld == LD_GALOIS) {
-            const u64 *t = a.tgt + (size_t)J * N;
-_Pragma("unroll")
-            for (int e = 0; e < 8; e++) S.x[e] = ldg_stream(t + galois_src_index((u32)(base + e), a.elt, T.logN));
-          } else {
-            const u64 *t = a.tgt + (size_t)J * N + base;
-            const u64 *t2 = a.tgt2 + (size_t)J * N + base;
-            u64 u[8], v[8];
-            ldg_stream4(t, u[0], u[1], u[2], u[3]);
-            ldg_stream4(t + 4, u[4], u[5], u[6], u[7]);
-            ldg_stream4(t2, v[0], v[1], v[2], v[3]);
-            ldg_stream4(t2 + 4, v[4], v[5], v[6], v[7]);
-_Pragma("unroll")
-            for (int e = 0; e < 8; e++) S.x[e] = mulmod(u[e], v[e], m);
-          }
-        });
-      } else {
-        const u64 *src = a.src + ((size_t)Iidx * a.l + J) * N + r * 256;
-        FOR_LANES(S, st, {
-_Pragma("unroll")
-          for (int e = 0; e < 8; e++) S.x[e] = ldg_stream(src + idxH(lane, e));
-        });
-        warp_fwdB8_regs(st, sm, r, tw, m.q);
-      }
-      const u64 *k0 = a.key + (((size_t)J * 2 + 0) * a.Ltot + I) * N + r * 256;
-      const u64 *k1 = a.key + (((size_t)J * 2 + 1) * a.Ltot + I) * N + r * 256;
-      FOR_LANES(S, st, {
-        const int li = (NLANE_STATE == 1) ? 0 : lane;
-        u64 ka[8], kb[8];
-        ldg_stream4(k0 + lane * 8, ka[0], ka[1], ka[2], ka[3]);
-        ldg_stream4(k0 + lane * 8 + 4, ka[4], ka[5], ka[6], ka[7]);
-        ldg_stream4(k1 + lane * 8, kb[0], kb[1], kb[2], kb[3]);
-        ldg_stream4(k1 + lane * 8 + 4, kb[4], kb[5], kb[6], kb[7]);
-_Pragma("unroll")
-        for (int e = 0; e < 8; e++) {
-          mac128(lo0[li][e], hi0[li][e], S.x[e], ka[e]);
-          mac128(lo1[li][e], hi1[li][e], S.x[e], kb[e]);
-        }
-      });
-    }
-    u64 *o0 = a.dst + ((size_t)0 * (a.l + 1) + Iidx) * N + r * 256;
-    u64 *o1 = a.dst + ((size_t)1 * (a.l + 1) + Iidx) * N + r * 256;
-    FOR_LANES(S, st, {
-      (void)S;
-      const int li = (NLANE_STATE == 1) ? 0 : lane;
-      u64 v0[8], v1[8];
-_Pragma("unroll")
-      for (int e = 0; e < 8; e++) {
-        v0[e] = reduce128(lo0[li][e], hi0[li][e], m);
-        v1[e] = reduce128(lo1[li][e], hi1[li][e], m);
-      }
-      stg4(o0 + lane * 8, v0[0], v0[1], v0[2], v0[3]);
-      stg4(o0 + lane * 8 + 4, v0[4], v0[5], v0[6], v0[7]);
-      stg4(o1 + lane * 8, v1[0], v1[1], v1[2], v1[3]);
-      stg4(o1 + lane * 8 + 4, v1[4], v1[5], v1[6], v1[7]);
-    });
-    return;
-  }
-
-  // --- single-limb variants: d indexes the limb ---
   if (EPI == EPI_CANON) {
     const int p = a.prime0 + d * a.pstep;
     const ModQ m = T.mod[p];
-    const u64 q = m.q, q2 = 2 * m.q;
     const u64 *src = a.src + (size_t)d * N + r * 256;
     FOR_LANES(S, st, {
-_Pragma("unroll")
+      stage_tw_B(tw, T.tw + (size_t)p * N, r, lane);
+      _Pragma("unroll")
       for (int e = 0; e < 8; e++) S.x[e] = ldg_stream(src + idxH(lane, e));
+      cp_async_wait();
     });
-    warp_fwdB8_regs(st, sm, r, T.tw + (size_t)p * N, q);
+    warp_fwdB8_regs(st, sm, tw, m);
     u64 *o = a.dst + (size_t)d * N + r * 256;
     FOR_LANES(S, st, {
       u64 v[8];
-_Pragma("unroll")
-      for (int e = 0; e < 8; e++) v[e] = csub(csub(S.x[e], q2), q);
-      stg4(o + lane * 8, v[0], v[1], v[2], v[3]);
-      stg4(o + lane * 8 + 4, v[4], v[5], v[6], v[7]);
+      _Pragma("unroll")
+      for (int e = 0; e < 8; e++) v[e] = canon60(S.x[e], m.q, m.delta);
+      store8(o + lane * 8, v);
     });
     return;
   }
@@ -298,43 +348,35 @@ _Pragma("unroll")
     // (a0,a1,b0,b1 at this position) is read before either output is written (dst may alias a or b).
     const int i = d;
     const ModQ m = T.mod[i];
-    const u64 q = m.q, q2 = 2 * m.q;
+    const u64 q = m.q;
     const Tw inv = T.qinv[a.plast][i];
     const size_t off = (size_t)i * N + r * 256;
     for (int K = 0; K < 2; K++) {
       const u64 *src = a.src + ((size_t)K * a.l + i) * N + r * 256;
       FOR_LANES(S, st, {
+        if (K == 0) stage_tw_B(tw, T.tw + (size_t)i * N, r, lane);
         if (K == 1) {
-_Pragma("unroll")
+          _Pragma("unroll")
           for (int e = 0; e < 8; e++) S.z[e] = S.x[e];
         }
-_Pragma("unroll")
+        _Pragma("unroll")
         for (int e = 0; e < 8; e++) S.x[e] = ldg_stream(src + idxH(lane, e));
+        cp_async_wait();
       });
-      warp_fwdB8_regs(st, sm, r, T.tw + (size_t)i * N, q);
+      warp_fwdB8_regs(st, sm, tw, m);
     }
     FOR_LANES(S, st, {
       const int b = lane * 8;
-      const u64 *c0p = a.acc + ((size_t)0 * (a.l + 1) + i) * N + r * 256 + b;
-      const u64 *c1p = a.acc + ((size_t)1 * (a.l + 1) + i) * N + r * 256 + b;
-      const u64 *pa0 = a.add0 + off + b, *pa1 = a.add0 + a.pitch + off + b;
-      const u64 *pb0 = a.add1 + off + b, *pb1 = a.add1 + a.pitch + off + b;
       u64 c0[8], c1[8], a0[8], a1[8], b0[8], b1[8], v0[8], v1[8];
-      ldg_stream4(c0p, c0[0], c0[1], c0[2], c0[3]);
-      ldg_stream4(c0p + 4, c0[4], c0[5], c0[6], c0[7]);
-      ldg_stream4(c1p, c1[0], c1[1], c1[2], c1[3]);
-      ldg_stream4(c1p + 4, c1[4], c1[5], c1[6], c1[7]);
-      ldg_stream4(pa0, a0[0], a0[1], a0[2], a0[3]);
-      ldg_stream4(pa0 + 4, a0[4], a0[5], a0[6], a0[7]);
-      ldg_stream4(pa1, a1[0], a1[1], a1[2], a1[3]);
-      ldg_stream4(pa1 + 4, a1[4], a1[5], a1[6], a1[7]);
-      ldg_stream4(pb0, b0[0], b0[1], b0[2], b0[3]);
-      ldg_stream4(pb0 + 4, b0[4], b0[5], b0[6], b0[7]);
-      ldg_stream4(pb1, b1[0], b1[1], b1[2], b1[3]);
-      ldg_stream4(pb1 + 4, b1[4], b1[5], b1[6], b1[7]);
-_Pragma("unroll")
+      load8_stream(a.acc + ((size_t)0 * (a.l + 1) + i) * N + r * 256 + b, c0);
+      load8_stream(a.acc + ((size_t)1 * (a.l + 1) + i) * N + r * 256 + b, c1);
+      load8_stream(a.add0 + off + b, a0);
+      load8_stream(a.add0 + a.pitch + off + b, a1);
+      load8_stream(a.add1 + off + b, b0);
+      load8_stream(a.add1 + a.pitch + off + b, b1);
+      _Pragma("unroll")
       for (int e = 0; e < 8; e++) {
-        u64 u0 = csub(csub(S.z[e], q2), q), u1 = csub(csub(S.x[e], q2), q);
+        u64 u0 = canon60(S.z[e], q, m.delta), u1 = canon60(S.x[e], q, m.delta);
         u64 t0 = shoup_mul(c0[e] + q - u0, inv, q);
         u64 t1 = shoup_mul(c1[e] + q - u1, inv, q);
         v0[e] = csub(t0 + mulmod(a0[e], b0[e], m), q);
@@ -344,11 +386,8 @@ _Pragma("unroll")
         mac128(lo, hi, a1[e], b0[e]);
         v1[e] = csub(t1 + reduce128(lo, hi, m), q);
       }
-      u64 *o0 = a.dst + off + b, *o1 = a.dst + a.pitch + off + b;
-      stg4(o0, v0[0], v0[1], v0[2], v0[3]);
-      stg4(o0 + 4, v0[4], v0[5], v0[6], v0[7]);
-      stg4(o1, v1[0], v1[1], v1[2], v1[3]);
-      stg4(o1 + 4, v1[4], v1[5], v1[6], v1[7]);
+      store8(a.dst + off + b, v0);
+      store8(a.dst + a.pitch + off + b, v1);
     });
     return;
   }
@@ -356,13 +395,15 @@ _Pragma("unroll")
   {
     const int K = d / a.l, i = d - K * a.l;
     const ModQ m = T.mod[i];
-    const u64 q = m.q, q2 = 2 * m.q;
+    const u64 q = m.q;
     const u64 *src = a.src + (size_t)d * N + r * 256;
     FOR_LANES(S, st, {
-_Pragma("unroll")
+      stage_tw_B(tw, T.tw + (size_t)i * N, r, lane);
+      _Pragma("unroll")
       for (int e = 0; e < 8; e++) S.x[e] = ldg_stream(src + idxH(lane, e));
+      cp_async_wait();
     });
-    warp_fwdB8_regs(st, sm, r, T.tw + (size_t)i * N, q);
+    warp_fwdB8_regs(st, sm, tw, m);
     const Tw inv = T.qinv[a.plast][i];
     const size_t off = (size_t)i * N + r * 256;
     u64 *o = a.dst + (size_t)K * a.pitch + off;
@@ -371,23 +412,19 @@ _Pragma("unroll")
       u64 c[8], v[8];
       const u64 *cin = (EPI == EPI_RESCALE) ? a.add0 + (size_t)K * a.pitch + off + b
                                             : a.acc + ((size_t)K * (a.l + 1) + i) * N + r * 256 + b;
-      ldg_stream4(cin, c[0], c[1], c[2], c[3]);
-      ldg_stream4(cin + 4, c[4], c[5], c[6], c[7]);
-_Pragma("unroll")
+      load8_stream(cin, c);
+      _Pragma("unroll")
       for (int e = 0; e < 8; e++) {
-        u64 u = csub(csub(S.x[e], q2), q);      // canonical NTT of the rounding term
+        u64 u = canon60(S.x[e], q, m.delta);    // canonical NTT of the rounding term
         v[e] = shoup_mul(c[e] + q - u, inv, q); // (c - u) * plast^-1 mod q
       }
       if (EPI == EPI_MODDOWN_GALOIS && K == 0) {
-        const u64 *p0 = a.add0 + off + b;
         u64 w[8];
-        ldg_stream4(p0, w[0], w[1], w[2], w[3]);
-        ldg_stream4(p0 + 4, w[4], w[5], w[6], w[7]);
-_Pragma("unroll")
+        load8_stream(a.add0 + off + b, w);
+        _Pragma("unroll")
         for (int e = 0; e < 8; e++) v[e] = csub(v[e] + w[e], q);
       }
-      stg4(o + b, v[0], v[1], v[2], v[3]);
-      stg4(o + b + 4, v[4], v[5], v[6], v[7]);
+      store8(o + b, v);
     });
   }
 }

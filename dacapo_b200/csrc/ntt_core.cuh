@@ -15,6 +15,10 @@
 //   only to re-distribute values between rounds of 2-4 register-resident stages (__syncwarp,
 //   never __syncthreads).  Shared tile index idx -> idx + idx/16 makes every 64-bit access
 //   pattern used here bank-conflict free.
+//   The twiddles a job needs (127 per pass-A prime, 255 per pass-B row) are staged into shared
+//   memory once per job with cp.async, so no butterfly stage waits on a global-memory round trip.
+//   Range control is lazy: butterflies never compare; values are folded into [0,2q) with
+//   fold60() (q = 2^60 - delta) only where a round of stages could otherwise exceed 16q < 2^64.
 //
 // Everything is __host__ __device__: `FOR_LANES` runs the per-lane code on the 32 lanes of a
 // real warp on the GPU, and as a 32-iteration loop over an array of lane states in the
@@ -43,13 +47,18 @@ struct NttTables {
     __syncwarp();                                                                                                      \
   }
 #define NLANE_STATE 1
-HD Tw ldtw(const Tw *p) {
-  ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(p));
+HD Tw ldtw(const Tw *p) { // twiddle from the warp's shared-memory copy (LDS.128)
+  const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(p);
   Tw t;
   t.w = v.x;
   t.wq = v.y;
   return t;
 }
+HD void cp_async16(void *smem_dst, const void *gsrc) { // LDGSTS: global -> shared without registers
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+HD void cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // streaming 64-bit / 256-bit accesses (no L1 allocation: each value is touched once per pass)
 HD u64 ldg_stream(const u64 *p) {
   u64 v;
@@ -71,18 +80,39 @@ HD void stg4(u64 *p, u64 a, u64 b, u64 c, u64 d) {
   }
 #define NLANE_STATE 32
 HD Tw ldtw(const Tw *p) { return *p; }
+HD void cp_async16(void *smem_dst, const void *gsrc) { *(Tw *)smem_dst = *(const Tw *)gsrc; }
+HD void cp_async_wait() {}
 HD u64 ldg_stream(const u64 *p) { return *p; }
 HD void ldg_stream4(const u64 *p, u64 &a, u64 &b, u64 &c, u64 &d) { a = p[0], b = p[1], c = p[2], d = p[3]; }
 HD void stg4(u64 *p, u64 a, u64 b, u64 c, u64 d) { p[0] = a, p[1] = b, p[2] = c, p[3] = d; }
 #endif
 
 HD int padx(int idx) { return idx + (idx >> 4); }
-#define TILE_A_WORDS 544 // 512 + 512/16
-template <int LOGB> struct TileB {
-  static constexpr int E = (1 << LOGB) / 32;                   // values per lane
-  static constexpr int WORDS = (1 << LOGB) + ((1 << LOGB) >> 4); // padded
-};
-#define WARP_SMEM_WORDS 544 // max(TILE_A_WORDS, TileB<9>::WORDS)
+#define WARP_TILE_WORDS 544  // 512 values + 512/16 padding
+#define WARP_TW_ENTRIES 256  // staged twiddles (pass A uses 128, pass B 255)
+#define WARP_SMEM_WORDS (WARP_TILE_WORDS + 2 * WARP_TW_ENTRIES)
+
+// ---- twiddle staging (one cp.async batch per job) ------------------------------------------------
+// pass A: entries [0,128) of the prime's table (tw[m+g], m+g < 128)
+HD void stage_tw_A(Tw *dst, const Tw *table, int lane) {
+  _Pragma("unroll")
+  for (int i = 0; i < 4; i++) cp_async16(dst + lane + 32 * i, table + lane + 32 * i);
+}
+// pass B, row r: local entry (2^k - 1 + g) <- table[(128 << k) + (r << k) + g],  k < 8, g < 2^k
+// `tid`/`nthr`: the threads sharing the copy (one warp: lane/32; a 4-warp MAC job: threadIdx.x/128)
+HD void stage_tw_B(Tw *dst, const Tw *table, int r, int tid, int nthr = 32) {
+  _Pragma("unroll")
+  for (int i = 0; i < 8; i++) {
+    const int e = tid + nthr * i; // 0..255 (255 unused)
+    if (i * nthr < 256 && e < 255) {
+      int k = 0;
+      _Pragma("unroll")
+      for (int b = 1; b < 8; b++) k += ((e + 1) >> b) ? 1 : 0; // floor(log2(e+1))
+      const int g = e + 1 - (1 << k);
+      cp_async16(dst + e, table + (128 << k) + (r << k) + g);
+    }
+  }
+}
 
 // =====================================================================================
 // Pass A (strided): tile = 128 rows x 4 cols, tile index = row*4 + col.
@@ -90,64 +120,67 @@ template <int LOGB> struct TileB {
 //   layout S  ("stage lanes"):     x[e] <-> row = (lane>>2)*16 + e,      col = lane&3, idx = (lane>>2)*64 + e*4 + (lane&3)
 // forward: stages 0-3 in layout R (row bits 6..3), stages 4-6 in layout S (row bits 2..0)
 // inverse: row gaps 1,2,4 in layout S, row gaps 8..64 in layout R (last one carries N^-1)
+// `tw` points at the staged table (entries 0..127 of the prime's table).
 // =====================================================================================
 HD int rowR(int lane, int e) { return e * 8 + (lane >> 2); }
 HD int rowS(int lane, int e) { return (lane >> 2) * 16 + e; }
 HD int idxR(int lane, int e) { return e * 32 + lane; }
 HD int idxS(int lane, int e) { return (lane >> 2) * 64 + e * 4 + (lane & 3); }
 
+// in: < 2q   out: < 10q
 HD void fwdA_stages_R(u64 (&x)[16], const Tw *tw, u64 q, u64 q2) {
-_Pragma("unroll")
+  _Pragma("unroll")
   for (int s = 0; s < 4; s++) {
     const int half = 8 >> s;
     Tw t[8];
-_Pragma("unroll")
+    _Pragma("unroll")
     for (int g = 0; g < (1 << s); g++) t[g] = ldtw(tw + (1 << s) + g);
-_Pragma("unroll")
+    _Pragma("unroll")
     for (int e = 0; e < 16; e++)
-      if (!(e & half)) ct_bfly(x[e], x[e + half], t[e >> (4 - s)], q, q2);
+      if (!(e & half)) ct_bfly_lazy(x[e], x[e + half], t[e >> (4 - s)], q, q2);
   }
 }
+// in: < 2q   out: < 8q
 HD void fwdA_stages_S(u64 (&x)[16], int lane, const Tw *tw, u64 q, u64 q2) {
   const int rbase = (lane >> 2) * 16;
-_Pragma("unroll")
+  _Pragma("unroll")
   for (int s = 4; s < 7; s++) {
     const int half = 1 << (6 - s);
-_Pragma("unroll")
+    _Pragma("unroll")
     for (int e = 0; e < 16; e++)
       if (!(e & half)) {
         Tw t = ldtw(tw + (1 << s) + ((rbase + e) >> (7 - s)));
-        ct_bfly(x[e], x[e + half], t, q, q2);
+        ct_bfly_lazy(x[e], x[e + half], t, q, q2);
       }
   }
 }
-// inverse, layout S: row gaps 1,2,4  (m = 64,32,16 groups)
-HD void invA_stages_S(u64 (&x)[16], int lane, const Tw *itw, u64 q, u64 q2) {
+// inverse, layout S: row gaps 1,2,4  (m = 64,32,16 groups); in/out < 2q
+HD void invA_stages_S(u64 (&x)[16], int lane, const Tw *itw, u64 q, u64 q2, u64 dl) {
   const int rbase = (lane >> 2) * 16;
-_Pragma("unroll")
+  _Pragma("unroll")
   for (int j = 0; j < 3; j++) {
     const int half = 1 << j;
-_Pragma("unroll")
+    _Pragma("unroll")
     for (int e = 0; e < 16; e++)
       if (!(e & half)) {
         Tw t = ldtw(itw + (64 >> j) + ((rbase + e) >> (j + 1)));
-        gs_bfly(x[e], x[e + half], t, q, q2);
+        gs_bfly_fold(x[e], x[e + half], t, q, q2, dl);
       }
   }
 }
 // inverse, layout R: row gaps 8,16,32,64 (m = 8,4,2,1); the last stage applies N^-1; output canonical
-HD void invA_stages_R(u64 (&x)[16], const Tw *itw, u64 q, u64 q2, Tw invn, Tw invn_w) {
-_Pragma("unroll")
+HD void invA_stages_R(u64 (&x)[16], const Tw *itw, u64 q, u64 q2, u64 dl, Tw invn, Tw invn_w) {
+  _Pragma("unroll")
   for (int j = 3; j < 6; j++) {
     const int half = 1 << (j - 3);
     Tw t[8];
-_Pragma("unroll")
+    _Pragma("unroll")
     for (int g = 0; g < (64 >> j); g++) t[g] = ldtw(itw + (64 >> j) + g);
-_Pragma("unroll")
+    _Pragma("unroll")
     for (int e = 0; e < 16; e++)
-      if (!(e & half)) gs_bfly(x[e], x[e + half], t[e >> (j - 2)], q, q2);
+      if (!(e & half)) gs_bfly_fold(x[e], x[e + half], t[e >> (j - 2)], q, q2, dl);
   }
-_Pragma("unroll")
+  _Pragma("unroll")
   for (int e = 0; e < 8; e++) {
     u64 u = x[e], v = x[e + 8];
     x[e] = csub(shoup_lazy(u + v, invn, q), q);
@@ -156,93 +189,93 @@ _Pragma("unroll")
 }
 
 // =====================================================================================
-// Pass B (contiguous): a row of 2^LOGB values, E = 2^LOGB/32 per lane, row index r in [0,128).
+// Pass B (contiguous): a row of 256 values, 8 per lane, row index r in [0,128).
 //   layout H ("high bits in registers"): x[e] <-> idx = e*32 + lane
-//   layout M ("middle bits in registers", LOGB=8): idx = hi*32 + e*4 + (lane&3), hi = ((lane>>2)&3)*2 + (lane>>4)
-//   layout C ("consecutive"):            x[e] <-> idx = lane*E + e
-// forward LOGB=8: stages k=0..2 in H (distance 128,64,32), k=3..5 in M (16,8,4), k=6,7 in C (2,1)
-// inverse LOGB=8: gaps 1,2 in C; 4,8,16 in M; 32,64,128 in H
-// twiddle of local stage k, local group g:  tw[(128<<k) + (r<<k) + g]
+//   layout M ("middle bits in registers"): idx = hi*32 + e*4 + (lane&3), hi = ((lane>>2)&3)*2 + (lane>>4)
+//   layout C ("consecutive"):            x[e] <-> idx = lane*8 + e
+// forward: stages k=0..2 in H (distance 128,64,32), k=3..5 in M (16,8,4), k=6,7 in C (2,1)
+// inverse: gaps 1,2 in C; 4,8,16 in M; 32,64,128 in H
+// `tw` points at the staged row table: entry (2^k - 1 + g) = twiddle of local stage k, local group g.
 // =====================================================================================
 HD int idxH(int lane, int e) { return e * 32 + lane; }
 HD int idxM8(int lane, int e) { return ((((lane >> 2) & 3) * 2 + (lane >> 4)) << 5) + e * 4 + (lane & 3); }
 HD int idxC8(int lane, int e) { return lane * 8 + e; }
 
-HD void fwdB8_stages_H(u64 (&x)[8], int r, const Tw *tw, u64 q, u64 q2) {
-_Pragma("unroll")
+HD void fwdB8_stages_H(u64 (&x)[8], const Tw *tw, u64 q, u64 q2) { // in < 2q, out < 8q
+  _Pragma("unroll")
   for (int k = 0; k < 3; k++) {
     const int half = 4 >> k;
     Tw t[4];
-_Pragma("unroll")
-    for (int g = 0; g < (1 << k); g++) t[g] = ldtw(tw + (128 << k) + (r << k) + g);
-_Pragma("unroll")
+    _Pragma("unroll")
+    for (int g = 0; g < (1 << k); g++) t[g] = ldtw(tw + ((1 << k) - 1) + g);
+    _Pragma("unroll")
     for (int e = 0; e < 8; e++)
-      if (!(e & half)) ct_bfly(x[e], x[e + half], t[e >> (3 - k)], q, q2);
+      if (!(e & half)) ct_bfly_lazy(x[e], x[e + half], t[e >> (3 - k)], q, q2);
   }
 }
-HD void fwdB8_stages_M(u64 (&x)[8], int lane, int r, const Tw *tw, u64 q, u64 q2) {
+HD void fwdB8_stages_M(u64 (&x)[8], int lane, const Tw *tw, u64 q, u64 q2) { // in < 2q, out < 8q
   const int base = idxM8(lane, 0);
-_Pragma("unroll")
+  _Pragma("unroll")
   for (int k = 3; k < 6; k++) {
     const int half = 4 >> (k - 3);
-_Pragma("unroll")
+    _Pragma("unroll")
     for (int e = 0; e < 8; e++)
       if (!(e & half)) {
-        Tw t = ldtw(tw + (128 << k) + (r << k) + ((base + e * 4) >> (8 - k)));
-        ct_bfly(x[e], x[e + half], t, q, q2);
+        Tw t = ldtw(tw + ((1 << k) - 1) + ((base + e * 4) >> (8 - k)));
+        ct_bfly_lazy(x[e], x[e + half], t, q, q2);
       }
   }
 }
-HD void fwdB8_stages_C(u64 (&x)[8], int lane, int r, const Tw *tw, u64 q, u64 q2) {
+HD void fwdB8_stages_C(u64 (&x)[8], int lane, const Tw *tw, u64 q, u64 q2) { // in < 2q, out < 6q
   const int base = lane * 8;
-_Pragma("unroll")
+  _Pragma("unroll")
   for (int k = 6; k < 8; k++) {
     const int half = 2 >> (k - 6);
-_Pragma("unroll")
+    _Pragma("unroll")
     for (int e = 0; e < 8; e++)
       if (!(e & half)) {
-        Tw t = ldtw(tw + (128 << k) + (r << k) + ((base + e) >> (8 - k)));
-        ct_bfly(x[e], x[e + half], t, q, q2);
+        Tw t = ldtw(tw + ((1 << k) - 1) + ((base + e) >> (8 - k)));
+        ct_bfly_lazy(x[e], x[e + half], t, q, q2);
       }
   }
 }
-// inverse: gap 2^j, m_loc = 128>>j, twiddle itw[128*m_loc + r*m_loc + (idx >> (j+1))]
-HD void invB8_stages_C(u64 (&x)[8], int lane, int r, const Tw *itw, u64 q, u64 q2) {
+// inverse: gap 2^j <-> m_loc = 128>>j groups, staged entry (m_loc - 1 + group); in/out < 2q
+HD void invB8_stages_C(u64 (&x)[8], int lane, const Tw *itw, u64 q, u64 q2, u64 dl) {
   const int base = lane * 8;
-_Pragma("unroll")
+  _Pragma("unroll")
   for (int j = 0; j < 2; j++) {
     const int half = 1 << j, ml = 128 >> j;
-_Pragma("unroll")
+    _Pragma("unroll")
     for (int e = 0; e < 8; e++)
       if (!(e & half)) {
-        Tw t = ldtw(itw + 128 * ml + r * ml + ((base + e) >> (j + 1)));
-        gs_bfly(x[e], x[e + half], t, q, q2);
+        Tw t = ldtw(itw + (ml - 1) + ((base + e) >> (j + 1)));
+        gs_bfly_fold(x[e], x[e + half], t, q, q2, dl);
       }
   }
 }
-HD void invB8_stages_M(u64 (&x)[8], int lane, int r, const Tw *itw, u64 q, u64 q2) {
+HD void invB8_stages_M(u64 (&x)[8], int lane, const Tw *itw, u64 q, u64 q2, u64 dl) {
   const int base = idxM8(lane, 0);
-_Pragma("unroll")
+  _Pragma("unroll")
   for (int j = 2; j < 5; j++) {
     const int half = 1 << (j - 2), ml = 128 >> j;
-_Pragma("unroll")
+    _Pragma("unroll")
     for (int e = 0; e < 8; e++)
       if (!(e & half)) {
-        Tw t = ldtw(itw + 128 * ml + r * ml + ((base + e * 4) >> (j + 1)));
-        gs_bfly(x[e], x[e + half], t, q, q2);
+        Tw t = ldtw(itw + (ml - 1) + ((base + e * 4) >> (j + 1)));
+        gs_bfly_fold(x[e], x[e + half], t, q, q2, dl);
       }
   }
 }
-HD void invB8_stages_H(u64 (&x)[8], int r, const Tw *itw, u64 q, u64 q2) {
-_Pragma("unroll")
+HD void invB8_stages_H(u64 (&x)[8], const Tw *itw, u64 q, u64 q2, u64 dl) {
+  _Pragma("unroll")
   for (int j = 5; j < 8; j++) {
     const int half = 1 << (j - 5), ml = 128 >> j;
     Tw t[4];
-_Pragma("unroll")
-    for (int g = 0; g < ml; g++) t[g] = ldtw(itw + 128 * ml + r * ml + g);
-_Pragma("unroll")
+    _Pragma("unroll")
+    for (int g = 0; g < ml; g++) t[g] = ldtw(itw + (ml - 1) + g);
+    _Pragma("unroll")
     for (int e = 0; e < 8; e++)
-      if (!(e & half)) gs_bfly(x[e], x[e + half], t[e >> (j - 4)], q, q2);
+      if (!(e & half)) gs_bfly_fold(x[e], x[e + half], t[e >> (j - 4)], q, q2, dl);
   }
 }
 
@@ -257,90 +290,92 @@ struct LaneB8 {
 };
 
 // =====================================================================================
-// Warp-level pass bodies.  `sm` is the warp-private shared tile (WARP_SMEM_WORDS words).
+// Warp-level pass bodies.  `sm` = warp-private tile (WARP_TILE_WORDS words); `tw` = staged twiddles.
 // =====================================================================================
 
-// forward pass A on values already held in layout R by st[].y (lazy < 4q); result -> dst tile
+// forward pass A on values already held in layout R by st[].y (< 2q); result (< 8q) -> dst tile
 // (128 rows x 4 cols at column c0 of the limb `dst`, row pitch = 2^LOGB)
 template <int LOGB>
-HD void warp_fwdA_from_regs(LaneA *st, u64 *sm, u64 *dst, int c0, const Tw *tw, u64 q) {
-  const u64 q2 = 2 * q;
+HD void warp_fwdA_from_regs(LaneA *st, u64 *sm, u64 *dst, int c0, const Tw *tw, const ModQ &m) {
+  const u64 q = m.q, q2 = 2 * m.q, dl = m.delta;
   LANE_DECL;
   FOR_LANES(S, st, {
     fwdA_stages_R(S.y, tw, q, q2);
-_Pragma("unroll")
-    for (int e = 0; e < 16; e++) sm[padx(idxR(lane, e))] = S.y[e];
+    _Pragma("unroll")
+    for (int e = 0; e < 16; e++) sm[padx(idxR(lane, e))] = fold60(S.y[e], dl);
   });
   FOR_LANES(S, st, {
-_Pragma("unroll")
+    _Pragma("unroll")
     for (int e = 0; e < 16; e++) S.y[e] = sm[padx(idxS(lane, e))];
     fwdA_stages_S(S.y, lane, tw, q, q2);
-_Pragma("unroll")
+    _Pragma("unroll")
     for (int e = 0; e < 16; e++) dst[((size_t)rowS(lane, e) << LOGB) + c0 + (lane & 3)] = S.y[e];
   });
 }
 
-// inverse pass A: src tile (layout S load) -> canonical coefficients in st[].x, layout R
+// inverse pass A: src tile (layout S load, values < 2q) -> canonical coefficients in st[].x, layout R
 template <int LOGB>
-HD void warp_invA_to_regs(LaneA *st, u64 *sm, const u64 *src, int c0, const Tw *itw, u64 q, Tw invn, Tw invn_w) {
-  const u64 q2 = 2 * q;
+HD void warp_invA_to_regs(LaneA *st, u64 *sm, const u64 *src, int c0, const Tw *itw, const ModQ &m, Tw invn, Tw invn_w) {
+  const u64 q = m.q, q2 = 2 * m.q, dl = m.delta;
   LANE_DECL;
   FOR_LANES(S, st, {
-_Pragma("unroll")
+    _Pragma("unroll")
     for (int e = 0; e < 16; e++) S.x[e] = ldg_stream(src + ((size_t)rowS(lane, e) << LOGB) + c0 + (lane & 3));
-    invA_stages_S(S.x, lane, itw, q, q2);
-_Pragma("unroll")
+    invA_stages_S(S.x, lane, itw, q, q2, dl);
+    _Pragma("unroll")
     for (int e = 0; e < 16; e++) sm[padx(idxS(lane, e))] = S.x[e];
   });
   FOR_LANES(S, st, {
-_Pragma("unroll")
+    _Pragma("unroll")
     for (int e = 0; e < 16; e++) S.x[e] = sm[padx(idxR(lane, e))];
-    invA_stages_R(S.x, itw, q, q2, invn, invn_w);
+    invA_stages_R(S.x, itw, q, q2, dl, invn, invn_w);
   });
 }
 
-// forward pass B, LOGB = 8: values in st[].x layout H (lazy < 4q) -> st[].x layout C (lazy < 4q)
-HD void warp_fwdB8_regs(LaneB8 *st, u64 *sm, int r, const Tw *tw, u64 q) {
-  const u64 q2 = 2 * q;
+// forward pass B: values in st[].x layout H (any lazy bound) -> st[].x layout C (< 6q)
+HD void warp_fwdB8_regs(LaneB8 *st, u64 *sm, const Tw *tw, const ModQ &m) {
+  const u64 q = m.q, q2 = 2 * m.q, dl = m.delta;
   LANE_DECL;
   FOR_LANES(S, st, {
-    fwdB8_stages_H(S.x, r, tw, q, q2);
-_Pragma("unroll")
-    for (int e = 0; e < 8; e++) sm[padx(idxH(lane, e))] = S.x[e];
+    _Pragma("unroll")
+    for (int e = 0; e < 8; e++) S.x[e] = fold60(S.x[e], dl);
+    fwdB8_stages_H(S.x, tw, q, q2);
+    _Pragma("unroll")
+    for (int e = 0; e < 8; e++) sm[padx(idxH(lane, e))] = fold60(S.x[e], dl);
   });
   FOR_LANES(S, st, {
-_Pragma("unroll")
+    _Pragma("unroll")
     for (int e = 0; e < 8; e++) S.x[e] = sm[padx(idxM8(lane, e))];
-    fwdB8_stages_M(S.x, lane, r, tw, q, q2);
-_Pragma("unroll")
-    for (int e = 0; e < 8; e++) sm[padx(idxM8(lane, e))] = S.x[e];
+    fwdB8_stages_M(S.x, lane, tw, q, q2);
+    _Pragma("unroll")
+    for (int e = 0; e < 8; e++) sm[padx(idxM8(lane, e))] = fold60(S.x[e], dl);
   });
   FOR_LANES(S, st, {
-_Pragma("unroll")
+    _Pragma("unroll")
     for (int e = 0; e < 8; e++) S.x[e] = sm[padx(idxC8(lane, e))];
-    fwdB8_stages_C(S.x, lane, r, tw, q, q2);
+    fwdB8_stages_C(S.x, lane, tw, q, q2);
   });
 }
-// inverse pass B, LOGB = 8: st[].x layout C (values < 2q) -> st[].x layout H (lazy < 2q)
-HD void warp_invB8_regs(LaneB8 *st, u64 *sm, int r, const Tw *itw, u64 q) {
-  const u64 q2 = 2 * q;
+// inverse pass B: st[].x layout C (values < 2q) -> st[].x layout H (< 2q)
+HD void warp_invB8_regs(LaneB8 *st, u64 *sm, const Tw *itw, const ModQ &m) {
+  const u64 q = m.q, q2 = 2 * m.q, dl = m.delta;
   LANE_DECL;
   FOR_LANES(S, st, {
-    invB8_stages_C(S.x, lane, r, itw, q, q2);
-_Pragma("unroll")
+    invB8_stages_C(S.x, lane, itw, q, q2, dl);
+    _Pragma("unroll")
     for (int e = 0; e < 8; e++) sm[padx(idxC8(lane, e))] = S.x[e];
   });
   FOR_LANES(S, st, {
-_Pragma("unroll")
+    _Pragma("unroll")
     for (int e = 0; e < 8; e++) S.x[e] = sm[padx(idxM8(lane, e))];
-    invB8_stages_M(S.x, lane, r, itw, q, q2);
-_Pragma("unroll")
+    invB8_stages_M(S.x, lane, itw, q, q2, dl);
+    _Pragma("unroll")
     for (int e = 0; e < 8; e++) sm[padx(idxM8(lane, e))] = S.x[e];
   });
   FOR_LANES(S, st, {
-_Pragma("unroll")
+    _Pragma("unroll")
     for (int e = 0; e < 8; e++) S.x[e] = sm[padx(idxH(lane, e))];
-    invB8_stages_H(S.x, r, itw, q, q2);
+    invB8_stages_H(S.x, itw, q, q2, dl);
   });
 }
 

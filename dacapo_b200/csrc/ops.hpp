@@ -98,7 +98,7 @@ template <class LA> struct HeOps {
       ArgsFwdB x{};
       x.T = T, x.src = sc.s2, x.dst = sc.acc, x.l = l, x.sp = sp(), x.key = key, x.Ltot = L, x.ld = mode, x.elt = elt;
       x.tgt = a + pitch, x.tgt2 = (mode == LD_PRODUCT) ? b + pitch : nullptr;
-      la.template fwd_B<EPI_MAC>(x, (l + 1) * ROWS);
+      la.mac(x, (l + 1) * ROWS);
     }
     // 4. mod-down by the special prime with rounding, fused with the final accumulate
     {

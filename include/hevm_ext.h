@@ -41,6 +41,7 @@ int64_t hevmx_galois_elt(void *vm, int64_t step);
 const char *hevmx_backend(void);
 /* --- libB200_HEVM.so only (measurement; not part of the oracle) --- */
 double hevmx_timer(void *vm, int which);        /* CUDA events on the VM stream: 0 start, 1 stop -> ms */
+void hevmx_profiler_range(void *vm, int on);  /* cudaProfilerStart/Stop (ncu --profile-from-start off) */
 void hevmx_profile(void *vm, int on);           /* per-kernel-class CUDA-event timing */
 const char *hevmx_profile_read(void *vm, int cls, double *ms, int64_t *count); /* NULL past the last class */
 
