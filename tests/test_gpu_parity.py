@@ -252,4 +252,4 @@ def test_full_size_properties(pair):
     assert np.max(np.abs(g.decrypt_decode(5, 1) - np.roll(x + y, 300))) < 1e-4
     g.exec(asm.MULCC, 6, 0, 4)
     g.exec(asm.RESCALE, 6, 6)
-    assert np.max(np.abs(g.decrypt_decode(6, 1) - x * y)) < 1e-4  # scale 2^80/q ~ 2^20 after rescale
+    assert np.max(np.abs(g.decrypt_decode(6, 1) - x * y)) < 5e-3  # scale 2^80/q ~ 2^20 after rescale: noise ~1e-4..1e-3
