@@ -13,7 +13,8 @@ unsigned long long g_launch_count = 0;
 KProfiler g_prof;
 const char *const g_kernel_class_names[KC_COUNT] = {
     "intt_B_plain", "intt_B_galois", "intt_B_product", "intt_A", "fwd_A_plain", "fwd_A_modup", "fwd_A_round",
-    "fwd_B_canon", "fwd_B_mac", "fwd_B_moddown_galois", "fwd_B_moddown_relin", "fwd_B_rescale", "elementwise", "other"};
+    "fwd_B_canon", "fwd_B_mac", "fwd_B_moddown_galois", "fwd_B_moddown_relin", "fwd_B_rescale", "invA_fwdA_modup",
+    "invA_fwdA_round", "elementwise", "other"};
 cudaEvent_t KProfiler::ev() {
   if (used == pool.size()) {
     cudaEvent_t e;
@@ -77,11 +78,15 @@ template <int EPI> __global__ void __launch_bounds__(CTA_THREADS) k_fwd_B(ArgsFw
   WARP_KERNEL_PROLOGUE(LaneB8)
   body_fwd_B<EPI>(a, job, st, sm[warp]);
 }
+template <int PRE> __global__ void __launch_bounds__(CTA_THREADS, 4) k_invA_fwdA(ArgsInvFwdA a, int njobs) {
+  WARP_KERNEL_PROLOGUE(LaneA)
+  body_invA_fwdA<PRE>(a, job, st, sm[warp]);
+}
 // key-switch inner product: CTA = one (output prime, row) job, its MAC_WARPS warps split the digits
 __global__ void __launch_bounds__(MAC_WARPS * 32, 3) k_mac(ArgsFwdB a) {
   __shared__ __align__(16) u64 sm[MAC_SMEM_WORDS];
   Tw *tw_s = reinterpret_cast<Tw *>(sm);
-  u64 *tiles = sm + 2 * WARP_TW_ENTRIES;
+  u64 *tiles = sm + MAC_TW_WORDS;
   u64 *parts = tiles + MAC_WARPS * TILE_B_WORDS;
   const int job = blockIdx.x, warp = threadIdx.x >> 5;
   body_mac_stage(a, job, threadIdx.x, tw_s);
@@ -89,10 +94,26 @@ __global__ void __launch_bounds__(MAC_WARPS * 32, 3) k_mac(ArgsFwdB a) {
   LaneB8 st[1];
   body_mac_warp(a, job, warp, st, tiles + warp * TILE_B_WORDS, tw_s, parts + warp * MAC_PART_WORDS);
   __syncthreads();
-  body_mac_reduce(a, job, threadIdx.x, parts);
+  body_mac_reduce(a, job, threadIdx.x, parts, tiles);
+  if (mac_Iidx(a, job) == a.l) { // special prime: continue with the inverse pass B of the two accumulator rows
+    __syncthreads();
+    if (warp < 2) body_mac_tail(a, job, warp, st, parts + warp * MAC_PART_WORDS, tw_s, tiles);
+  }
 }
 
 static inline int ctas_for(int njobs) { return (njobs + WARPS_PER_CTA - 1) / WARPS_PER_CTA; }
+// launch with programmatic stream serialization: the kernel may begin (twiddle staging) while its
+// predecessor drains; every such kernel executes griddepcontrol.wait before touching global data
+template <class... KArgs, class... Args>
+static void launch_pdl(void (*kern)(KArgs...), int grid, int block, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(block), cfg.dynamicSmemBytes = 0, cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at, cfg.numAttrs = 1;
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, args...));
+}
 #define PRE_LAUNCH(s, cls) g_prof.begin(s, cls)
 #define POST_LAUNCH_S(s)                                                                                               \
   do {                                                                                                                 \
@@ -104,33 +125,41 @@ static inline int ctas_for(int njobs) { return (njobs + WARPS_PER_CTA - 1) / WAR
 template <int LD> void GpuLauncher::intt_B(const ArgsInttB &a, int njobs) {
   if (njobs <= 0) return;
   PRE_LAUNCH(stream, KC_INTT_B_PLAIN + LD);
-  k_intt_B<LD><<<ctas_for(njobs), CTA_THREADS, 0, stream>>>(a, njobs);
+  launch_pdl(k_intt_B<LD>, ctas_for(njobs), CTA_THREADS, stream, a, njobs);
   POST_LAUNCH_S(stream);
 }
 void GpuLauncher::intt_A(const ArgsInttA &a, int njobs) {
   if (njobs <= 0) return;
   PRE_LAUNCH(stream, KC_INTT_A);
-  k_intt_A<<<ctas_for(njobs), CTA_THREADS, 0, stream>>>(a, njobs);
+  launch_pdl(k_intt_A, ctas_for(njobs), CTA_THREADS, stream, a, njobs);
   POST_LAUNCH_S(stream);
 }
 template <int PRE> void GpuLauncher::fwd_A(const ArgsFwdA &a, int njobs) {
   if (njobs <= 0) return;
   PRE_LAUNCH(stream, KC_FWD_A_NONE + PRE);
-  k_fwd_A<PRE><<<ctas_for(njobs), CTA_THREADS, 0, stream>>>(a, njobs);
+  launch_pdl(k_fwd_A<PRE>, ctas_for(njobs), CTA_THREADS, stream, a, njobs);
   POST_LAUNCH_S(stream);
 }
 template <int EPI> void GpuLauncher::fwd_B(const ArgsFwdB &a, int njobs) {
   if (njobs <= 0) return;
   PRE_LAUNCH(stream, KC_FWD_B_CANON + EPI);
-  k_fwd_B<EPI><<<ctas_for(njobs), CTA_THREADS, 0, stream>>>(a, njobs);
+  launch_pdl(k_fwd_B<EPI>, ctas_for(njobs), CTA_THREADS, stream, a, njobs);
   POST_LAUNCH_S(stream);
 }
 void GpuLauncher::mac(const ArgsFwdB &a, int njobs) {
   if (njobs <= 0) return;
   PRE_LAUNCH(stream, KC_FWD_B_MAC);
-  k_mac<<<njobs, MAC_WARPS * 32, 0, stream>>>(a);
+  launch_pdl(k_mac, njobs, MAC_WARPS * 32, stream, a);
   POST_LAUNCH_S(stream);
 }
+template <int PRE> void GpuLauncher::invA_fwdA(const ArgsInvFwdA &a, int njobs) {
+  if (njobs <= 0) return;
+  PRE_LAUNCH(stream, PRE == PRE_MODUP ? KC_INVA_FWDA_MODUP : KC_INVA_FWDA_ROUND);
+  launch_pdl(k_invA_fwdA<PRE>, ctas_for(njobs), CTA_THREADS, stream, a, njobs);
+  POST_LAUNCH_S(stream);
+}
+template void GpuLauncher::invA_fwdA<PRE_MODUP>(const ArgsInvFwdA &, int);
+template void GpuLauncher::invA_fwdA<PRE_ROUND>(const ArgsInvFwdA &, int);
 template void GpuLauncher::intt_B<LD_PLAIN>(const ArgsInttB &, int);
 template void GpuLauncher::intt_B<LD_GALOIS>(const ArgsInttB &, int);
 template void GpuLauncher::intt_B<LD_PRODUCT>(const ArgsInttB &, int);

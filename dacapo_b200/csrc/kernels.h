@@ -22,7 +22,7 @@ extern unsigned long long g_launch_count;
 // Optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline).
 enum {
   KC_INTT_B_PLAIN = 0, KC_INTT_B_GALOIS, KC_INTT_B_PRODUCT, KC_INTT_A, KC_FWD_A_NONE, KC_FWD_A_MODUP, KC_FWD_A_ROUND,
-  KC_FWD_B_CANON, KC_FWD_B_MAC, KC_FWD_B_MODDOWN_GALOIS, KC_FWD_B_MODDOWN_RELIN, KC_FWD_B_RESCALE, KC_ELEMENTWISE,
+  KC_FWD_B_CANON, KC_FWD_B_MAC, KC_FWD_B_MODDOWN_GALOIS, KC_FWD_B_MODDOWN_RELIN, KC_FWD_B_RESCALE, KC_INVA_FWDA_MODUP, KC_INVA_FWDA_ROUND, KC_ELEMENTWISE,
   KC_OTHER, KC_COUNT
 };
 extern const char *const g_kernel_class_names[KC_COUNT];
@@ -48,6 +48,7 @@ struct GpuLauncher {
   void intt_A(const ArgsInttA &a, int njobs);
   template <int PRE> void fwd_A(const ArgsFwdA &a, int njobs);
   template <int EPI> void fwd_B(const ArgsFwdB &a, int njobs);
+  template <int PRE> void invA_fwdA(const ArgsInvFwdA &a, int njobs);
   void mac(const ArgsFwdB &a, int njobs); // one 4-warp CTA per job
 };
 

@@ -38,7 +38,8 @@ HD u64 mulhi64(u64 a, u64 b) {
 }
 
 // x * w mod q, result in [0, 2q) for ANY 64-bit x (Shoup / Harvey lazy product)
-HD u64 shoup_lazy(u64 x, Tw t, u64 q) { return x * t.w - mulhi64(x, t.wq) * q; }
+// written as x*w + Q*(2^64 - q) so that both low products chain into one multiply-add sequence
+HD u64 shoup_lazy(u64 x, Tw t, u64 q) { return x * t.w + mulhi64(x, t.wq) * (0 - q); }
 HD u64 csub(u64 x, u64 m) { // x in [0,2m) -> [0,m)
   u64 y = x - m;
   return y < x ? y : x; // unsigned wrap: x < m  =>  y > x

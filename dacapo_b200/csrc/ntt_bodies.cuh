@@ -29,7 +29,8 @@ enum { EPI_CANON = 0, EPI_MAC = 1, EPI_MODDOWN_GALOIS = 2, EPI_MODDOWN_RELIN = 3
 #define MAC_PART_WORDS 1024 // per warp: 2 keys x 256 values x (lo,hi)
 // shared memory of one MAC CTA (words): staged twiddles | MAC_WARPS tiles | MAC_WARPS partial-sum blocks
 #define TILE_B_WORDS 272 // 256 values + 256/16 padding
-#define MAC_SMEM_WORDS (2 * WARP_TW_ENTRIES + MAC_WARPS * TILE_B_WORDS + MAC_WARPS * MAC_PART_WORDS)
+#define MAC_TW_WORDS 512  // 256 staged twiddles
+#define MAC_SMEM_WORDS (MAC_TW_WORDS + MAC_WARPS * TILE_B_WORDS + MAC_WARPS * MAC_PART_WORDS)
 
 HD Tw *warp_tw(u64 *sm) { return reinterpret_cast<Tw *>(sm + WARP_TILE_WORDS); }
 
@@ -55,6 +56,7 @@ struct ArgsInttB {
   u64 *pc0;
   int nl, prime0, pstep;
   u32 elt;
+  size_t sstride; // words between consecutive source limbs (0 = N)
 };
 
 template <int LD> HD void body_intt_B(const ArgsInttB &a, int job, LaneB8 *st, u64 *sm) {
@@ -63,11 +65,13 @@ template <int LD> HD void body_intt_B(const ArgsInttB &a, int job, LaneB8 *st, u
   const int limb = job >> 7, r = job & 127;
   const int p = a.prime0 + limb * a.pstep;
   const ModQ m = T.mod[p];
-  const u64 *src = a.src + (size_t)limb * N;
+  const u64 *src = a.src + (size_t)limb * (a.sstride ? a.sstride : (size_t)N);
   Tw *tw = warp_tw(sm);
   LANE_DECL;
   FOR_LANES(S, st, {
+    grid_dep_launch();
     stage_tw_B(tw, T.itw + (size_t)p * N, r, lane);
+    grid_dep_wait();
     const int base = r * 256 + lane * 8;
     if (LD == LD_PLAIN) {
       load8_stream(src + base, S.x);
@@ -119,7 +123,9 @@ HD void body_intt_A(const ArgsInttA &a, int job, LaneA *st, u64 *sm) {
   LANE_DECL;
   FOR_LANES(S, st, {
     (void)S;
+    grid_dep_launch();
     stage_tw_A(tw, T.itw + (size_t)p * N, lane);
+    grid_dep_wait();
     cp_async_wait();
   });
   warp_invA_to_regs<LOGB8>(st, sm, a.src + (size_t)limb * N, tile * 4, tw, m, T.invn[p], T.invn_w[p]);
@@ -177,7 +183,9 @@ template <int PRE> HD void body_fwd_A(const ArgsFwdA &a, int job, LaneA *st, u64
   Tw *tw = warp_tw(sm);
   LANE_DECL;
   FOR_LANES(S, st, {
+    grid_dep_launch();
     stage_tw_A(tw, T.tw + (size_t)pd * N, lane);
+    grid_dep_wait();
     _Pragma("unroll")
     for (int e = 0; e < 16; e++) S.y[e] = ldg_stream(src + ((size_t)rowR(lane, e) << LOGB8) + (lane & 3));
     _Pragma("unroll")
@@ -189,6 +197,88 @@ template <int PRE> HD void body_fwd_A(const ArgsFwdA &a, int job, LaneA *st, u64
     cp_async_wait();
   });
   warp_fwdA_from_regs<LOGB8>(st, sm, a.dst + (size_t)d * N, tile * 4, tw, m);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// fused: inverse pass A (+N^-1, canonical) of one source limb tile, then for a group of targets
+// [mod-up reduction | rounding + fix-up] + forward pass A, all on the same 128x4 tile held in
+// registers.  job = ((source limb * ngroups) + group) * 64 + tile.
+//   PRE_MODUP: source limb J (prime J) of s1[l][N]; targets Iidx in [0,l] except the diagonal;
+//              dst s2[Iidx][J]
+//   PRE_ROUND: source limb K (prime plast) of s1[2][N]; x <- (x + q_last/2) mod q_last;
+//              targets i in [0,nlim): dst s4[K][i] <- (x mod q_i) + q_i - (q_last/2 mod q_i)
+// Forward twiddle tables are double-buffered in the warp's staging area (cp.async groups).
+// ---------------------------------------------------------------------------------------------
+struct ArgsInvFwdA {
+  const NttTables *T;
+  const u64 *src;
+  u64 *dst;
+  int nsrc, l, sp, plast, ngroups;
+};
+template <int PRE> HD void body_invA_fwdA(const ArgsInvFwdA &a, int job, LaneA *st, u64 *sm) {
+  const NttTables &T = *a.T;
+  const int N = 1 << T.logN;
+  const int tile = job & 63, rest = job >> 6;
+  const int sl = rest / a.ngroups, grp = rest - sl * a.ngroups;
+  const int ntargets = (PRE == PRE_MODUP) ? a.l + 1 : a.l;
+  const int tpj = (ntargets + a.ngroups - 1) / a.ngroups;
+  const int tend = (grp + 1) * tpj < ntargets ? (grp + 1) * tpj : ntargets;
+  const int ps = (PRE == PRE_MODUP) ? sl : a.plast;
+  const ModQ ms = T.mod[ps];
+  // target slot -> prime (MODUP: slot l is the special prime); -1 when past the end
+  auto prime_of = [&](int t) { return (PRE == PRE_MODUP && t == a.l) ? a.sp : t; };
+  auto next_valid = [&](int t) {
+    while (t < tend && prime_of(t) == ps) t++; // the diagonal is taken from the NTT-form input by the MAC kernel
+    return t;
+  };
+  int t = next_valid(grp * tpj);
+  if (t >= tend) return;
+  Tw *tw_inv = warp_tw(sm), *tw_fwd = tw_inv + 128;
+  int buf = 0;
+  LANE_DECL;
+  FOR_LANES(S, st, {
+    (void)S;
+    grid_dep_launch();
+    stage_tw_A(tw_inv, T.itw + (size_t)ps * N, lane);
+    stage_tw_A(tw_fwd, T.tw + (size_t)prime_of(t) * N, lane);
+    grid_dep_wait();
+    cp_async_wait();
+  });
+  warp_invA_to_regs<LOGB8>(st, sm, a.src + (size_t)sl * N, tile * 4, tw_inv, ms, T.invn[ps], T.invn_w[ps]);
+  if (PRE == PRE_ROUND) {
+    const u64 half = ms.q >> 1;
+    FOR_LANES(S, st, {
+      _Pragma("unroll")
+      for (int e = 0; e < 16; e++) S.x[e] = csub(S.x[e] + half, ms.q);
+    });
+  }
+  while (t < tend) {
+    const int pd = prime_of(t);
+    const int tn = next_valid(t + 1);
+    const ModQ m = T.mod[pd];
+    u64 fix = 0;
+    if (PRE == PRE_ROUND) fix = m.q - reduce64(ms.q >> 1, m);
+    FOR_LANES(S, st, {
+      if (tn < tend) stage_tw_A(tw_fwd + 128 * (buf ^ 1), T.tw + (size_t)prime_of(tn) * N, lane); // prefetch next table
+      cp_async_commit();
+      _Pragma("unroll")
+      for (int e = 0; e < 16; e++) {
+        u64 v = S.x[e];
+        if (ps > pd) v = reduce64(v, m);
+        S.y[e] = v + fix;
+      }
+      cp_async_wait_keep1(); // the current table (older group) has landed
+    });
+    u64 *dst = (PRE == PRE_MODUP) ? a.dst + ((size_t)t * a.l + sl) * N : a.dst + ((size_t)sl * a.l + t) * N;
+    warp_fwdA_from_regs<LOGB8>(st, sm, dst, tile * 4, tw_fwd + 128 * buf, m);
+    buf ^= 1;
+    t = tn;
+  }
+  FOR_LANES(S, st, {
+    (void)S;
+    cp_async_wait();
+  });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -213,22 +303,27 @@ struct ArgsFwdB {
   const u64 *add1;   // RELIN: b (ct)
   size_t pitch;      // poly pitch (words) of ct operands / output
   int plast;         // prime divided out (sp for MODDOWN, l_in-1 for RESCALE)
+  u64 *sp_rows;      // MAC: [2][N] inverse pass-B output of the special-prime accumulators (mod-down input)
 };
 
 // ---- key-switch inner product: one CTA of MAC_WARPS warps per (Iidx, row) ----------------------
 // phase 0 (all threads of the CTA): stage the row's twiddles of prime I
+// job -> (Iidx, row): the special prime (Iidx = l) comes first because its CTAs carry the extra tail
+HD int mac_Iidx(const ArgsFwdB &a, int job) { return a.l - (job >> 7); }
 HD void body_mac_stage(const ArgsFwdB &a, int job, int tid, Tw *tw_s) {
   const NttTables &T = *a.T;
   const int N = 1 << T.logN;
-  const int r = job & 127, Iidx = job >> 7, I = (Iidx == a.l) ? a.sp : Iidx;
+  const int r = job & 127, Iidx = mac_Iidx(a, job), I = (Iidx == a.l) ? a.sp : Iidx;
+  grid_dep_launch();
   stage_tw_B(tw_s, T.tw + (size_t)I * N, r, tid, MAC_WARPS * 32);
+  grid_dep_wait();
   cp_async_wait();
 }
 // phase 1 (per warp): digits J = w, w + MAC_WARPS, ...; partial sums -> part[(K*256 + e*32 + lane)*2 + {lo,hi}]
 HD void body_mac_warp(const ArgsFwdB &a, int job, int w, LaneB8 *st, u64 *tile, const Tw *tw_s, u64 *part) {
   const NttTables &T = *a.T;
   const int N = 1 << T.logN;
-  const int r = job & 127, Iidx = job >> 7, I = (Iidx == a.l) ? a.sp : Iidx;
+  const int r = job & 127, Iidx = mac_Iidx(a, job), I = (Iidx == a.l) ? a.sp : Iidx;
   const ModQ m = T.mod[I];
   LANE_DECL;
   u64 lo0[NLANE_STATE][8], hi0[NLANE_STATE][8], lo1[NLANE_STATE][8], hi1[NLANE_STATE][8];
@@ -295,26 +390,53 @@ HD void body_mac_warp(const ArgsFwdB &a, int job, int w, LaneB8 *st, u64 *tile, 
     }
   });
 }
-// phase 2 (all threads, after a CTA barrier): sum the per-warp partials, Barrett, store acc[K][Iidx][row]
-HD void body_mac_reduce(const ArgsFwdB &a, int job, int tid, const u64 *parts) {
+// phase 2 (all threads, after a CTA barrier): sum the per-warp partials, Barrett.
+// Data primes: store acc[K][Iidx][row].  Special prime: keep the two rows in shared memory (`rows`,
+// [2][256]) for phase 3 instead -- nobody else reads them.
+HD void body_mac_reduce(const ArgsFwdB &a, int job, int tid, const u64 *parts, u64 *rows) {
   const NttTables &T = *a.T;
   const int N = 1 << T.logN;
-  const int r = job & 127, Iidx = job >> 7, I = (Iidx == a.l) ? a.sp : Iidx;
+  const int r = job & 127, Iidx = mac_Iidx(a, job), I = (Iidx == a.l) ? a.sp : Iidx;
   const ModQ m = T.mod[I];
-  const int nw = a.l < MAC_WARPS ? a.l : MAC_WARPS; // warps that own at least one digit
   _Pragma("unroll")
   for (int it = 0; it < 512 / (MAC_WARPS * 32); it++) {
     const int slot = tid + it * MAC_WARPS * 32; // K*256 + e*32 + lane
     u64 lo = 0, hi = 0;
-    for (int w = 0; w < nw; w++) {
+    _Pragma("unroll")
+    for (int w = 0; w < MAC_WARPS; w++) {
       const u64 *p = parts + (size_t)w * MAC_PART_WORDS + (size_t)slot * 2;
       const u64 pl = p[0], ph = p[1];
       lo += pl;
       hi += ph + (lo < pl ? 1 : 0);
     }
     const int K = slot >> 8, e = (slot >> 5) & 7, lane = slot & 31;
-    a.dst[((size_t)K * (a.l + 1) + Iidx) * N + r * 256 + lane * 8 + e] = reduce128(lo, hi, m);
+    const u64 v = reduce128(lo, hi, m);
+    if (Iidx == a.l)
+      rows[K * 256 + lane * 8 + e] = v;
+    else
+      a.dst[((size_t)K * (a.l + 1) + Iidx) * N + r * 256 + lane * 8 + e] = v;
   }
+}
+// phase 3 (special-prime CTAs only, warps K = 0,1, after a CTA barrier): inverse pass B of row r of the
+// accumulator acc[K][special] (first step of the mod-down), straight from shared memory.
+HD void body_mac_tail(const ArgsFwdB &a, int job, int K, LaneB8 *st, u64 *tile, Tw *tw_s, const u64 *rows) {
+  const NttTables &T = *a.T;
+  const int N = 1 << T.logN;
+  const int r = job & 127;
+  const ModQ m = T.mod[a.sp];
+  LANE_DECL;
+  FOR_LANES(S, st, {
+    stage_tw_B(tw_s, T.itw + (size_t)a.sp * N, r, lane); // both warps stage the same table (identical bytes)
+    _Pragma("unroll")
+    for (int e = 0; e < 8; e++) S.x[e] = rows[K * 256 + lane * 8 + e];
+    cp_async_wait();
+  });
+  warp_invB8_regs(st, tile, tw_s, m);
+  u64 *dst = a.sp_rows + (size_t)K * N + r * 256;
+  FOR_LANES(S, st, {
+    _Pragma("unroll")
+    for (int e = 0; e < 8; e++) dst[idxH(lane, e)] = S.x[e];
+  });
 }
 
 template <int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, LaneB8 *st, u64 *sm) {
@@ -328,7 +450,9 @@ template <int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, LaneB8 *st, u6
     const ModQ m = T.mod[p];
     const u64 *src = a.src + (size_t)d * N + r * 256;
     FOR_LANES(S, st, {
+      grid_dep_launch();
       stage_tw_B(tw, T.tw + (size_t)p * N, r, lane);
+      grid_dep_wait();
       _Pragma("unroll")
       for (int e = 0; e < 8; e++) S.x[e] = ldg_stream(src + idxH(lane, e));
       cp_async_wait();
@@ -354,7 +478,11 @@ template <int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, LaneB8 *st, u6
     for (int K = 0; K < 2; K++) {
       const u64 *src = a.src + ((size_t)K * a.l + i) * N + r * 256;
       FOR_LANES(S, st, {
-        if (K == 0) stage_tw_B(tw, T.tw + (size_t)i * N, r, lane);
+        if (K == 0) {
+          grid_dep_launch();
+          stage_tw_B(tw, T.tw + (size_t)i * N, r, lane);
+          grid_dep_wait();
+        }
         if (K == 1) {
           _Pragma("unroll")
           for (int e = 0; e < 8; e++) S.z[e] = S.x[e];
@@ -398,7 +526,9 @@ template <int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, LaneB8 *st, u6
     const u64 q = m.q;
     const u64 *src = a.src + (size_t)d * N + r * 256;
     FOR_LANES(S, st, {
+      grid_dep_launch();
       stage_tw_B(tw, T.tw + (size_t)i * N, r, lane);
+      grid_dep_wait();
       _Pragma("unroll")
       for (int e = 0; e < 8; e++) S.x[e] = ldg_stream(src + idxH(lane, e));
       cp_async_wait();

@@ -59,6 +59,12 @@ HD void cp_async16(void *smem_dst, const void *gsrc) { // LDGSTS: global -> shar
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
 }
 HD void cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+HD void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+HD void cp_async_wait_keep1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); } // all but the newest group
+// Programmatic dependent launch: a kernel may start (and stage its twiddles) while its predecessor
+// drains; it must not touch the predecessor's output before grid_dep_wait().
+HD void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+HD void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // streaming 64-bit / 256-bit accesses (no L1 allocation: each value is touched once per pass)
 HD u64 ldg_stream(const u64 *p) {
   u64 v;
@@ -82,6 +88,10 @@ HD void stg4(u64 *p, u64 a, u64 b, u64 c, u64 d) {
 HD Tw ldtw(const Tw *p) { return *p; }
 HD void cp_async16(void *smem_dst, const void *gsrc) { *(Tw *)smem_dst = *(const Tw *)gsrc; }
 HD void cp_async_wait() {}
+HD void cp_async_commit() {}
+HD void cp_async_wait_keep1() {}
+HD void grid_dep_wait() {}
+HD void grid_dep_launch() {}
 HD u64 ldg_stream(const u64 *p) { return *p; }
 HD void ldg_stream4(const u64 *p, u64 &a, u64 &b, u64 &c, u64 &d) { a = p[0], b = p[1], c = p[2], d = p[3]; }
 HD void stg4(u64 *p, u64 a, u64 b, u64 c, u64 d) { p[0] = a, p[1] = b, p[2] = c, p[3] = d; }
@@ -89,7 +99,7 @@ HD void stg4(u64 *p, u64 a, u64 b, u64 c, u64 d) { p[0] = a, p[1] = b, p[2] = c,
 
 HD int padx(int idx) { return idx + (idx >> 4); }
 #define WARP_TILE_WORDS 544  // 512 values + 512/16 padding
-#define WARP_TW_ENTRIES 256  // staged twiddles (pass A uses 128, pass B 255)
+#define WARP_TW_ENTRIES 384  // staged twiddles: pass B 255; fused inverse+forward pass A 128 + 2x128
 #define WARP_SMEM_WORDS (WARP_TILE_WORDS + 2 * WARP_TW_ENTRIES)
 
 // ---- twiddle staging (one cp.async batch per job) ------------------------------------------------
@@ -173,12 +183,12 @@ HD void invA_stages_R(u64 (&x)[16], const Tw *itw, u64 q, u64 q2, u64 dl, Tw inv
   _Pragma("unroll")
   for (int j = 3; j < 6; j++) {
     const int half = 1 << (j - 3);
-    Tw t[8];
-    _Pragma("unroll")
-    for (int g = 0; g < (64 >> j); g++) t[g] = ldtw(itw + (64 >> j) + g);
     _Pragma("unroll")
     for (int e = 0; e < 16; e++)
-      if (!(e & half)) gs_bfly_fold(x[e], x[e + half], t[e >> (j - 2)], q, q2, dl);
+      if (!(e & half)) {
+        const Tw t = ldtw(itw + (64 >> j) + (e >> (j - 2))); // warp-uniform address: broadcast LDS.128
+        gs_bfly_fold(x[e], x[e + half], t, q, q2, dl);
+      }
   }
   _Pragma("unroll")
   for (int e = 0; e < 8; e++) {

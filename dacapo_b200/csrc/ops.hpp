@@ -67,12 +67,23 @@ template <class LA> struct HeOps {
     }
   }
 
+  // how many target groups the fused inverse+forward pass-A kernel is split into: enough warp jobs to
+  // cover the machine (148 SMs x 8 warps) without recomputing the inverse pass more than needed
+  static int pick_groups(int nsrc, int ntargets) {
+    const int base = nsrc * TILES_A;
+    int g = (1184 + base - 1) / base;
+    if (g < 1) g = 1;
+    if (g > ntargets) g = ntargets;
+    return g;
+  }
+
   // ---- key switching --------------------------------------------------------------------
   // mode LD_GALOIS : dst = (perm(c0), 0) + KS(perm(c1))   with src ciphertext `a`, Galois element elt
   // mode LD_PRODUCT: dst = (a0 b0, a0 b1 + a1 b0) + KS(a1 b1)           (multiply + relinearize)
   // `pitch` = words between the two polys of every ciphertext operand.  dst may alias a or b.
+  // Five launches: B' | A'+mod-up+A | B+MAC(+B' of the special limb) | A'+round+A | B+mod-down epilogue
   void keyswitch(int mode, const u64 *a, const u64 *b, u64 *dst, size_t pitch, int l, const u64 *key, u32 elt) {
-    // 1. t = INTT(target): inverse pass B fused with the gather / the tensor product d2
+    // 1. inverse pass B of the target, fused with the Galois gather / the tensor product d2
     {
       ArgsInttB x{};
       x.T = T, x.dst = sc.s1, x.nl = l, x.prime0 = 0, x.pstep = 1, x.elt = elt;
@@ -83,37 +94,30 @@ template <class LA> struct HeOps {
         x.src = a + pitch, x.src2 = b + pitch;
         la.template intt_B<LD_PRODUCT>(x, l * ROWS);
       }
-      ArgsInttA y{};
-      y.T = T, y.src = sc.s1, y.dst = sc.t, y.nl = l, y.prime0 = 0, y.pstep = 1, y.round = 0;
-      la.intt_A(y, l * TILES_A);
     }
-    // 2. mod-up: (t_J mod q_I) -> forward pass A, for every output prime I and digit J != I
+    // 2. inverse pass A -> coefficient digits t_J (registers only) -> (t_J mod q_I) -> forward pass A
     {
-      ArgsFwdA x{};
-      x.T = T, x.src = sc.t, x.dst = sc.s2, x.nd = (l + 1) * l, x.l = l, x.sp = sp();
-      la.template fwd_A<PRE_MODUP>(x, (l + 1) * l * TILES_A);
+      ArgsInvFwdA x{};
+      x.T = T, x.src = sc.s1, x.dst = sc.s2, x.nsrc = l, x.l = l, x.sp = sp(), x.ngroups = pick_groups(l, l + 1);
+      la.template invA_fwdA<PRE_MODUP>(x, l * x.ngroups * TILES_A);
     }
-    // 3. forward pass B + inner product with the key over all digits
+    // 3. forward pass B + inner product with the key over all digits; the special-prime CTAs also run the
+    //    inverse pass B of their accumulator rows (first step of the mod-down) into s1[0..1]
     {
       ArgsFwdB x{};
       x.T = T, x.src = sc.s2, x.dst = sc.acc, x.l = l, x.sp = sp(), x.key = key, x.Ltot = L, x.ld = mode, x.elt = elt;
       x.tgt = a + pitch, x.tgt2 = (mode == LD_PRODUCT) ? b + pitch : nullptr;
+      x.sp_rows = sc.s1;
       la.mac(x, (l + 1) * ROWS);
     }
-    // 4. mod-down by the special prime with rounding, fused with the final accumulate
+    // 4. mod-down: inverse pass A of the special limb + rounding + per-target fix-up + forward pass A
     {
-      // r = INTT_p(acc[K][l]) + p/2   (two limbs at stride (l+1)*N: run them as two 1-limb launches)
-      for (int K = 0; K < 2; K++) {
-        ArgsInttB x{};
-        x.T = T, x.src = sc.acc + ((size_t)K * (l + 1) + l) * N, x.dst = sc.s1 + (size_t)K * N, x.nl = 1, x.prime0 = sp(), x.pstep = 0;
-        la.template intt_B<LD_PLAIN>(x, ROWS);
-      }
-      ArgsInttA y{};
-      y.T = T, y.src = sc.s1, y.dst = sc.t, y.nl = 2, y.prime0 = sp(), y.pstep = 0, y.round = 1;
-      la.intt_A(y, 2 * TILES_A);
-      ArgsFwdA z{};
-      z.T = T, z.src = sc.t, z.dst = sc.s4, z.nd = 2 * l, z.l = l, z.plast = sp();
-      la.template fwd_A<PRE_ROUND>(z, 2 * l * TILES_A);
+      ArgsInvFwdA x{};
+      x.T = T, x.src = sc.s1, x.dst = sc.s4, x.nsrc = 2, x.l = l, x.plast = sp(), x.ngroups = pick_groups(2, l);
+      la.template invA_fwdA<PRE_ROUND>(x, 2 * x.ngroups * TILES_A);
+    }
+    // 5. forward pass B + (acc - u) * p^-1 + addend
+    {
       ArgsFwdB w{};
       w.T = T, w.src = sc.s4, w.dst = dst, w.l = l, w.sp = sp(), w.acc = sc.acc, w.pitch = pitch, w.plast = sp();
       if (mode == LD_GALOIS) {
@@ -126,20 +130,19 @@ template <class LA> struct HeOps {
     }
   }
 
-  // ---- rescale: npoly polys with l limbs -> l-1 limbs (divide by q_{l-1} and round) -------
+  // ---- rescale: 2 polys with l limbs -> l-1 limbs (divide by q_{l-1} and round); three launches -------
   // src/dst poly pitches may differ (encrypt uses a compact (l)-limb temporary).
   void rescale(const u64 *src, size_t src_pitch, u64 *dst, size_t dst_pitch, int l) {
-    for (int K = 0; K < 2; K++) {
+    {
       ArgsInttB x{};
-      x.T = T, x.src = src + (size_t)K * src_pitch + (size_t)(l - 1) * N, x.dst = sc.s1 + (size_t)K * N, x.nl = 1, x.prime0 = l - 1, x.pstep = 0;
-      la.template intt_B<LD_PLAIN>(x, ROWS);
+      x.T = T, x.src = src + (size_t)(l - 1) * N, x.sstride = src_pitch, x.dst = sc.s1, x.nl = 2, x.prime0 = l - 1, x.pstep = 0;
+      la.template intt_B<LD_PLAIN>(x, 2 * ROWS);
     }
-    ArgsInttA y{};
-    y.T = T, y.src = sc.s1, y.dst = sc.t, y.nl = 2, y.prime0 = l - 1, y.pstep = 0, y.round = 1;
-    la.intt_A(y, 2 * TILES_A);
-    ArgsFwdA z{};
-    z.T = T, z.src = sc.t, z.dst = sc.s4, z.nd = 2 * (l - 1), z.l = l - 1, z.plast = l - 1;
-    la.template fwd_A<PRE_ROUND>(z, 2 * (l - 1) * TILES_A);
+    {
+      ArgsInvFwdA x{};
+      x.T = T, x.src = sc.s1, x.dst = sc.s4, x.nsrc = 2, x.l = l - 1, x.plast = l - 1, x.ngroups = pick_groups(2, l - 1);
+      la.template invA_fwdA<PRE_ROUND>(x, 2 * x.ngroups * TILES_A);
+    }
     if (src_pitch != dst_pitch) {
       // epilogue addresses input and output with one pitch: run per poly
       for (int K = 0; K < 2; K++) {

@@ -39,17 +39,29 @@ struct EmuLauncher {
       body_fwd_B<EPI>(a, j, st, sm);
     }
   }
+  template <int PRE> void invA_fwdA(const ArgsInvFwdA &a, int njobs) {
+    for (int j = 0; j < njobs; j++) {
+      LaneA st[32];
+      alignas(16) u64 sm[WARP_SMEM_WORDS];
+      body_invA_fwdA<PRE>(a, j, st, sm);
+    }
+  }
   void mac(const ArgsFwdB &a, int njobs) { // one CTA of MAC_WARPS warps per job; CTA barriers = phase boundaries
     for (int j = 0; j < njobs; j++) {
       alignas(16) u64 sm[MAC_SMEM_WORDS];
       Tw *tw_s = reinterpret_cast<Tw *>(sm);
-      u64 *tiles = sm + 2 * WARP_TW_ENTRIES, *parts = tiles + MAC_WARPS * TILE_B_WORDS;
+      u64 *tiles = sm + MAC_TW_WORDS, *parts = tiles + MAC_WARPS * TILE_B_WORDS;
       for (int tid = 0; tid < MAC_WARPS * 32; tid++) body_mac_stage(a, j, tid, tw_s);
       for (int w = 0; w < MAC_WARPS; w++) {
         LaneB8 st[32];
         body_mac_warp(a, j, w, st, tiles + w * TILE_B_WORDS, tw_s, parts + w * MAC_PART_WORDS);
       }
-      for (int tid = 0; tid < MAC_WARPS * 32; tid++) body_mac_reduce(a, j, tid, parts);
+      for (int tid = 0; tid < MAC_WARPS * 32; tid++) body_mac_reduce(a, j, tid, parts, tiles);
+      if (mac_Iidx(a, j) == a.l)
+        for (int K = 0; K < 2; K++) {
+          LaneB8 st[32];
+          body_mac_tail(a, j, K, st, parts + K * MAC_PART_WORDS, tw_s, tiles);
+        }
     }
   }
 };
