@@ -17,19 +17,19 @@ def needs_build():
     return any(f.stat().st_mtime > t for f in CSRC.iterdir())
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=OUT, defs=()):
+    if not force and out == OUT and not needs_build():
         return OUT
     objs = []
     for src in ("kernels.cu", "vm.cu"):
         obj = CSRC / (src + ".o")
-        cmd = ["nvcc", *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = ["nvcc", *NVCC_FLAGS, *[f"-D{d}" for d in defs], "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.run(cmd, check=True)
         objs.append(str(obj))
-    subprocess.run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(OUT), *objs], check=True)
-    return OUT
+    subprocess.run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(out), *objs], check=True)
+    return out
 
 
 if __name__ == "__main__":

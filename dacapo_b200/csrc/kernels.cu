@@ -10,6 +10,7 @@
 #include "kernels.h"
 
 unsigned long long g_launch_count = 0;
+bool g_pdl_suspended = false;
 KProfiler g_prof;
 const char *const g_kernel_class_names[KC_COUNT] = {
     "intt_B_plain", "intt_B_galois", "intt_B_product", "intt_A", "fwd_A_plain", "fwd_A_modup", "fwd_A_round",
@@ -83,7 +84,10 @@ template <int PRE> __global__ void __launch_bounds__(CTA_THREADS, 4) k_invA_fwdA
   body_invA_fwdA<PRE>(a, job, st, sm[warp]);
 }
 // key-switch inner product: CTA = one (output prime, row) job, its MAC_WARPS warps split the digits
-__global__ void __launch_bounds__(MAC_WARPS * 32, 3) k_mac(ArgsFwdB a) {
+#ifndef MAC_MIN_CTAS
+#define MAC_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(MAC_WARPS * 32, MAC_MIN_CTAS) k_mac(ArgsFwdB a) {
   __shared__ __align__(16) u64 sm[MAC_SMEM_WORDS];
   Tw *tw_s = reinterpret_cast<Tw *>(sm);
   u64 *tiles = sm + MAC_TW_WORDS;
@@ -111,7 +115,8 @@ static void launch_pdl(void (*kern)(KArgs...), int grid, int block, cudaStream_t
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at, cfg.numAttrs = 1;
+  static const bool no_pdl = std::getenv("HEVM_PDL") && std::atoi(std::getenv("HEVM_PDL")) == 0;
+  cfg.attrs = at, cfg.numAttrs = (no_pdl || g_pdl_suspended) ? 0 : 1;
   CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, args...));
 }
 #define PRE_LAUNCH(s, cls) g_prof.begin(s, cls)
@@ -248,8 +253,9 @@ __device__ __forceinline__ u64 rnd64(u64 seed, u64 stream, u64 idx) {
   return mix64(mix64(seed + G * (stream + 1)) + G * (idx + 1));
 }
 template <int CBD>
-__global__ void k_sample_small(const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream) {
+__global__ void k_sample_small(const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream, const u64 *ctr) {
   const size_t N = (size_t)1 << logN;
+  if (ctr) stream += *ctr * 4; // encryption counter base kept on the device (graph replays advance it)
   for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < N; k += (size_t)gridDim.x * blockDim.x) {
     const u64 w = rnd64(seed, stream, k);
     int t;
@@ -269,12 +275,12 @@ __global__ void k_sample_uniform(const NttTables *T, int logN, u64 *out, int lim
     out[v] = reduce128(lo, hi, T->mod[i]);
   }
 }
-void launch_sample_ternary(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream) {
-  k_sample_small<0><<<ew_grid((size_t)1 << logN), 256, 0, s>>>(T, logN, out, limbs, seed, stream);
+void launch_sample_ternary(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream, const u64 *ctr) {
+  k_sample_small<0><<<ew_grid((size_t)1 << logN), 256, 0, s>>>(T, logN, out, limbs, seed, stream, ctr);
   POST_LAUNCH_S(s);
 }
-void launch_sample_cbd(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream) {
-  k_sample_small<1><<<ew_grid((size_t)1 << logN), 256, 0, s>>>(T, logN, out, limbs, seed, stream);
+void launch_sample_cbd(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream, const u64 *ctr) {
+  k_sample_small<1><<<ew_grid((size_t)1 << logN), 256, 0, s>>>(T, logN, out, limbs, seed, stream, ctr);
   POST_LAUNCH_S(s);
 }
 void launch_sample_uniform(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream_base) {

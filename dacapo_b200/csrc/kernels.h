@@ -18,6 +18,7 @@
 
 // counts every kernel this library launches (bench.py reports it as gpu_launches)
 extern unsigned long long g_launch_count;
+extern bool g_pdl_suspended; // set while run() is being captured into a CUDA graph (plain edges there)
 
 // Optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline).
 enum {
@@ -59,8 +60,8 @@ void launch_elementwise(cudaStream_t s, int op, const NttTables *T, int logN, u6
                         const u64 *p, size_t pitch, int l);
 
 // ---- samplers (specification shared with the oracle: oracle/ckks_oracle.hpp "sampler") ----
-void launch_sample_ternary(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream);
-void launch_sample_cbd(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream);
+void launch_sample_ternary(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream, const u64 *ctr = nullptr);
+void launch_sample_cbd(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream, const u64 *ctr = nullptr);
 void launch_sample_uniform(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream_base);
 
 // ---- key generation / encryption helpers ----

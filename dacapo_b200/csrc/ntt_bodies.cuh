@@ -38,6 +38,10 @@ HD void load8_stream(const u64 *p, u64 (&v)[8]) {
   ldg_stream4(p, v[0], v[1], v[2], v[3]);
   ldg_stream4(p + 4, v[4], v[5], v[6], v[7]);
 }
+HD void load8_ro(const u64 *p, u64 (&v)[8]) { // key material
+  ldg_ro4(p, v[0], v[1], v[2], v[3]);
+  ldg_ro4(p + 4, v[4], v[5], v[6], v[7]);
+}
 HD void store8(u64 *p, const u64 (&v)[8]) {
   stg4(p, v[0], v[1], v[2], v[3]);
   stg4(p + 4, v[4], v[5], v[6], v[7]);
@@ -369,8 +373,8 @@ HD void body_mac_warp(const ArgsFwdB &a, int job, int w, LaneB8 *st, u64 *tile, 
     FOR_LANES(S, st, {
       const int li = (NLANE_STATE == 1) ? 0 : lane;
       u64 ka[8], kb[8];
-      load8_stream(k0 + lane * 8, ka);
-      load8_stream(k1 + lane * 8, kb);
+      load8_ro(k0 + lane * 8, ka);
+      load8_ro(k1 + lane * 8, kb);
       _Pragma("unroll")
       for (int e = 0; e < 8; e++) {
         mac128(lo0[li][e], hi0[li][e], S.x[e], ka[e]);

@@ -64,14 +64,25 @@ HD void cp_async_wait_keep1() { asm volatile("cp.async.wait_group 1;" ::: "memor
 // Programmatic dependent launch: a kernel may start (and stage its twiddles) while its predecessor
 // drains; it must not touch the predecessor's output before grid_dep_wait().
 HD void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-HD void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-// streaming 64-bit / 256-bit accesses (no L1 allocation: each value is touched once per pass)
+HD void grid_dep_launch() {
+#ifndef HEVM_NO_PDL_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+// Streaming 64-bit / 256-bit loads of data produced by EARLIER KERNELS (ciphertext limbs, scratch):
+// ld.global.cg = cached in L2 only.  They must not use the non-coherent (.nc) path: with programmatic
+// dependent launch a kernel becomes resident -- and its SM's L1 is invalidated -- before its
+// predecessor has finished writing, so a .nc load could hit a stale L1 line of a reused scratch buffer.
 HD u64 ldg_stream(const u64 *p) {
   u64 v;
-  asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 HD void ldg_stream4(const u64 *p, u64 &a, u64 &b, u64 &c, u64 &d) {
+  asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory");
+}
+// read-only for the whole life of the VM (key-switch keys): non-coherent path, no L1 allocation
+HD void ldg_ro4(const u64 *p, u64 &a, u64 &b, u64 &c, u64 &d) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
 }
 HD void stg4(u64 *p, u64 a, u64 b, u64 c, u64 d) {
@@ -94,6 +105,7 @@ HD void grid_dep_wait() {}
 HD void grid_dep_launch() {}
 HD u64 ldg_stream(const u64 *p) { return *p; }
 HD void ldg_stream4(const u64 *p, u64 &a, u64 &b, u64 &c, u64 &d) { a = p[0], b = p[1], c = p[2], d = p[3]; }
+HD void ldg_ro4(const u64 *p, u64 &a, u64 &b, u64 &c, u64 &d) { a = p[0], b = p[1], c = p[2], d = p[3]; }
 HD void stg4(u64 *p, u64 a, u64 b, u64 c, u64 d) { p[0] = a, p[1] = b, p[2] = c, p[3] = d; }
 #endif
 

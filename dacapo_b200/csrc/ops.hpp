@@ -71,7 +71,10 @@ template <class LA> struct HeOps {
   // cover the machine (148 SMs x 8 warps) without recomputing the inverse pass more than needed
   static int pick_groups(int nsrc, int ntargets) {
     const int base = nsrc * TILES_A;
-    int g = (1184 + base - 1) / base;
+#ifndef GROUP_TARGET_WARPS
+#define GROUP_TARGET_WARPS 1184
+#endif
+    int g = (GROUP_TARGET_WARPS + base - 1) / base;
     if (g < 1) g = 1;
     if (g > ntargets) g = ntargets;
     return g;

@@ -247,9 +247,13 @@ def test_full_size_properties(pair):
     y = rng.uniform(-1, 1, n)
     g.encode(1, y, 13, 40)
     g.encrypt_pt(1, 4)
+    g.encode(0, x, 13, 50)
+    g.encode(1, y, 13, 50)
+    g.encrypt_pt(0, 6)
+    g.encrypt_pt(1, 7)
     g.exec(asm.ADDCC, 5, 0, 4)
     g.exec(asm.ROTATE, 5, 5, -300)
     assert np.max(np.abs(g.decrypt_decode(5, 1) - np.roll(x + y, 300))) < 1e-4
-    g.exec(asm.MULCC, 6, 0, 4)
+    g.exec(asm.MULCC, 6, 6, 7)
     g.exec(asm.RESCALE, 6, 6)
-    assert np.max(np.abs(g.decrypt_decode(6, 1) - x * y)) < 5e-3  # scale 2^80/q ~ 2^20 after rescale: noise ~1e-4..1e-3
+    assert np.max(np.abs(g.decrypt_decode(6, 1) - x * y)) < 1e-4  # scale 2^100/q ~ 2^40 after rescale
