@@ -192,15 +192,14 @@ template <int PRE> HD void body_fwd_A(const ArgsFwdA &a, int job, LaneA *st, u64
     grid_dep_wait();
     _Pragma("unroll")
     for (int e = 0; e < 16; e++) S.y[e] = ldg_stream(src + ((size_t)rowR(lane, e) << LOGB8) + (lane & 3));
+    // No modular reduction: every prime is 2^60 - delta with delta < 2^32, so a canonical residue of
+    // ANY prime is < 2^60 < 2*q_dst, i.e. already a valid lazy representative mod q_dst.
     _Pragma("unroll")
-    for (int e = 0; e < 16; e++) {
-      u64 v = S.y[e];
-      if (PRE != PRE_NONE && ps > pd) v = reduce64(v, m);
-      S.y[e] = v + fix;
-    }
+    for (int e = 0; e < 16; e++) S.y[e] += fix;
     cp_async_wait();
   });
-  warp_fwdA_from_regs<LOGB8>(st, sm, a.dst + (size_t)d * N, tile * 4, tw, m);
+  (void)ps;
+  warp_fwdA_from_regs<LOGB8, PRE == PRE_ROUND>(st, sm, a.dst + (size_t)d * N, tile * 4, tw, m);
 }
 
 
@@ -266,16 +265,13 @@ template <int PRE> HD void body_invA_fwdA(const ArgsInvFwdA &a, int job, LaneA *
     FOR_LANES(S, st, {
       if (tn < tend) stage_tw_A(tw_fwd + 128 * (buf ^ 1), T.tw + (size_t)prime_of(tn) * N, lane); // prefetch next table
       cp_async_commit();
+      // no modular reduction needed (see body_fwd_A): x < 2^60 < 2*q_dst is a valid lazy representative
       _Pragma("unroll")
-      for (int e = 0; e < 16; e++) {
-        u64 v = S.x[e];
-        if (ps > pd) v = reduce64(v, m);
-        S.y[e] = v + fix;
-      }
+      for (int e = 0; e < 16; e++) S.y[e] = S.x[e] + fix;
       cp_async_wait_keep1(); // the current table (older group) has landed
     });
     u64 *dst = (PRE == PRE_MODUP) ? a.dst + ((size_t)t * a.l + sl) * N : a.dst + ((size_t)sl * a.l + t) * N;
-    warp_fwdA_from_regs<LOGB8>(st, sm, dst, tile * 4, tw_fwd + 128 * buf, m);
+    warp_fwdA_from_regs<LOGB8, PRE == PRE_ROUND>(st, sm, dst, tile * 4, tw_fwd + 128 * buf, m);
     buf ^= 1;
     t = tn;
   }
@@ -365,10 +361,12 @@ HD void body_mac_warp(const ArgsFwdB &a, int job, int w, LaneB8 *st, u64 *tile, 
         for (int e = 0; e < 8; e++) S.x[e] = ldg_stream(src + idxH(lane, e));
       });
       warp_fwdB8_regs(st, tile, tw_s, m);
-      FOR_LANES(S, st, {
-        _Pragma("unroll")
-        for (int e = 0; e < 8; e++) S.x[e] = fold60(S.x[e], m.delta);
-      });
+      if (a.l > 20) { // sum of l products (< 12q * q each) stays below 2^128 up to l = 20
+        FOR_LANES(S, st, {
+          _Pragma("unroll")
+          for (int e = 0; e < 8; e++) S.x[e] = fold60(S.x[e], m.delta);
+        });
+      }
     }
     FOR_LANES(S, st, {
       const int li = (NLANE_STATE == 1) ? 0 : lane;

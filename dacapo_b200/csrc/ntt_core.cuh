@@ -121,18 +121,13 @@ HD void stage_tw_A(Tw *dst, const Tw *table, int lane) {
   for (int i = 0; i < 4; i++) cp_async16(dst + lane + 32 * i, table + lane + 32 * i);
 }
 // pass B, row r: local entry (2^k - 1 + g) <- table[(128 << k) + (r << k) + g],  k < 8, g < 2^k
-// `tid`/`nthr`: the threads sharing the copy (one warp: lane/32; a 4-warp MAC job: threadIdx.x/128)
+// (one contiguous run of 2^k entries per local stage).  `tid`/`nthr`: the threads sharing the copy.
 HD void stage_tw_B(Tw *dst, const Tw *table, int r, int tid, int nthr = 32) {
   _Pragma("unroll")
-  for (int i = 0; i < 8; i++) {
-    const int e = tid + nthr * i; // 0..255 (255 unused)
-    if (i * nthr < 256 && e < 255) {
-      int k = 0;
-      _Pragma("unroll")
-      for (int b = 1; b < 8; b++) k += ((e + 1) >> b) ? 1 : 0; // floor(log2(e+1))
-      const int g = e + 1 - (1 << k);
-      cp_async16(dst + e, table + (128 << k) + (r << k) + g);
-    }
+  for (int k = 0; k < 8; k++) {
+    const Tw *src = table + (128 << k) + (r << k);
+    Tw *d = dst + ((1 << k) - 1);
+    for (int g = tid; g < (1 << k); g += nthr) cp_async16(d + g, src + g);
   }
 }
 
@@ -315,16 +310,18 @@ struct LaneB8 {
 // Warp-level pass bodies.  `sm` = warp-private tile (WARP_TILE_WORDS words); `tw` = staged twiddles.
 // =====================================================================================
 
-// forward pass A on values already held in layout R by st[].y (< 2q); result (< 8q) -> dst tile
+// forward pass A on values already held in layout R by st[].y; result (lazy, < 16q) -> dst tile
 // (128 rows x 4 cols at column c0 of the limb `dst`, row pitch = 2^LOGB)
-template <int LOGB>
+// Range: every stage adds at most 2q to the bound, so inputs < 2q leave the 7 stages < 16q < 2^64
+// without any correction (FOLD = false); inputs up to 4q need one fold between the rounds (FOLD = true).
+template <int LOGB, bool FOLD>
 HD void warp_fwdA_from_regs(LaneA *st, u64 *sm, u64 *dst, int c0, const Tw *tw, const ModQ &m) {
   const u64 q = m.q, q2 = 2 * m.q, dl = m.delta;
   LANE_DECL;
   FOR_LANES(S, st, {
     fwdA_stages_R(S.y, tw, q, q2);
     _Pragma("unroll")
-    for (int e = 0; e < 16; e++) sm[padx(idxR(lane, e))] = fold60(S.y[e], dl);
+    for (int e = 0; e < 16; e++) sm[padx(idxR(lane, e))] = FOLD ? fold60(S.y[e], dl) : S.y[e];
   });
   FOR_LANES(S, st, {
     _Pragma("unroll")
@@ -354,7 +351,8 @@ HD void warp_invA_to_regs(LaneA *st, u64 *sm, const u64 *src, int c0, const Tw *
   });
 }
 
-// forward pass B: values in st[].x layout H (any lazy bound) -> st[].x layout C (< 6q)
+// forward pass B: values in st[].x layout H (any lazy bound) -> st[].x layout C (< 12q):
+// fold on load (< 2q), H stages (< 8q), fold (< 2q), M stages (< 8q), C stages (< 12q)
 HD void warp_fwdB8_regs(LaneB8 *st, u64 *sm, const Tw *tw, const ModQ &m) {
   const u64 q = m.q, q2 = 2 * m.q, dl = m.delta;
   LANE_DECL;
@@ -370,7 +368,7 @@ HD void warp_fwdB8_regs(LaneB8 *st, u64 *sm, const Tw *tw, const ModQ &m) {
     for (int e = 0; e < 8; e++) S.x[e] = sm[padx(idxM8(lane, e))];
     fwdB8_stages_M(S.x, lane, tw, q, q2);
     _Pragma("unroll")
-    for (int e = 0; e < 8; e++) sm[padx(idxM8(lane, e))] = fold60(S.x[e], dl);
+    for (int e = 0; e < 8; e++) sm[padx(idxM8(lane, e))] = S.x[e];
   });
   FOR_LANES(S, st, {
     _Pragma("unroll")

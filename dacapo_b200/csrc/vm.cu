@@ -137,7 +137,7 @@ struct VM {
     CUDA_CHECK(cudaMemcpy(dT, &P.tab, sizeof(NttTables), cudaMemcpyHostToDevice));
     d_ctr_base = dalloc<u64>(1);
     CUDA_CHECK(cudaMemset(d_ctr_base, 0, 8));
-    int nl = 8;
+    int nl = 16;
     if (const char *e = std::getenv("HEVM_STREAMS")) nl = std::max(1, std::min(32, std::atoi(e)));
     if (const char *e = std::getenv("HEVM_GRAPH")) use_graph = std::atoi(e) != 0;
     lanes.resize(nl);
