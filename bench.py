@@ -214,6 +214,69 @@ def workload_config(batch, note=None):
     return c
 
 
+def resnet_mix(lib, vm, tmp, cpu=True, reps=3):
+    """ResNet-20 op-mix replay (SURVEY 8d fallback; dacapo_b200/workloads.py): run() latency on the GPU and the
+    CPU port's time for the same op mix, estimated from its per-op / per-level timings."""
+    from dacapo_b200 import workloads
+    prog, stats, per_level = workloads.resnet20_opmix()
+    cst, hv = os.path.join(tmp, "resnet_mix.cst"), os.path.join(tmp, "resnet_mix.hevm")
+    prog.save(cst, hv)
+    t0 = time.perf_counter()
+    lib.load(vm, cst.encode(), hv.encode())
+    lib.preprocess(vm)
+    t_pre = time.perf_counter() - t0
+    x = np.random.default_rng(5).uniform(-0.5, 0.5, SLOTS)
+    out = np.zeros(SLOTS)
+    lat, e2e = [], []
+    for i in range(reps + 1):
+        t0 = time.perf_counter()
+        lib.encrypt(vm, 0, x.ctypes.data_as(f64p), SLOTS)
+        t1 = time.perf_counter()
+        lib.run(vm)
+        t2 = time.perf_counter()
+        lib.decrypt_result(vm, 0, out.ctypes.data_as(f64p))
+        t3 = time.perf_counter()
+        if i:  # first run builds the CUDA graph
+            lat.append(t2 - t1)
+            e2e.append(t3 - t0)
+    res = {"what": "ResNet-20 op-mix replay, NOT the compiled network (hecate-opt/MLIR unavailable): op counts of "
+                   "examples/benchmarks/ResNet.py at nt=2^14 (SURVEY App. C), 19 bootstrap segments, levels 13..3",
+           "ops": {k: v for k, v in stats.items()}, "hevm_ops": len(prog.ops), "run_latency_s": float(np.median(lat)),
+           "e2e_latency_s": float(np.median(e2e)), "preprocess_s": t_pre, "finite_output": bool(np.all(np.isfinite(out))),
+           "reference_README_latency_s": 53.726}
+    if cpu:
+        olib = _binding.bind(_binding.ORACLE_LIB)
+        kd = tempfile.mkdtemp(prefix="hevm_cpu_mix_")
+        ovm = make_vm(olib, kd)
+        olib.hevmx_resize(ovm, 4, 2)
+        u64p = C.POINTER(C.c_uint64)
+        primes = np.zeros(NPRIMES, dtype=np.uint64)
+        olib.hevmx_primes(ovm, primes.ctypes.data_as(u64p))
+        est, table = 0.0, {}
+        rng = np.random.default_rng(3)
+        for lvl in sorted({l for (_, l) in per_level}):
+            a = np.zeros((2, lvl, N), dtype=np.uint64)
+            for i in range(lvl):
+                a[:, i, :] = rng.integers(0, int(primes[i]), size=(2, N), dtype=np.uint64)
+            olib.hevmx_ct_write(ovm, 0, a.ctypes.data_as(u64p), lvl, 2.0 ** 40)
+            olib.hevmx_pt_write(ovm, 0, a[0].ctypes.data_as(u64p), lvl, 2.0 ** 40)
+            for name, opc, rhs in (("ks_steps", asm.ROTATE, 1), ("mulcc", asm.MULCC, 0), ("rescale", asm.RESCALE, 0),
+                                   ("mulcp", asm.MULCP, 0), ("addcc", asm.ADDCC, 0)):
+                n = per_level.get((name, lvl), 0)
+                if not n:
+                    continue
+                t0 = time.perf_counter()
+                olib.hevmx_exec(ovm, opc, 1, 0, rhs)
+                dt = time.perf_counter() - t0
+                table[f"{name}@{lvl}"] = dt
+                est += n * dt
+        res["cpu_port_estimate_s"] = est
+        res["cpu_port_estimate_note"] = ("sum over (op, level) of count x single-thread oracle time for rotate-step, mulcc, rescale, "
+                                         "mulcp, addcc (bootstrap / negate / addcp not counted)")
+        res["speedup_vs_cpu_port_estimate"] = est / res["run_latency_s"]
+    return res
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -224,6 +287,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--op-table", action="store_true", help="also measure the per-op/per-level table and emit profiled_B200_GPU.json")
+    ap.add_argument("--no-resnet-mix", action="store_true", help="skip the ResNet-20 op-mix replay (N=1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -250,11 +314,8 @@ def main():
         torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        from dacapo_b200 import dist as D
+        return D.max_over_ranks(x, device="cuda")
 
     lib = _binding.bind(_binding.B200_LIB)  # raises if the CUDA library is missing
     keydir = tempfile.mkdtemp(prefix=f"hevm_bench_keys_r{rank}_")
@@ -369,6 +430,9 @@ def main():
         line["op_table_us"] = {op: {str(l): round(v, 2) for l, v in lv.items()} for op, lv in table.items()}
         line["op_roofline_l13"] = {op: {"us": table[op][13], "frac": profile.algorithmic_bytes(op, 13) / (table[op][13] * 1e-6) / 1e9 / peak}
                                    for op in ("rotate", "mulcc", "rescale", "addcc", "mulcp")}
+
+    if rank == 0 and world == 1 and not args.no_resnet_mix:
+        line["resnet20_opmix"] = resnet_mix(lib, vm, tmp, cpu=not args.no_cpu_baseline)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         subprocess.run(["make", "-s", "-C", str(REPO / "oracle")], check=True)
