@@ -177,7 +177,7 @@ def cpu_chain_rate(nthreads, reps, keydirs):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    cores = max(1, min(os.cpu_count() or 1, 8))
+    cores = max(1, min(os.cpu_count() or 1, 16))  # one oracle VM (2.9 GB of keys) per core
     subprocess.run(["make", "-s", "-C", str(REPO / "oracle")], check=True)
     base = tempfile.mkdtemp(prefix="hevm_ref_keys_")
     keydirs = []

@@ -79,7 +79,10 @@ template <int EPI> __global__ void __launch_bounds__(CTA_THREADS) k_fwd_B(ArgsFw
   WARP_KERNEL_PROLOGUE(LaneB8)
   body_fwd_B<EPI>(a, job, st, sm[warp]);
 }
-template <int PRE> __global__ void __launch_bounds__(CTA_THREADS, 4) k_invA_fwdA(ArgsInvFwdA a, int njobs) {
+#ifndef FUSEA_MIN_CTAS
+#define FUSEA_MIN_CTAS 4
+#endif
+template <int PRE> __global__ void __launch_bounds__(CTA_THREADS, FUSEA_MIN_CTAS) k_invA_fwdA(ArgsInvFwdA a, int njobs) {
   WARP_KERNEL_PROLOGUE(LaneA)
   body_invA_fwdA<PRE>(a, job, st, sm[warp]);
 }

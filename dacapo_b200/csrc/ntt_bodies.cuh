@@ -370,6 +370,15 @@ HD void body_mac_warp(const ArgsFwdB &a, int job, int w, LaneB8 *st, u64 *tile, 
     }
     FOR_LANES(S, st, {
       const int li = (NLANE_STATE == 1) ? 0 : lane;
+#ifdef MAC_SPLIT_KEYS
+      u64 ka[8];
+      load8_ro(k0 + lane * 8, ka);
+      _Pragma("unroll")
+      for (int e = 0; e < 8; e++) mac128(lo0[li][e], hi0[li][e], S.x[e], ka[e]);
+      load8_ro(k1 + lane * 8, ka);
+      _Pragma("unroll")
+      for (int e = 0; e < 8; e++) mac128(lo1[li][e], hi1[li][e], S.x[e], ka[e]);
+#else
       u64 ka[8], kb[8];
       load8_ro(k0 + lane * 8, ka);
       load8_ro(k1 + lane * 8, kb);
@@ -378,6 +387,7 @@ HD void body_mac_warp(const ArgsFwdB &a, int job, int w, LaneB8 *st, u64 *tile, 
         mac128(lo0[li][e], hi0[li][e], S.x[e], ka[e]);
         mac128(lo1[li][e], hi1[li][e], S.x[e], kb[e]);
       }
+#endif
     });
   }
   FOR_LANES(S, st, {

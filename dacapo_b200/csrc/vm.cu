@@ -109,6 +109,10 @@ struct VM {
   // run() schedule / CUDA graph
   cudaGraphExec_t graph_exec = nullptr;
   int graph_nboot = 0;
+  unsigned long long graph_launches = 0;
+  // register renaming: logical ciphertext register -> physical buffer.  `home[r]` is the identity buffer of
+  // register r (where encrypt / ct_write put data and where every run() starts); `spare` are extra buffers.
+  std::vector<u64 *> home, spare, final_map;
   bool use_graph = true;
   // program
   std::vector<std::vector<double>> consts;
@@ -308,11 +312,16 @@ struct VM {
   }
   void resize_regs(size_t nct, size_t npt) {
     invalidate_graph();
+    for (size_t r = 0; r < home.size(); r++) ct[r].d = home[r]; // so that each home buffer is freed exactly once
+    home.clear();
+    final_map.clear();
     for (auto &c : ct)
       if (c.d) CUDA_CHECK(cudaFree(c.d));
     for (auto &p : pt)
       if (p.d) CUDA_CHECK(cudaFree(p.d));
-    ct.assign(nct, CtReg());
+    ct.clear();
+    ct.reserve(nct + 1);
+    ct.resize(nct);
     pt.assign(npt, PtReg());
   }
 
@@ -526,16 +535,34 @@ struct VM {
   }
   void preallocate_registers() {
     for (size_t r = 0; r < ct.size(); r++) ctr(r);
+    if (home.size() != ct.size()) {
+      home.resize(ct.size());
+      for (size_t r = 0; r < ct.size(); r++) home[r] = ct[r].d;
+      int nspare = 48;
+      if (const char *e = std::getenv("HEVM_RENAME_POOL")) nspare = std::max(0, std::atoi(e));
+      if (lanes.size() == 1) nspare = 0; // nothing to overlap
+      while ((int)spare.size() < nspare) spare.push_back(dalloc<u64>(2 * pitch));
+    }
+  }
+  void reset_mapping() { // every run() starts from the identity mapping (so that a captured graph can be replayed)
+    for (size_t r = 0; r < home.size(); r++) ct[r].d = home[r];
+  }
+  void rehome(CtReg &c) { // data written through the API always lands in the register's home buffer
+    const size_t r = &c - ct.data();
+    if (r < home.size()) c.d = home[r];
   }
   // issue every op of the program over the lanes with event dependencies
   void issue_scheduled() {
     const int nl = (int)lanes.size();
-    struct RegState {
+    struct BufState { // dependency state of one PHYSICAL buffer
       cudaEvent_t wr = nullptr;
       int wr_lane = -1;
       std::vector<std::pair<int, cudaEvent_t>> readers;
     };
-    std::vector<RegState> rs(ct.size());
+    std::map<u64 *, BufState> bs;
+    std::vector<u64 *> pool(spare.begin(), spare.end()); // FIFO of free physical buffers (oldest first)
+    size_t pool_head = 0;
+    reset_mapping();
     for (Lane &l : lanes) l.load = 0;
     ev_used = 0;
     boot_index = 0;
@@ -559,28 +586,67 @@ struct VM {
       for (int k = 0; k < nrd; k++)
         if ((size_t)rd[k] >= ct.size()) die("ciphertext register index out of range");
       if ((size_t)wr >= ct.size()) die("ciphertext register index out of range");
-      // lane choice: least loaded; ties / near-ties prefer the producer of the first source (no wait needed)
+      if (op.opcode == 4 && op.lhs == op.dst) { // in-place limb drop: metadata only, no kernel, no dependency
+        exec(op);
+        continue;
+      }
+      // lane choice: least loaded; near-ties prefer the producer of the first source (no wait needed)
       int best = 0;
       for (int i = 1; i < nl; i++)
         if (lanes[i].load < lanes[best].load) best = i;
-      const int pl = rs[rd[0]].wr_lane;
+      u64 *src_buf[2] = {ct[rd[0]].d, nrd > 1 ? ct[rd[1]].d : nullptr};
+      const int pl = bs[src_buf[0]].wr_lane;
       if (pl >= 0 && lanes[pl].load <= lanes[best].load + 30.0) best = pl;
       Lane &L0 = lanes[best];
       auto wait_on = [&](int lane, cudaEvent_t e) {
         if (e && lane != best) CUDA_CHECK(cudaStreamWaitEvent(L0.stream, e, 0));
       };
-      for (int k = 0; k < nrd; k++) wait_on(rs[rd[k]].wr_lane, rs[rd[k]].wr);      // RAW
-      wait_on(rs[wr].wr_lane, rs[wr].wr);                                          // WAW
-      for (auto &r : rs[wr].readers) wait_on(r.first, r.second);                   // WAR
+      // renaming: the destination gets a fresh physical buffer; the old one returns to the FIFO, so the
+      // write-after-read / write-after-write hazards of recycled registers (ReuseBuffer.cpp:27-55) disappear
+      u64 *old_buf = ct[wr].d, *dst_buf = old_buf;
+      if (pool_head < pool.size()) {
+        dst_buf = pool[pool_head++];
+        pool.push_back(old_buf);
+      }
+      for (int k = 0; k < nrd; k++) wait_on(bs[src_buf[k]].wr_lane, bs[src_buf[k]].wr); // RAW
+      BufState &D = bs[dst_buf];
+      wait_on(D.wr_lane, D.wr);                                                        // WAW
+      for (auto &r : D.readers) wait_on(r.first, r.second);                            // WAR
       ln = &L0;
       const int lvl = ct[rd[0]].level;
-      exec(op);
+      // run the op out of place into dst_buf: temporarily point the destination register at it
+      if (dst_buf != old_buf) {
+        if (wr == rd[0] || (nrd > 1 && wr == rd[1])) {
+          // source and destination are the same logical register: read the old buffer through a shadow register
+          CtReg shadow = ct[wr];
+          ct.push_back(shadow); // index ct.size()-1 (capacity reserved below, references stay valid)
+          HevmOp o2 = op;
+          if (o2.lhs == wr) o2.lhs = (uint16_t)(ct.size() - 1);
+          if (nrd > 1 && o2.rhs == wr) o2.rhs = (uint16_t)(ct.size() - 1);
+          ct[wr].d = dst_buf;
+          exec(o2);
+          ct.pop_back();
+        } else {
+          ct[wr].d = dst_buf;
+          exec(op);
+        }
+      } else {
+        exec(op);
+      }
       cudaEvent_t done = new_event();
       CUDA_CHECK(cudaEventRecord(done, L0.stream));
       for (int k = 0; k < nrd; k++)
-        if (rd[k] != wr) rs[rd[k]].readers.emplace_back(best, done);
-      rs[wr].wr = done, rs[wr].wr_lane = best, rs[wr].readers.clear();
+        if (src_buf[k] != dst_buf) bs[src_buf[k]].readers.emplace_back(best, done);
+      BufState &D2 = bs[dst_buf];
+      D2.wr = done, D2.wr_lane = best, D2.readers.clear();
       L0.load += op_cost(op, lvl);
+    }
+    final_map.resize(home.size());
+    for (size_t r = 0; r < home.size(); r++) final_map[r] = ct[r].d;
+    if (std::getenv("HEVM_SCHED_DEBUG")) {
+      std::fprintf(stderr, "[b200-hevm] schedule: %zu events, lane loads:", ev_used);
+      for (Lane &l : lanes) std::fprintf(stderr, " %.0f", l.load);
+      std::fprintf(stderr, "\n");
     }
     // join: lane 0 waits for every other lane
     for (int i = 1; i < nl; i++) {
@@ -596,6 +662,7 @@ struct VM {
     CUDA_CHECK(cudaMemcpyAsync(d_ctr_base, &enc_counter, 8, cudaMemcpyHostToDevice, lanes[0].stream));
     if (g_prof.on || lanes.size() == 1 && !use_graph) { // kernel-class profiling / plain mode: in order on lane 0
       boot_index = 0;
+      reset_mapping();
       for (auto &op : prog) exec(op);
       enc_counter += boot_index;
     } else if (!use_graph) {
@@ -605,15 +672,20 @@ struct VM {
       if (!graph_exec) {
         cudaGraph_t g = nullptr;
         g_pdl_suspended = true;
+        const unsigned long long c0 = g_launch_count;
         CUDA_CHECK(cudaStreamBeginCapture(lanes[0].stream, cudaStreamCaptureModeRelaxed));
         issue_scheduled();
         CUDA_CHECK(cudaStreamEndCapture(lanes[0].stream, &g));
         g_pdl_suspended = false;
+        graph_launches = g_launch_count - c0; // kernels recorded, not yet executed
+        g_launch_count = c0;
         CUDA_CHECK(cudaGraphInstantiate(&graph_exec, g, 0));
         CUDA_CHECK(cudaGraphDestroy(g));
         graph_nboot = (int)boot_index;
       }
       CUDA_CHECK(cudaGraphLaunch(graph_exec, lanes[0].stream));
+      for (size_t r = 0; r < final_map.size(); r++) ct[r].d = final_map[r]; // where the replay leaves each register
+      g_launch_count += graph_launches; // every replay executes all recorded kernels
       enc_counter += graph_nboot;
     }
     CUDA_CHECK(cudaStreamSynchronize(lanes[0].stream));
@@ -714,6 +786,7 @@ void encrypt(void *h, int64_t i, double *dat, int len) {
   if ((size_t)i >= vm->arg_level.size()) die("encrypt: argument index out of range");
   vm->stage_host_values(dat, (size_t)len);
   vm->encode_internal(vm->ln->boot_pt, vm->ln->d_vals_in, (int)std::min((size_t)len, vm->N / 2), (int64_t)vm->arg_level[i], (int64_t)vm->arg_scale[i]);
+  vm->rehome(vm->ctr((size_t)i));
   vm->encrypt_pt_now(vm->ln->boot_pt, vm->ctr((size_t)i));
   CUDA_CHECK(cudaStreamSynchronize(vm->ln->stream));
 }
@@ -779,6 +852,7 @@ void hevmx_ct_read(void *h, int64_t r, uint64_t *out) {
 void hevmx_ct_write(void *h, int64_t r, const uint64_t *in, int64_t level, double scale) {
   VM *vm = V(h);
   CtReg &c = vm->ctr((size_t)r);
+  vm->rehome(c);
   if (level < 1 || level > vm->L - 1) die("ct_write: level out of range");
   const size_t w = (size_t)level * vm->N;
   for (int K = 0; K < 2; K++) CUDA_CHECK(cudaMemcpyAsync(c.d + K * vm->pitch, in + K * w, w * 8, cudaMemcpyHostToDevice, vm->ln->stream));

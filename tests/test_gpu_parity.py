@@ -257,3 +257,85 @@ def test_full_size_properties(pair):
     g.exec(asm.MULCC, 6, 6, 7)
     g.exec(asm.RESCALE, 6, 6)
     assert np.max(np.abs(g.decrypt_decode(6, 1) - x * y)) < 1e-4  # scale 2^100/q ~ 2^40 after rescale
+
+
+def _random_program(seed, nops=160):
+    """Random dependency-rich program with aggressive register recycling (stress for the multi-lane
+    scheduler, register renaming and CUDA-graph replay in run())."""
+    rng = np.random.default_rng(seed)
+    p = asm.Program(init_level=13)
+    args = [p.arg(50, 6), p.arg(50, 6)]
+    regs = [p.new_ct() for _ in range(6)]
+    lvl = {}
+    pts = {}
+    for r, a in zip(regs[:2], args):
+        p.rotate(r, a, 0)
+        lvl[r] = 6
+    live = regs[:2]
+    for _ in range(nops):
+        kind = rng.choice(["rot", "rot", "mulcp", "addcc", "mulcc", "neg", "resc", "addcp", "modsw"])
+        src = int(rng.choice(live))
+        dst = int(rng.choice(regs))
+        l = lvl[src]
+        if kind == "rot":
+            p.rotate(dst, src, int(rng.choice([1, -2, 64, 96, -4097, 0])))
+        elif kind == "neg":
+            p.emit(asm.NEGATE, dst, src)
+        elif kind in ("mulcp", "addcp"):
+            key = (l, kind)
+            if key not in pts:
+                pts[key] = p.new_pt()
+                p.encode(pts[key], p.const(rng.uniform(-1, 1, 5)), l, 30)
+            p.emit(asm.MULCP if kind == "mulcp" else asm.ADDCP, dst, src, pts[key])
+        elif kind in ("addcc", "mulcc"):
+            same = [r for r in live if lvl[r] == l]
+            other = int(rng.choice(same))
+            p.emit(asm.ADDCC if kind == "addcc" else asm.MULCC, dst, src, other)
+        elif kind == "resc":
+            if l < 3:
+                continue
+            p.emit(asm.RESCALE, dst, src)
+            l -= 1
+        elif kind == "modsw":
+            if l < 3:
+                continue
+            p.emit(asm.MODSWITCH, dst, src, 1)
+            l -= 1
+        lvl[dst] = l
+        if dst not in live:
+            live.append(dst)
+    for r in live:
+        p.result(r, 40, lvl[r])
+    return p, live
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_scheduler_random_program_bit_exact(pair, tmp_path, seed):
+    g, o = pair
+    p, live = _random_program(seed)
+    cst, hv = tmp_path / "r.cst", tmp_path / "r.hevm"
+    p.save(cst, hv)
+    n = o.N // 2
+    rng = np.random.default_rng(seed)
+    xs = [rng.uniform(-1, 1, n) for _ in range(2)]
+    res = {}
+    for name, vm in (("g", g), ("o", o)):
+        lib = vm.lib
+        lib.load(vm.vm, str(cst).encode(), str(hv).encode())
+        lib.preprocess(vm.vm)
+        lib.hevmx_set_enc_counter(vm.vm, 9)
+        for i, d in enumerate(xs):
+            lib.encrypt(vm.vm, i, d.ctypes.data_as(C.POINTER(C.c_double)), n)
+        lib.run(vm.vm)
+        res[name] = [vm.ct_read(lib.getResIdx(vm.vm, i)) for i in range(len(live))]
+        if name == "g":  # second run = CUDA-graph replay from re-encrypted inputs must give the same registers
+            lib.hevmx_set_enc_counter(vm.vm, 9)
+            for i, d in enumerate(xs):
+                lib.encrypt(vm.vm, i, d.ctypes.data_as(C.POINTER(C.c_double)), n)
+            lib.run(vm.vm)
+            res["g2"] = [vm.ct_read(lib.getResIdx(vm.vm, i)) for i in range(len(live))]
+    for a, b, c in zip(res["g"], res["o"], res["g2"]):
+        assert np.array_equal(a, b)
+        assert np.array_equal(c, b)
+    for vm in pair:
+        vm.lib.hevmx_resize(vm.vm, 8, 4)
