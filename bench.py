@@ -286,7 +286,8 @@ def main():
     ap.add_argument("--batch", type=int, default=28, help="independent ciphertexts per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--op-table", action="store_true", help="also measure the per-op/per-level table and emit profiled_B200_GPU.json")
+    ap.add_argument("--op-table", action="store_true", help="(default at N=1) measure the per-op/per-level table and emit profiled_B200_GPU.json")
+    ap.add_argument("--no-op-table", action="store_true")
     ap.add_argument("--no-resnet-mix", action="store_true", help="skip the ResNet-20 op-mix replay (N=1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -424,15 +425,34 @@ def main():
         "kernels": kern,
     }
 
-    if args.op_table and rank == 0:
-        from dacapo_b200 import profile
-        table, prof = profile.emit_profile(str(REPO / "profiled_B200_GPU.json"), lib, vm)
-        line["op_table_us"] = {op: {str(l): round(v, 2) for l, v in lv.items()} for op, lv in table.items()}
-        line["op_roofline_l13"] = {op: {"us": table[op][13], "frac": profile.algorithmic_bytes(op, 13) / (table[op][13] * 1e-6) / 1e9 / peak}
-                                   for op in ("rotate", "mulcc", "rescale", "addcc", "mulcp")}
-
     if rank == 0 and world == 1 and not args.no_resnet_mix:
         line["resnet20_opmix"] = resnet_mix(lib, vm, tmp, cpu=not args.no_cpu_baseline)
+
+    if (args.op_table or world == 1) and not args.no_op_table and rank == 0:
+        from dacapo_b200 import profile
+        table, prof = profile.emit_profile(str(REPO / "profiled_B200_GPU.json"), lib, vm)
+        kl13 = table.pop("_kernels_rotate_l13", None)
+        line["op_table_us"] = {op: {str(l): round(v, 2) for l, v in lv.items()} for op, lv in table.items()}
+        if kl13 and "fwd_B_mac" in kl13:
+            # roofline of the dominant kernel on ONE well-defined launch shape: the key-switch MAC kernel at level 13
+            l = TOP
+            alg_bytes = (3 * l * l + 5 * l + 2) * BYTES_LIMB
+            us = 1e3 * kl13["fwd_B_mac"]["ms"] / kl13["fwd_B_mac"]["launches"]
+            traffic = None
+            try:
+                traffic = json.loads((REPO / "profiles" / "r01_mac_traffic.json").read_text())["k_mac_l13_dram_bytes"]
+            except Exception:
+                pass
+            tot = sum(k["ms"] for k in kl13.values())
+            line["roofline_all_levels"] = line["roofline"]
+            line["roofline"] = {"bound": "hbm", "kernel": "k_mac (key-switch inner product + forward pass B), level 13", "achieved": alg_bytes / (us * 1e-6) / 1e9,
+                                "peak": peak, "unit": "GB/s", "frac": alg_bytes / (us * 1e-6) / 1e9 / peak, "traffic": traffic,
+                                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": us, "share_of_rotate_l13": kl13["fwd_B_mac"]["ms"] / tot,
+                                "peak_source": peak_src, "kernels_rotate_l13": kl13,
+                                "ceiling_note": "64-bit Shoup butterflies top out at 1.04e12/s on this GPU (tools/pipe_bench.cu): >= 0.236 us per limb-NTT, "
+                                                "i.e. integer pipes, not HBM, bound this kernel"}
+        line["op_roofline_l13"] = {op: {"us": table[op][13], "frac": profile.algorithmic_bytes(op, 13) / (table[op][13] * 1e-6) / 1e9 / peak}
+                                   for op in ("rotate", "mulcc", "rescale", "addcc", "mulcp")}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         subprocess.run(["make", "-s", "-C", str(REPO / "oracle")], check=True)

@@ -38,7 +38,7 @@ def time_op(lib, vm, opcode, dst, lhs, rhs, reps, warmup=2):
     return lib.hevmx_timer(vm, 1) * 1e3 / reps
 
 
-def measure_op_table(lib, vm, levels=None, reps=20, rotate_steps=(1, -2, 4, -8, 16, -32, 64, -128)):
+def measure_op_table(lib, vm, levels=None, reps=20, rotate_steps=(1, -2, 4, -8, 16, -32, 64, -128), kernel_profile_level=None):
     """Per-op, per-level device latency in microseconds.  Register file is resized (program state is lost).
 
     rotate cycles through several Galois keys so that consecutive repetitions do not find their
@@ -62,8 +62,8 @@ def measure_op_table(lib, vm, levels=None, reps=20, rotate_steps=(1, -2, 4, -8, 
         lib.hevmx_pt_write(vm, 0, p.ctypes.data_as(C.POINTER(C.c_uint64)), l, 2.0 ** 40)
 
         def cyc(opcode, rhs_fn, n=reps):
-            # warm-up + timed loop over rotating register pairs
-            for i in range(2):
+            # warm-up (touch every key / register pair once) + timed loop over rotating register pairs
+            for i in range(8):
                 lib.hevmx_exec(vm, opcode, 8 + i % 8, i % 8, rhs_fn(i) & 0xFFFF)
             lib.hevmx_sync(vm)
             lib.hevmx_timer(vm, 0)
@@ -72,6 +72,21 @@ def measure_op_table(lib, vm, levels=None, reps=20, rotate_steps=(1, -2, 4, -8, 
             return lib.hevmx_timer(vm, 1) * 1e3 / n
 
         table["rotate"][l] = cyc(asm.ROTATE, lambda i: rotate_steps[i % len(rotate_steps)])
+        if l == kernel_profile_level and hasattr(lib, "hevmx_profile"):
+            # per-kernel-class CUDA-event timing of the same rotate loop (roofline of the dominant kernel)
+            lib.hevmx_profile(vm, 1)
+            cyc(asm.ROTATE, lambda i: rotate_steps[i % len(rotate_steps)])
+            lib.hevmx_profile(vm, 0)
+            kern, cls = {}, 0
+            while True:
+                t, c = C.c_double(), C.c_int64()
+                name = lib.hevmx_profile_read(vm, cls, C.byref(t), C.byref(c))
+                if name is None:
+                    break
+                if c.value:
+                    kern[name.decode()] = {"ms": t.value, "launches": c.value}
+                cls += 1
+            table["_kernels_rotate_l%d" % l] = kern
         table["mulcc"][l] = cyc(asm.MULCC, lambda i: (i + 1) % 8)
         table["addcc"][l] = cyc(asm.ADDCC, lambda i: (i + 1) % 8)
         table["addcp"][l] = cyc(asm.ADDCP, lambda i: 0)
@@ -122,8 +137,8 @@ def profile_json(table, logN=15, L=14):
     }
 
 
-def emit_profile(path, lib, vm, reps=20):
-    table = measure_op_table(lib, vm, reps=reps)
+def emit_profile(path, lib, vm, reps=20, kernel_profile_level=13):
+    table = measure_op_table(lib, vm, reps=reps, kernel_profile_level=kernel_profile_level)
     prof = profile_json(table, lib.hevmx_param(vm, 0), lib.hevmx_param(vm, 1))
     with open(path, "w") as f:
         json.dump(prof, f, indent=1)
