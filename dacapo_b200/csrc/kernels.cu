@@ -55,56 +55,58 @@ void KProfiler::reset() {
 #define WARPS_PER_CTA 4
 #define CTA_THREADS (WARPS_PER_CTA * 32)
 
-// Every NTT kernel: a CTA is WARPS_PER_CTA independent warps; warp = one job; per-warp shared region =
-// padded value tile + staged twiddles.  No __syncthreads (except the MAC kernel's two CTA barriers).
+// Every NTT kernel: a CTA is WARPS_PER_CTA independent warps; warp = one job; per-warp shared region
+// (dynamic shared memory) = padded value tile + staged twiddles.  No __syncthreads (except the MAC
+// kernel's CTA barriers).
+extern __shared__ __align__(16) u64 dyn_smem[];
 #define WARP_KERNEL_PROLOGUE(LaneT)                                                                                    \
-  __shared__ __align__(16) u64 sm[WARPS_PER_CTA][WARP_SMEM_WORDS];                                                     \
   const int warp = threadIdx.x >> 5, job = blockIdx.x * WARPS_PER_CTA + warp;                                          \
   if (job >= njobs) return;                                                                                            \
+  u64 *sm = dyn_smem + (size_t)warp * Geo<LOGA>::WARP_WORDS;                                                           \
   LaneT st[1];
 
-template <int LD> __global__ void __launch_bounds__(CTA_THREADS) k_intt_B(ArgsInttB a, int njobs) {
+template <int LOGA, int LD> __global__ void __launch_bounds__(CTA_THREADS) k_intt_B(ArgsInttB a, int njobs) {
   WARP_KERNEL_PROLOGUE(LaneB8)
-  body_intt_B<LD>(a, job, st, sm[warp]);
+  body_intt_B<LOGA, LD>(a, job, st, sm);
 }
-__global__ void __launch_bounds__(CTA_THREADS) k_intt_A(ArgsInttA a, int njobs) {
+template <int LOGA> __global__ void __launch_bounds__(CTA_THREADS) k_intt_A(ArgsInttA a, int njobs) {
   WARP_KERNEL_PROLOGUE(LaneA)
-  body_intt_A(a, job, st, sm[warp]);
+  body_intt_A<LOGA>(a, job, st, sm);
 }
-template <int PRE> __global__ void __launch_bounds__(CTA_THREADS) k_fwd_A(ArgsFwdA a, int njobs) {
+template <int LOGA, int PRE> __global__ void __launch_bounds__(CTA_THREADS) k_fwd_A(ArgsFwdA a, int njobs) {
   WARP_KERNEL_PROLOGUE(LaneA)
-  body_fwd_A<PRE>(a, job, st, sm[warp]);
+  body_fwd_A<LOGA, PRE>(a, job, st, sm);
 }
-template <int EPI> __global__ void __launch_bounds__(CTA_THREADS) k_fwd_B(ArgsFwdB a, int njobs) {
+template <int LOGA, int EPI> __global__ void __launch_bounds__(CTA_THREADS) k_fwd_B(ArgsFwdB a, int njobs) {
   WARP_KERNEL_PROLOGUE(LaneB8)
-  body_fwd_B<EPI>(a, job, st, sm[warp]);
+  body_fwd_B<LOGA, EPI>(a, job, st, sm);
 }
 #ifndef FUSEA_MIN_CTAS
 #define FUSEA_MIN_CTAS 4
 #endif
-template <int PRE> __global__ void __launch_bounds__(CTA_THREADS, FUSEA_MIN_CTAS) k_invA_fwdA(ArgsInvFwdA a, int njobs) {
+template <int LOGA, int PRE> __global__ void __launch_bounds__(CTA_THREADS, (LOGA >= 8 ? 3 : FUSEA_MIN_CTAS)) k_invA_fwdA(ArgsInvFwdA a, int njobs) {
   WARP_KERNEL_PROLOGUE(LaneA)
-  body_invA_fwdA<PRE>(a, job, st, sm[warp]);
+  body_invA_fwdA<LOGA, PRE>(a, job, st, sm);
 }
 // key-switch inner product: CTA = one (output prime, row) job, its MAC_WARPS warps split the digits
 #ifndef MAC_MIN_CTAS
-#define MAC_MIN_CTAS 3
+#define MAC_MIN_CTAS 4
 #endif
-__global__ void __launch_bounds__(MAC_WARPS * 32, MAC_MIN_CTAS) k_mac(ArgsFwdB a) {
+template <int LOGA> __global__ void __launch_bounds__(MAC_WARPS * 32, MAC_MIN_CTAS) k_mac(ArgsFwdB a) {
   __shared__ __align__(16) u64 sm[MAC_SMEM_WORDS];
   Tw *tw_s = reinterpret_cast<Tw *>(sm);
   u64 *tiles = sm + MAC_TW_WORDS;
   u64 *parts = tiles + MAC_WARPS * TILE_B_WORDS;
   const int job = blockIdx.x, warp = threadIdx.x >> 5;
-  body_mac_stage(a, job, threadIdx.x, tw_s);
+  body_mac_stage<LOGA>(a, job, threadIdx.x, tw_s);
   __syncthreads();
   LaneB8 st[1];
-  body_mac_warp(a, job, warp, st, tiles + warp * TILE_B_WORDS, tw_s, parts + warp * MAC_PART_WORDS);
+  body_mac_warp<LOGA>(a, job, warp, st, tiles + warp * TILE_B_WORDS, tw_s, parts + warp * MAC_PART_WORDS);
   __syncthreads();
-  body_mac_reduce(a, job, threadIdx.x, parts, tiles);
-  if (mac_Iidx(a, job) == a.l) { // special prime: continue with the inverse pass B of the two accumulator rows
+  body_mac_reduce<LOGA>(a, job, threadIdx.x, parts, tiles);
+  if (mac_Iidx<LOGA>(a, job) == a.l) { // special prime: continue with the inverse pass B of the two accumulator rows
     __syncthreads();
-    if (warp < 2) body_mac_tail(a, job, warp, st, parts + warp * MAC_PART_WORDS, tw_s, tiles);
+    if (warp < 2) body_mac_tail<LOGA>(a, job, warp, st, parts + warp * MAC_PART_WORDS, tw_s, tiles);
   }
 }
 
@@ -112,15 +114,28 @@ static inline int ctas_for(int njobs) { return (njobs + WARPS_PER_CTA - 1) / WAR
 // launch with programmatic stream serialization: the kernel may begin (twiddle staging) while its
 // predecessor drains; every such kernel executes griddepcontrol.wait before touching global data
 template <class... KArgs, class... Args>
-static void launch_pdl(void (*kern)(KArgs...), int grid, int block, cudaStream_t s, Args... args) {
+static void launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args... args) {
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(block), cfg.dynamicSmemBytes = 0, cfg.stream = s;
+  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(block), cfg.dynamicSmemBytes = smem, cfg.stream = s;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   static const bool no_pdl = std::getenv("HEVM_PDL") && std::atoi(std::getenv("HEVM_PDL")) == 0;
   cfg.attrs = at, cfg.numAttrs = (no_pdl || g_pdl_suspended) ? 0 : 1;
   CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, args...));
+}
+// dynamic shared memory of the warp kernels (may exceed the 48 KB default: opt in once per kernel)
+template <int LOGA, class K> static size_t warp_smem(K kern) {
+  const size_t bytes = (size_t)WARPS_PER_CTA * Geo<LOGA>::WARP_WORDS * sizeof(u64);
+  static bool done = false; // one instance per (LOGA, K) instantiation... K is a function-pointer TYPE: guard per pointer below
+  static const void *seen[16];
+  static int nseen = 0;
+  (void)done;
+  for (int i = 0; i < nseen; i++)
+    if (seen[i] == (const void *)kern) return bytes;
+  CUDA_CHECK(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  if (nseen < 16) seen[nseen++] = (const void *)kern;
+  return bytes;
 }
 #define PRE_LAUNCH(s, cls) g_prof.begin(s, cls)
 #define POST_LAUNCH_S(s)                                                                                               \
@@ -130,54 +145,58 @@ static void launch_pdl(void (*kern)(KArgs...), int grid, int block, cudaStream_t
     CUDA_CHECK(cudaGetLastError());                                                                                    \
   } while (0)
 
-template <int LD> void GpuLauncher::intt_B(const ArgsInttB &a, int njobs) {
+template <int LOGA, int LD> void GpuLauncher::intt_B(const ArgsInttB &a, int njobs) {
   if (njobs <= 0) return;
   PRE_LAUNCH(stream, KC_INTT_B_PLAIN + LD);
-  launch_pdl(k_intt_B<LD>, ctas_for(njobs), CTA_THREADS, stream, a, njobs);
+  launch_pdl(k_intt_B<LOGA, LD>, ctas_for(njobs), CTA_THREADS, warp_smem<LOGA>(k_intt_B<LOGA, LD>), stream, a, njobs);
   POST_LAUNCH_S(stream);
 }
-void GpuLauncher::intt_A(const ArgsInttA &a, int njobs) {
+template <int LOGA> void GpuLauncher::intt_A(const ArgsInttA &a, int njobs) {
   if (njobs <= 0) return;
   PRE_LAUNCH(stream, KC_INTT_A);
-  launch_pdl(k_intt_A, ctas_for(njobs), CTA_THREADS, stream, a, njobs);
+  launch_pdl(k_intt_A<LOGA>, ctas_for(njobs), CTA_THREADS, warp_smem<LOGA>(k_intt_A<LOGA>), stream, a, njobs);
   POST_LAUNCH_S(stream);
 }
-template <int PRE> void GpuLauncher::fwd_A(const ArgsFwdA &a, int njobs) {
+template <int LOGA, int PRE> void GpuLauncher::fwd_A(const ArgsFwdA &a, int njobs) {
   if (njobs <= 0) return;
   PRE_LAUNCH(stream, KC_FWD_A_NONE + PRE);
-  launch_pdl(k_fwd_A<PRE>, ctas_for(njobs), CTA_THREADS, stream, a, njobs);
+  launch_pdl(k_fwd_A<LOGA, PRE>, ctas_for(njobs), CTA_THREADS, warp_smem<LOGA>(k_fwd_A<LOGA, PRE>), stream, a, njobs);
   POST_LAUNCH_S(stream);
 }
-template <int EPI> void GpuLauncher::fwd_B(const ArgsFwdB &a, int njobs) {
+template <int LOGA, int EPI> void GpuLauncher::fwd_B(const ArgsFwdB &a, int njobs) {
   if (njobs <= 0) return;
   PRE_LAUNCH(stream, KC_FWD_B_CANON + EPI);
-  launch_pdl(k_fwd_B<EPI>, ctas_for(njobs), CTA_THREADS, stream, a, njobs);
+  launch_pdl(k_fwd_B<LOGA, EPI>, ctas_for(njobs), CTA_THREADS, warp_smem<LOGA>(k_fwd_B<LOGA, EPI>), stream, a, njobs);
   POST_LAUNCH_S(stream);
 }
-void GpuLauncher::mac(const ArgsFwdB &a, int njobs) {
+template <int LOGA> void GpuLauncher::mac(const ArgsFwdB &a, int njobs) {
   if (njobs <= 0) return;
   PRE_LAUNCH(stream, KC_FWD_B_MAC);
-  launch_pdl(k_mac, njobs, MAC_WARPS * 32, stream, a);
+  launch_pdl(k_mac<LOGA>, njobs, MAC_WARPS * 32, 0, stream, a);
   POST_LAUNCH_S(stream);
 }
-template <int PRE> void GpuLauncher::invA_fwdA(const ArgsInvFwdA &a, int njobs) {
+template <int LOGA, int PRE> void GpuLauncher::invA_fwdA(const ArgsInvFwdA &a, int njobs) {
   if (njobs <= 0) return;
   PRE_LAUNCH(stream, PRE == PRE_MODUP ? KC_INVA_FWDA_MODUP : KC_INVA_FWDA_ROUND);
-  launch_pdl(k_invA_fwdA<PRE>, ctas_for(njobs), CTA_THREADS, stream, a, njobs);
+  launch_pdl(k_invA_fwdA<LOGA, PRE>, ctas_for(njobs), CTA_THREADS, warp_smem<LOGA>(k_invA_fwdA<LOGA, PRE>), stream, a, njobs);
   POST_LAUNCH_S(stream);
 }
-template void GpuLauncher::invA_fwdA<PRE_MODUP>(const ArgsInvFwdA &, int);
-template void GpuLauncher::invA_fwdA<PRE_ROUND>(const ArgsInvFwdA &, int);
-template void GpuLauncher::intt_B<LD_PLAIN>(const ArgsInttB &, int);
-template void GpuLauncher::intt_B<LD_GALOIS>(const ArgsInttB &, int);
-template void GpuLauncher::intt_B<LD_PRODUCT>(const ArgsInttB &, int);
-template void GpuLauncher::fwd_A<PRE_NONE>(const ArgsFwdA &, int);
-template void GpuLauncher::fwd_A<PRE_MODUP>(const ArgsFwdA &, int);
-template void GpuLauncher::fwd_A<PRE_ROUND>(const ArgsFwdA &, int);
-template void GpuLauncher::fwd_B<EPI_CANON>(const ArgsFwdB &, int);
-template void GpuLauncher::fwd_B<EPI_MODDOWN_GALOIS>(const ArgsFwdB &, int);
-template void GpuLauncher::fwd_B<EPI_MODDOWN_RELIN>(const ArgsFwdB &, int);
-template void GpuLauncher::fwd_B<EPI_RESCALE>(const ArgsFwdB &, int);
+#define INSTANTIATE(LOGA)                                                                                              \
+  template void GpuLauncher::intt_B<LOGA, LD_PLAIN>(const ArgsInttB &, int);                                           \
+  template void GpuLauncher::intt_B<LOGA, LD_GALOIS>(const ArgsInttB &, int);                                          \
+  template void GpuLauncher::intt_B<LOGA, LD_PRODUCT>(const ArgsInttB &, int);                                         \
+  template void GpuLauncher::intt_A<LOGA>(const ArgsInttA &, int);                                                     \
+  template void GpuLauncher::fwd_A<LOGA, PRE_NONE>(const ArgsFwdA &, int);                                             \
+  template void GpuLauncher::fwd_B<LOGA, EPI_CANON>(const ArgsFwdB &, int);                                            \
+  template void GpuLauncher::fwd_B<LOGA, EPI_MODDOWN_GALOIS>(const ArgsFwdB &, int);                                   \
+  template void GpuLauncher::fwd_B<LOGA, EPI_MODDOWN_RELIN>(const ArgsFwdB &, int);                                    \
+  template void GpuLauncher::fwd_B<LOGA, EPI_RESCALE>(const ArgsFwdB &, int);                                          \
+  template void GpuLauncher::mac<LOGA>(const ArgsFwdB &, int);                                                         \
+  template void GpuLauncher::invA_fwdA<LOGA, PRE_MODUP>(const ArgsInvFwdA &, int);                                     \
+  template void GpuLauncher::invA_fwdA<LOGA, PRE_ROUND>(const ArgsInvFwdA &, int);
+INSTANTIATE(6)
+INSTANTIATE(7)
+INSTANTIATE(8)
 
 // =====================================================================================
 // element-wise kernels.  One thread = 4 consecutive coefficients (256-bit accesses).

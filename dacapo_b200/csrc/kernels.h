@@ -45,12 +45,12 @@ extern KProfiler g_prof;
 
 struct GpuLauncher {
   cudaStream_t stream = nullptr;
-  template <int LD> void intt_B(const ArgsInttB &a, int njobs);
-  void intt_A(const ArgsInttA &a, int njobs);
-  template <int PRE> void fwd_A(const ArgsFwdA &a, int njobs);
-  template <int EPI> void fwd_B(const ArgsFwdB &a, int njobs);
-  template <int PRE> void invA_fwdA(const ArgsInvFwdA &a, int njobs);
-  void mac(const ArgsFwdB &a, int njobs); // one 4-warp CTA per job
+  template <int LOGA, int LD> void intt_B(const ArgsInttB &a, int njobs);
+  template <int LOGA> void intt_A(const ArgsInttA &a, int njobs);
+  template <int LOGA, int PRE> void fwd_A(const ArgsFwdA &a, int njobs);
+  template <int LOGA, int EPI> void fwd_B(const ArgsFwdB &a, int njobs);
+  template <int LOGA, int PRE> void invA_fwdA(const ArgsInvFwdA &a, int njobs);
+  template <int LOGA> void mac(const ArgsFwdB &a, int njobs); // one 4-warp CTA per job
 };
 
 // ---- element-wise ciphertext kernels (SEAL add/negate/add_plain/multiply_plain, limb drop) ----

@@ -1,4 +1,4 @@
-// Warp-job bodies of the NTT-based kernels (N = 2^15: 128 rows x 256 cols).
+// Warp-job bodies of the NTT-based kernels (N = 2^LOGA rows x 256 cols; LOGA = 6,7,8 <=> N = 2^14..2^16).
 // One warp executes one job (a (limb, tile) or (limb, row) pair); the key-switch inner-product
 // kernel uses one 4-warp CTA per (output prime, row) and splits the digit loop over its warps.
 // See ntt_core.cuh for the schedule, kernels.cu for the __global__ wrappers.
@@ -22,9 +22,6 @@ enum { LD_PLAIN = 0, LD_GALOIS = 1, LD_PRODUCT = 2 };
 enum { PRE_NONE = 0, PRE_MODUP = 1, PRE_ROUND = 2 };
 enum { EPI_CANON = 0, EPI_MAC = 1, EPI_MODDOWN_GALOIS = 2, EPI_MODDOWN_RELIN = 3, EPI_RESCALE = 4 };
 
-#define LOGB8 8
-#define ROWS 128
-#define TILES_A 64 // 256 cols / 4
 #define MAC_WARPS 4
 #define MAC_PART_WORDS 1024 // per warp: 2 keys x 256 values x (lo,hi)
 // shared memory of one MAC CTA (words): staged twiddles | MAC_WARPS tiles | MAC_WARPS partial-sum blocks
@@ -33,6 +30,7 @@ enum { EPI_CANON = 0, EPI_MAC = 1, EPI_MODDOWN_GALOIS = 2, EPI_MODDOWN_RELIN = 3
 #define MAC_SMEM_WORDS (MAC_TW_WORDS + MAC_WARPS * TILE_B_WORDS + MAC_WARPS * MAC_PART_WORDS)
 
 HD Tw *warp_tw(u64 *sm) { return reinterpret_cast<Tw *>(sm + WARP_TILE_WORDS); }
+template <int LOGA> constexpr bool pass_a_needs_fold(int pre) { return pre == 2 /*PRE_ROUND*/ || LOGA >= 8; }
 
 HD void load8_stream(const u64 *p, u64 (&v)[8]) {
   ldg_stream4(p, v[0], v[1], v[2], v[3]);
@@ -63,10 +61,10 @@ struct ArgsInttB {
   size_t sstride; // words between consecutive source limbs (0 = N)
 };
 
-template <int LD> HD void body_intt_B(const ArgsInttB &a, int job, LaneB8 *st, u64 *sm) {
+template <int LOGA, int LD> HD void body_intt_B(const ArgsInttB &a, int job, LaneB8 *st, u64 *sm) {
   const NttTables &T = *a.T;
   const int N = 1 << T.logN;
-  const int limb = job >> 7, r = job & 127;
+  const int limb = job >> LOGA, r = job & (Geo<LOGA>::ROWS - 1);
   const int p = a.prime0 + limb * a.pstep;
   const ModQ m = T.mod[p];
   const u64 *src = a.src + (size_t)limb * (a.sstride ? a.sstride : (size_t)N);
@@ -74,7 +72,7 @@ template <int LD> HD void body_intt_B(const ArgsInttB &a, int job, LaneB8 *st, u
   LANE_DECL;
   FOR_LANES(S, st, {
     grid_dep_launch();
-    stage_tw_B(tw, T.itw + (size_t)p * N, r, lane);
+    stage_tw_B<LOGA>(tw, T.itw + (size_t)p * N, r, lane);
     grid_dep_wait();
     const int base = r * 256 + lane * 8;
     if (LD == LD_PLAIN) {
@@ -116,10 +114,10 @@ struct ArgsInttA {
   int nl, prime0, pstep;
   int round; // add half
 };
-HD void body_intt_A(const ArgsInttA &a, int job, LaneA *st, u64 *sm) {
+template <int LOGA> HD void body_intt_A(const ArgsInttA &a, int job, LaneA *st, u64 *sm) {
   const NttTables &T = *a.T;
   const int N = 1 << T.logN;
-  const int limb = job >> 6, tile = job & 63;
+  const int limb = job >> Geo<LOGA>::LOGT, tile = job & (Geo<LOGA>::TILES - 1);
   const int p = a.prime0 + limb * a.pstep;
   const ModQ m = T.mod[p];
   const u64 q = m.q;
@@ -128,19 +126,19 @@ HD void body_intt_A(const ArgsInttA &a, int job, LaneA *st, u64 *sm) {
   FOR_LANES(S, st, {
     (void)S;
     grid_dep_launch();
-    stage_tw_A(tw, T.itw + (size_t)p * N, lane);
+    stage_tw_A<LOGA>(tw, T.itw + (size_t)p * N, lane);
     grid_dep_wait();
     cp_async_wait();
   });
-  warp_invA_to_regs<LOGB8>(st, sm, a.src + (size_t)limb * N, tile * 4, tw, m, T.invn[p], T.invn_w[p]);
-  u64 *dst = a.dst + (size_t)limb * N + tile * 4;
+  warp_invA_to_regs<LOGA>(st, sm, a.src + (size_t)limb * N, tile * Geo<LOGA>::C, tw, m, T.invn[p], T.invn_w[p]);
+  u64 *dst = a.dst + (size_t)limb * N + tile * Geo<LOGA>::C;
   const u64 half = q >> 1;
   FOR_LANES(S, st, {
     _Pragma("unroll")
     for (int e = 0; e < 16; e++) {
       u64 v = S.x[e];
       if (a.round) v = csub(v + half, q);
-      dst[((size_t)rowR(lane, e) << LOGB8) + (lane & 3)] = v;
+      dst[((size_t)rowR<LOGA>(lane, e) << 8) + colA<LOGA>(lane)] = v;
     }
   });
 }
@@ -160,10 +158,10 @@ struct ArgsFwdA {
   int sp;    // MODUP: special prime index
   int plast; // ROUND: prime index of the divided-out modulus
 };
-template <int PRE> HD void body_fwd_A(const ArgsFwdA &a, int job, LaneA *st, u64 *sm) {
+template <int LOGA, int PRE> HD void body_fwd_A(const ArgsFwdA &a, int job, LaneA *st, u64 *sm) {
   const NttTables &T = *a.T;
   const int N = 1 << T.logN;
-  const int d = job >> 6, tile = job & 63;
+  const int d = job >> Geo<LOGA>::LOGT, tile = job & (Geo<LOGA>::TILES - 1);
   int ps, pd, sl; // source prime, destination prime, source limb
   if (PRE == PRE_NONE) {
     sl = d;
@@ -181,17 +179,17 @@ template <int PRE> HD void body_fwd_A(const ArgsFwdA &a, int job, LaneA *st, u64
     pd = d - K * a.l;
   }
   const ModQ m = T.mod[pd];
-  const u64 *src = a.src + (size_t)sl * N + tile * 4;
+  const u64 *src = a.src + (size_t)sl * N + tile * Geo<LOGA>::C;
   u64 fix = 0;
   if (PRE == PRE_ROUND) fix = m.q - reduce64(T.mod[ps].q >> 1, m);
   Tw *tw = warp_tw(sm);
   LANE_DECL;
   FOR_LANES(S, st, {
     grid_dep_launch();
-    stage_tw_A(tw, T.tw + (size_t)pd * N, lane);
+    stage_tw_A<LOGA>(tw, T.tw + (size_t)pd * N, lane);
     grid_dep_wait();
     _Pragma("unroll")
-    for (int e = 0; e < 16; e++) S.y[e] = ldg_stream(src + ((size_t)rowR(lane, e) << LOGB8) + (lane & 3));
+    for (int e = 0; e < 16; e++) S.y[e] = ldg_stream(src + ((size_t)rowR<LOGA>(lane, e) << 8) + colA<LOGA>(lane));
     // No modular reduction: every prime is 2^60 - delta with delta < 2^32, so a canonical residue of
     // ANY prime is < 2^60 < 2*q_dst, i.e. already a valid lazy representative mod q_dst.
     _Pragma("unroll")
@@ -199,7 +197,7 @@ template <int PRE> HD void body_fwd_A(const ArgsFwdA &a, int job, LaneA *st, u64
     cp_async_wait();
   });
   (void)ps;
-  warp_fwdA_from_regs<LOGB8, PRE == PRE_ROUND>(st, sm, a.dst + (size_t)d * N, tile * 4, tw, m);
+  warp_fwdA_from_regs<LOGA, pass_a_needs_fold<LOGA>(PRE)>(st, sm, a.dst + (size_t)d * N, tile * Geo<LOGA>::C, tw, m);
 }
 
 
@@ -219,10 +217,10 @@ struct ArgsInvFwdA {
   u64 *dst;
   int nsrc, l, sp, plast, ngroups;
 };
-template <int PRE> HD void body_invA_fwdA(const ArgsInvFwdA &a, int job, LaneA *st, u64 *sm) {
+template <int LOGA, int PRE> HD void body_invA_fwdA(const ArgsInvFwdA &a, int job, LaneA *st, u64 *sm) {
   const NttTables &T = *a.T;
   const int N = 1 << T.logN;
-  const int tile = job & 63, rest = job >> 6;
+  const int tile = job & (Geo<LOGA>::TILES - 1), rest = job >> Geo<LOGA>::LOGT;
   const int sl = rest / a.ngroups, grp = rest - sl * a.ngroups;
   const int ntargets = (PRE == PRE_MODUP) ? a.l + 1 : a.l;
   const int tpj = (ntargets + a.ngroups - 1) / a.ngroups;
@@ -237,18 +235,18 @@ template <int PRE> HD void body_invA_fwdA(const ArgsInvFwdA &a, int job, LaneA *
   };
   int t = next_valid(grp * tpj);
   if (t >= tend) return;
-  Tw *tw_inv = warp_tw(sm), *tw_fwd = tw_inv + 128;
+  Tw *tw_inv = warp_tw(sm), *tw_fwd = tw_inv + Geo<LOGA>::ROWS;
   int buf = 0;
   LANE_DECL;
   FOR_LANES(S, st, {
     (void)S;
     grid_dep_launch();
-    stage_tw_A(tw_inv, T.itw + (size_t)ps * N, lane);
-    stage_tw_A(tw_fwd, T.tw + (size_t)prime_of(t) * N, lane);
+    stage_tw_A<LOGA>(tw_inv, T.itw + (size_t)ps * N, lane);
+    stage_tw_A<LOGA>(tw_fwd, T.tw + (size_t)prime_of(t) * N, lane);
     grid_dep_wait();
     cp_async_wait();
   });
-  warp_invA_to_regs<LOGB8>(st, sm, a.src + (size_t)sl * N, tile * 4, tw_inv, ms, T.invn[ps], T.invn_w[ps]);
+  warp_invA_to_regs<LOGA>(st, sm, a.src + (size_t)sl * N, tile * Geo<LOGA>::C, tw_inv, ms, T.invn[ps], T.invn_w[ps]);
   if (PRE == PRE_ROUND) {
     const u64 half = ms.q >> 1;
     FOR_LANES(S, st, {
@@ -263,7 +261,7 @@ template <int PRE> HD void body_invA_fwdA(const ArgsInvFwdA &a, int job, LaneA *
     u64 fix = 0;
     if (PRE == PRE_ROUND) fix = m.q - reduce64(ms.q >> 1, m);
     FOR_LANES(S, st, {
-      if (tn < tend) stage_tw_A(tw_fwd + 128 * (buf ^ 1), T.tw + (size_t)prime_of(tn) * N, lane); // prefetch next table
+      if (tn < tend) stage_tw_A<LOGA>(tw_fwd + Geo<LOGA>::ROWS * (buf ^ 1), T.tw + (size_t)prime_of(tn) * N, lane); // prefetch next table
       cp_async_commit();
       // no modular reduction needed (see body_fwd_A): x < 2^60 < 2*q_dst is a valid lazy representative
       _Pragma("unroll")
@@ -271,7 +269,7 @@ template <int PRE> HD void body_invA_fwdA(const ArgsInvFwdA &a, int job, LaneA *
       cp_async_wait_keep1(); // the current table (older group) has landed
     });
     u64 *dst = (PRE == PRE_MODUP) ? a.dst + ((size_t)t * a.l + sl) * N : a.dst + ((size_t)sl * a.l + t) * N;
-    warp_fwdA_from_regs<LOGB8, PRE == PRE_ROUND>(st, sm, dst, tile * 4, tw_fwd + 128 * buf, m);
+    warp_fwdA_from_regs<LOGA, pass_a_needs_fold<LOGA>(PRE)>(st, sm, dst, tile * Geo<LOGA>::C, tw_fwd + Geo<LOGA>::ROWS * buf, m);
     buf ^= 1;
     t = tn;
   }
@@ -309,21 +307,21 @@ struct ArgsFwdB {
 // ---- key-switch inner product: one CTA of MAC_WARPS warps per (Iidx, row) ----------------------
 // phase 0 (all threads of the CTA): stage the row's twiddles of prime I
 // job -> (Iidx, row): the special prime (Iidx = l) comes first because its CTAs carry the extra tail
-HD int mac_Iidx(const ArgsFwdB &a, int job) { return a.l - (job >> 7); }
-HD void body_mac_stage(const ArgsFwdB &a, int job, int tid, Tw *tw_s) {
+template <int LOGA> HD int mac_Iidx(const ArgsFwdB &a, int job) { return a.l - (job >> LOGA); }
+template <int LOGA> HD void body_mac_stage(const ArgsFwdB &a, int job, int tid, Tw *tw_s) {
   const NttTables &T = *a.T;
   const int N = 1 << T.logN;
-  const int r = job & 127, Iidx = mac_Iidx(a, job), I = (Iidx == a.l) ? a.sp : Iidx;
+  const int r = job & (Geo<LOGA>::ROWS - 1), Iidx = mac_Iidx<LOGA>(a, job), I = (Iidx == a.l) ? a.sp : Iidx;
   grid_dep_launch();
-  stage_tw_B(tw_s, T.tw + (size_t)I * N, r, tid, MAC_WARPS * 32);
+  stage_tw_B<LOGA>(tw_s, T.tw + (size_t)I * N, r, tid, MAC_WARPS * 32);
   grid_dep_wait();
   cp_async_wait();
 }
 // phase 1 (per warp): digits J = w, w + MAC_WARPS, ...; partial sums -> part[(K*256 + e*32 + lane)*2 + {lo,hi}]
-HD void body_mac_warp(const ArgsFwdB &a, int job, int w, LaneB8 *st, u64 *tile, const Tw *tw_s, u64 *part) {
+template <int LOGA> HD void body_mac_warp(const ArgsFwdB &a, int job, int w, LaneB8 *st, u64 *tile, const Tw *tw_s, u64 *part) {
   const NttTables &T = *a.T;
   const int N = 1 << T.logN;
-  const int r = job & 127, Iidx = mac_Iidx(a, job), I = (Iidx == a.l) ? a.sp : Iidx;
+  const int r = job & (Geo<LOGA>::ROWS - 1), Iidx = mac_Iidx<LOGA>(a, job), I = (Iidx == a.l) ? a.sp : Iidx;
   const ModQ m = T.mod[I];
   LANE_DECL;
   u64 lo0[NLANE_STATE][8], hi0[NLANE_STATE][8], lo1[NLANE_STATE][8], hi1[NLANE_STATE][8];
@@ -405,10 +403,10 @@ HD void body_mac_warp(const ArgsFwdB &a, int job, int w, LaneB8 *st, u64 *tile, 
 // phase 2 (all threads, after a CTA barrier): sum the per-warp partials, Barrett.
 // Data primes: store acc[K][Iidx][row].  Special prime: keep the two rows in shared memory (`rows`,
 // [2][256]) for phase 3 instead -- nobody else reads them.
-HD void body_mac_reduce(const ArgsFwdB &a, int job, int tid, const u64 *parts, u64 *rows) {
+template <int LOGA> HD void body_mac_reduce(const ArgsFwdB &a, int job, int tid, const u64 *parts, u64 *rows) {
   const NttTables &T = *a.T;
   const int N = 1 << T.logN;
-  const int r = job & 127, Iidx = mac_Iidx(a, job), I = (Iidx == a.l) ? a.sp : Iidx;
+  const int r = job & (Geo<LOGA>::ROWS - 1), Iidx = mac_Iidx<LOGA>(a, job), I = (Iidx == a.l) ? a.sp : Iidx;
   const ModQ m = T.mod[I];
   _Pragma("unroll")
   for (int it = 0; it < 512 / (MAC_WARPS * 32); it++) {
@@ -431,14 +429,14 @@ HD void body_mac_reduce(const ArgsFwdB &a, int job, int tid, const u64 *parts, u
 }
 // phase 3 (special-prime CTAs only, warps K = 0,1, after a CTA barrier): inverse pass B of row r of the
 // accumulator acc[K][special] (first step of the mod-down), straight from shared memory.
-HD void body_mac_tail(const ArgsFwdB &a, int job, int K, LaneB8 *st, u64 *tile, Tw *tw_s, const u64 *rows) {
+template <int LOGA> HD void body_mac_tail(const ArgsFwdB &a, int job, int K, LaneB8 *st, u64 *tile, Tw *tw_s, const u64 *rows) {
   const NttTables &T = *a.T;
   const int N = 1 << T.logN;
-  const int r = job & 127;
+  const int r = job & (Geo<LOGA>::ROWS - 1);
   const ModQ m = T.mod[a.sp];
   LANE_DECL;
   FOR_LANES(S, st, {
-    stage_tw_B(tw_s, T.itw + (size_t)a.sp * N, r, lane); // both warps stage the same table (identical bytes)
+    stage_tw_B<LOGA>(tw_s, T.itw + (size_t)a.sp * N, r, lane); // both warps stage the same table (identical bytes)
     _Pragma("unroll")
     for (int e = 0; e < 8; e++) S.x[e] = rows[K * 256 + lane * 8 + e];
     cp_async_wait();
@@ -451,10 +449,10 @@ HD void body_mac_tail(const ArgsFwdB &a, int job, int K, LaneB8 *st, u64 *tile, 
   });
 }
 
-template <int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, LaneB8 *st, u64 *sm) {
+template <int LOGA, int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, LaneB8 *st, u64 *sm) {
   const NttTables &T = *a.T;
   const int N = 1 << T.logN;
-  const int r = job & 127, d = job >> 7;
+  const int r = job & (Geo<LOGA>::ROWS - 1), d = job >> LOGA;
   Tw *tw = warp_tw(sm);
   LANE_DECL;
   if (EPI == EPI_CANON) {
@@ -463,7 +461,7 @@ template <int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, LaneB8 *st, u6
     const u64 *src = a.src + (size_t)d * N + r * 256;
     FOR_LANES(S, st, {
       grid_dep_launch();
-      stage_tw_B(tw, T.tw + (size_t)p * N, r, lane);
+      stage_tw_B<LOGA>(tw, T.tw + (size_t)p * N, r, lane);
       grid_dep_wait();
       _Pragma("unroll")
       for (int e = 0; e < 8; e++) S.x[e] = ldg_stream(src + idxH(lane, e));
@@ -492,7 +490,7 @@ template <int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, LaneB8 *st, u6
       FOR_LANES(S, st, {
         if (K == 0) {
           grid_dep_launch();
-          stage_tw_B(tw, T.tw + (size_t)i * N, r, lane);
+          stage_tw_B<LOGA>(tw, T.tw + (size_t)i * N, r, lane);
           grid_dep_wait();
         }
         if (K == 1) {
@@ -539,7 +537,7 @@ template <int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, LaneB8 *st, u6
     const u64 *src = a.src + (size_t)d * N + r * 256;
     FOR_LANES(S, st, {
       grid_dep_launch();
-      stage_tw_B(tw, T.tw + (size_t)i * N, r, lane);
+      stage_tw_B<LOGA>(tw, T.tw + (size_t)i * N, r, lane);
       grid_dep_wait();
       _Pragma("unroll")
       for (int e = 0; e < 8; e++) S.x[e] = ldg_stream(src + idxH(lane, e));

@@ -1,4 +1,4 @@
-// Warp-synchronous negacyclic NTT building blocks (N = 2^LOGN, LOGN = 7 + LOGB).
+// Warp-synchronous negacyclic NTT building blocks (N = 2^(LOGA+8)).
 //
 // Replaces SEAL 4.0 ntt_negacyclic_harvey(_lazy) / inverse_ntt_negacyclic_harvey that the
 // reference reaches through seal::Evaluator (reference: lib/Runtime/SEAL_HEVM.cpp:273,283,
@@ -6,11 +6,11 @@
 // natural in -> bit-reversed out; inverse = Gentleman-Sande + N^-1.  Any schedule of the
 // same butterfly DAG gives the same canonical residues, so the schedule is B200-first:
 //
-//   N = 2^7 (rows) x 2^LOGB (cols).  Two passes per transform, one HBM/L2 round trip between:
-//   pass A  "strided":    a warp owns a tile of 128 rows x 4 cols (32 B sectors, 16 values/lane)
-//                         and does the 7 stages whose butterfly span is >= one row.
-//   pass B  "contiguous": a warp owns one row (2^LOGB contiguous values, 8 or 16 per lane) and
-//                         does the remaining LOGB stages.
+//   N = 2^LOGA (rows) x 256 (cols), LOGA = 6,7,8.  Two passes per transform, one HBM/L2 round trip between:
+//   pass A  "strided":    a warp owns a tile of 2^LOGA rows x C cols (512 values, 16 per lane; C = 4 and
+//                         32 B sectors at N = 2^15) and does the LOGA stages whose span is >= one row.
+//   pass B  "contiguous": a warp owns one row (256 contiguous values, 8 per lane) and does the
+//                         remaining 8 stages.
 //   Inside a pass, values live in registers; a warp-private padded shared-memory tile is used
 //   only to re-distribute values between rounds of 2-4 register-resident stages (__syncwarp,
 //   never __syncthreads).  Shared tile index idx -> idx + idx/16 makes every 64-bit access
@@ -111,38 +111,50 @@ HD void stg4(u64 *p, u64 a, u64 b, u64 c, u64 d) { p[0] = a, p[1] = b, p[2] = c,
 
 HD int padx(int idx) { return idx + (idx >> 4); }
 #define WARP_TILE_WORDS 544  // 512 values + 512/16 padding
-#define WARP_TW_ENTRIES 384  // staged twiddles: pass B 255; fused inverse+forward pass A 128 + 2x128
-#define WARP_SMEM_WORDS (WARP_TILE_WORDS + 2 * WARP_TW_ENTRIES)
+
+// Ring geometry: N = 2^LOGA rows x 256 columns (LOGA = logN - 8; 6, 7, 8 <=> N = 2^14, 2^15, 2^16).
+// Pass A tile = 2^LOGA rows x C columns with 2^LOGA * C = 512 values (16 per lane).
+template <int LOGA> struct Geo {
+  static constexpr int ROWS = 1 << LOGA;
+  static constexpr int LOGC = 9 - LOGA;      // log2(columns per pass-A tile)
+  static constexpr int C = 1 << LOGC;
+  static constexpr int TILES = 256 / C;      // pass-A tiles per limb
+  static constexpr int LOGT = 8 - LOGC;
+  // staged twiddles per warp: pass B 255; fused inverse+forward pass A: ROWS + 2 x ROWS
+  static constexpr int TW = (3 * ROWS > 256) ? 3 * ROWS : 256;
+  static constexpr int WARP_WORDS = WARP_TILE_WORDS + 2 * TW;
+};
 
 // ---- twiddle staging (one cp.async batch per job) ------------------------------------------------
-// pass A: entries [0,128) of the prime's table (tw[m+g], m+g < 128)
-HD void stage_tw_A(Tw *dst, const Tw *table, int lane) {
+// pass A: entries [0,ROWS) of the prime's table (tw[m+g], m+g < ROWS)
+template <int LOGA> HD void stage_tw_A(Tw *dst, const Tw *table, int lane) {
   _Pragma("unroll")
-  for (int i = 0; i < 4; i++) cp_async16(dst + lane + 32 * i, table + lane + 32 * i);
+  for (int i = 0; i < Geo<LOGA>::ROWS / 32; i++) cp_async16(dst + lane + 32 * i, table + lane + 32 * i);
 }
-// pass B, row r: local entry (2^k - 1 + g) <- table[(128 << k) + (r << k) + g],  k < 8, g < 2^k
+// pass B, row r: local entry (2^k - 1 + g) <- table[(ROWS << k) + (r << k) + g],  k < 8, g < 2^k
 // (one contiguous run of 2^k entries per local stage).  `tid`/`nthr`: the threads sharing the copy.
-HD void stage_tw_B(Tw *dst, const Tw *table, int r, int tid, int nthr = 32) {
+template <int LOGA> HD void stage_tw_B(Tw *dst, const Tw *table, int r, int tid, int nthr = 32) {
   _Pragma("unroll")
   for (int k = 0; k < 8; k++) {
-    const Tw *src = table + (128 << k) + (r << k);
+    const Tw *src = table + (Geo<LOGA>::ROWS << k) + (r << k);
     Tw *d = dst + ((1 << k) - 1);
     for (int g = tid; g < (1 << k); g += nthr) cp_async16(d + g, src + g);
   }
 }
 
 // =====================================================================================
-// Pass A (strided): tile = 128 rows x 4 cols, tile index = row*4 + col.
-//   layout R  ("row-major lanes"): x[e] <-> row = e*8 + (lane>>2),       col = lane&3, idx = e*32 + lane
-//   layout S  ("stage lanes"):     x[e] <-> row = (lane>>2)*16 + e,      col = lane&3, idx = (lane>>2)*64 + e*4 + (lane&3)
-// forward: stages 0-3 in layout R (row bits 6..3), stages 4-6 in layout S (row bits 2..0)
-// inverse: row gaps 1,2,4 in layout S, row gaps 8..64 in layout R (last one carries N^-1)
-// `tw` points at the staged table (entries 0..127 of the prime's table).
+// Pass A (strided): tile = ROWS rows x C cols (512 values), tile index = row*C + col.
+//   layout R  ("row-major lanes"): x[e] <-> row = e*(ROWS/16) + (lane>>LOGC), col = lane&(C-1), idx = e*32 + lane
+//   layout S  ("stage lanes"):     x[e] <-> row = (lane>>LOGC)*16 + e,        col = lane&(C-1)
+// forward: stages 0-3 in layout R (top four row bits), stages 4..LOGA-1 in layout S (low row bits)
+// inverse: row gaps 1..2^(LOGA-5) in layout S, the four largest gaps in layout R (last one carries N^-1)
+// `tw` points at the staged table (entries 0..ROWS-1 of the prime's table).
 // =====================================================================================
-HD int rowR(int lane, int e) { return e * 8 + (lane >> 2); }
-HD int rowS(int lane, int e) { return (lane >> 2) * 16 + e; }
+template <int LOGA> HD int rowR(int lane, int e) { return e * (Geo<LOGA>::ROWS / 16) + (lane >> Geo<LOGA>::LOGC); }
+template <int LOGA> HD int rowS(int lane, int e) { return (lane >> Geo<LOGA>::LOGC) * 16 + e; }
+template <int LOGA> HD int colA(int lane) { return lane & (Geo<LOGA>::C - 1); }
 HD int idxR(int lane, int e) { return e * 32 + lane; }
-HD int idxS(int lane, int e) { return (lane >> 2) * 64 + e * 4 + (lane & 3); }
+template <int LOGA> HD int idxS(int lane, int e) { return rowS<LOGA>(lane, e) * Geo<LOGA>::C + colA<LOGA>(lane); }
 
 // in: < 2q   out: < 10q
 HD void fwdA_stages_R(u64 (&x)[16], const Tw *tw, u64 q, u64 q2) {
@@ -157,43 +169,43 @@ HD void fwdA_stages_R(u64 (&x)[16], const Tw *tw, u64 q, u64 q2) {
       if (!(e & half)) ct_bfly_lazy(x[e], x[e + half], t[e >> (4 - s)], q, q2);
   }
 }
-// in: < 2q   out: < 8q
-HD void fwdA_stages_S(u64 (&x)[16], int lane, const Tw *tw, u64 q, u64 q2) {
-  const int rbase = (lane >> 2) * 16;
+// stages 4..LOGA-1; every stage adds 2q to the bound
+template <int LOGA> HD void fwdA_stages_S(u64 (&x)[16], int lane, const Tw *tw, u64 q, u64 q2) {
+  const int rbase = (lane >> Geo<LOGA>::LOGC) * 16;
   _Pragma("unroll")
-  for (int s = 4; s < 7; s++) {
-    const int half = 1 << (6 - s);
+  for (int s = 4; s < LOGA; s++) {
+    const int half = 1 << (LOGA - 1 - s);
     _Pragma("unroll")
     for (int e = 0; e < 16; e++)
       if (!(e & half)) {
-        Tw t = ldtw(tw + (1 << s) + ((rbase + e) >> (7 - s)));
+        Tw t = ldtw(tw + (1 << s) + ((rbase + e) >> (LOGA - s)));
         ct_bfly_lazy(x[e], x[e + half], t, q, q2);
       }
   }
 }
-// inverse, layout S: row gaps 1,2,4  (m = 64,32,16 groups); in/out < 2q
-HD void invA_stages_S(u64 (&x)[16], int lane, const Tw *itw, u64 q, u64 q2, u64 dl) {
-  const int rbase = (lane >> 2) * 16;
+// inverse, layout S: row gaps 2^j, j < LOGA-4  (m = ROWS/2 >> j groups); in/out < 2q
+template <int LOGA> HD void invA_stages_S(u64 (&x)[16], int lane, const Tw *itw, u64 q, u64 q2, u64 dl) {
+  const int rbase = (lane >> Geo<LOGA>::LOGC) * 16;
   _Pragma("unroll")
-  for (int j = 0; j < 3; j++) {
+  for (int j = 0; j < LOGA - 4; j++) {
     const int half = 1 << j;
     _Pragma("unroll")
     for (int e = 0; e < 16; e++)
       if (!(e & half)) {
-        Tw t = ldtw(itw + (64 >> j) + ((rbase + e) >> (j + 1)));
+        Tw t = ldtw(itw + ((Geo<LOGA>::ROWS / 2) >> j) + ((rbase + e) >> (j + 1)));
         gs_bfly_fold(x[e], x[e + half], t, q, q2, dl);
       }
   }
 }
-// inverse, layout R: row gaps 8,16,32,64 (m = 8,4,2,1); the last stage applies N^-1; output canonical
+// inverse, layout R: the four largest row gaps (m = 8,4,2,1 groups); the last stage applies N^-1; output canonical
 HD void invA_stages_R(u64 (&x)[16], const Tw *itw, u64 q, u64 q2, u64 dl, Tw invn, Tw invn_w) {
   _Pragma("unroll")
-  for (int j = 3; j < 6; j++) {
-    const int half = 1 << (j - 3);
+  for (int jj = 0; jj < 3; jj++) {
+    const int half = 1 << jj;
     _Pragma("unroll")
     for (int e = 0; e < 16; e++)
       if (!(e & half)) {
-        const Tw t = ldtw(itw + (64 >> j) + (e >> (j - 2))); // warp-uniform address: broadcast LDS.128
+        const Tw t = ldtw(itw + (8 >> jj) + (e >> (jj + 1))); // warp-uniform address: broadcast LDS.128
         gs_bfly_fold(x[e], x[e + half], t, q, q2, dl);
       }
   }
@@ -311,10 +323,10 @@ struct LaneB8 {
 // =====================================================================================
 
 // forward pass A on values already held in layout R by st[].y; result (lazy, < 16q) -> dst tile
-// (128 rows x 4 cols at column c0 of the limb `dst`, row pitch = 2^LOGB)
+// (ROWS x C tile at column c0 of the limb `dst`, row pitch = 256)
 // Range: every stage adds at most 2q to the bound, so inputs < 2q leave the 7 stages < 16q < 2^64
 // without any correction (FOLD = false); inputs up to 4q need one fold between the rounds (FOLD = true).
-template <int LOGB, bool FOLD>
+template <int LOGA, bool FOLD>
 HD void warp_fwdA_from_regs(LaneA *st, u64 *sm, u64 *dst, int c0, const Tw *tw, const ModQ &m) {
   const u64 q = m.q, q2 = 2 * m.q, dl = m.delta;
   LANE_DECL;
@@ -325,24 +337,24 @@ HD void warp_fwdA_from_regs(LaneA *st, u64 *sm, u64 *dst, int c0, const Tw *tw, 
   });
   FOR_LANES(S, st, {
     _Pragma("unroll")
-    for (int e = 0; e < 16; e++) S.y[e] = sm[padx(idxS(lane, e))];
-    fwdA_stages_S(S.y, lane, tw, q, q2);
+    for (int e = 0; e < 16; e++) S.y[e] = sm[padx(idxS<LOGA>(lane, e))];
+    fwdA_stages_S<LOGA>(S.y, lane, tw, q, q2);
     _Pragma("unroll")
-    for (int e = 0; e < 16; e++) dst[((size_t)rowS(lane, e) << LOGB) + c0 + (lane & 3)] = S.y[e];
+    for (int e = 0; e < 16; e++) dst[((size_t)rowS<LOGA>(lane, e) << 8) + c0 + colA<LOGA>(lane)] = S.y[e];
   });
 }
 
 // inverse pass A: src tile (layout S load, values < 2q) -> canonical coefficients in st[].x, layout R
-template <int LOGB>
+template <int LOGA>
 HD void warp_invA_to_regs(LaneA *st, u64 *sm, const u64 *src, int c0, const Tw *itw, const ModQ &m, Tw invn, Tw invn_w) {
   const u64 q = m.q, q2 = 2 * m.q, dl = m.delta;
   LANE_DECL;
   FOR_LANES(S, st, {
     _Pragma("unroll")
-    for (int e = 0; e < 16; e++) S.x[e] = ldg_stream(src + ((size_t)rowS(lane, e) << LOGB) + c0 + (lane & 3));
-    invA_stages_S(S.x, lane, itw, q, q2, dl);
+    for (int e = 0; e < 16; e++) S.x[e] = ldg_stream(src + ((size_t)rowS<LOGA>(lane, e) << 8) + c0 + colA<LOGA>(lane));
+    invA_stages_S<LOGA>(S.x, lane, itw, q, q2, dl);
     _Pragma("unroll")
-    for (int e = 0; e < 16; e++) sm[padx(idxS(lane, e))] = S.x[e];
+    for (int e = 0; e < 16; e++) sm[padx(idxS<LOGA>(lane, e))] = S.x[e];
   });
   FOR_LANES(S, st, {
     _Pragma("unroll")

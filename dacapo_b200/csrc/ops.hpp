@@ -27,42 +27,52 @@ struct Scratch {      // device (or emulator-host) buffers, sized for the top le
   }
 };
 
-template <class LA> struct HeOps {
+// ring-size independent interface (the VM holds one of these per lane)
+struct OpsIface {
+  Scratch sc;
+  virtual ~OpsIface() {}
+  virtual void ntt_fwd(const u64 *src, u64 *dst, int nl, int prime0, int pstep) = 0;
+  virtual void ntt_inv(const u64 *src, u64 *dst, int nl, int prime0, int pstep, int round = 0) = 0;
+  virtual void keyswitch(int mode, const u64 *a, const u64 *b, u64 *dst, size_t pitch, int l, const u64 *key, u32 elt) = 0;
+  virtual void rescale(const u64 *src, size_t src_pitch, u64 *dst, size_t dst_pitch, int l) = 0;
+};
+
+template <class LA, int LOGA> struct HeOps : OpsIface {
+  static constexpr int ROWS = Geo<LOGA>::ROWS, TILES_A = Geo<LOGA>::TILES;
   LA &la;
   const NttTables *T; // device-visible tables
   int logN, L;
   size_t N;
-  Scratch sc;
-  HeOps(LA &l, const NttTables *tab, int logn, int nprimes) : la(l), T(tab), logN(logn), L(nprimes), N((size_t)1 << logn) {}
+  HeOps(LA &l, const NttTables *tab, int nprimes) : la(l), T(tab), logN(LOGA + 8), L(nprimes), N((size_t)1 << (LOGA + 8)) {}
   int sp() const { return L - 1; }
 
   // forward NTT of nl limbs (limb k under prime prime0 + k*pstep); src may equal dst; canonical output
-  void ntt_fwd(const u64 *src, u64 *dst, int nl, int prime0, int pstep) {
+  void ntt_fwd(const u64 *src, u64 *dst, int nl, int prime0, int pstep) override {
     for (int done = 0; done < nl;) { // staged through s2 in chunks
       int chunk = nl - done;
       int cap = L * (L - 1);
       if (chunk > cap) chunk = cap;
       ArgsFwdA a{};
       a.T = T, a.src = src + (size_t)done * N, a.dst = sc.s2, a.nd = chunk, a.prime0 = prime0 + done * pstep, a.pstep = pstep;
-      la.template fwd_A<PRE_NONE>(a, chunk * TILES_A);
+      la.template fwd_A<LOGA, PRE_NONE>(a, chunk * TILES_A);
       ArgsFwdB b{};
       b.T = T, b.src = sc.s2, b.dst = dst + (size_t)done * N, b.nd = chunk, b.prime0 = a.prime0, b.pstep = pstep;
-      la.template fwd_B<EPI_CANON>(b, chunk * ROWS);
+      la.template fwd_B<LOGA, EPI_CANON>(b, chunk * ROWS);
       done += chunk;
     }
   }
   // inverse NTT (canonical coefficients).  round=1 adds floor(q/2) mod q.
-  void ntt_inv(const u64 *src, u64 *dst, int nl, int prime0, int pstep, int round = 0) {
+  void ntt_inv(const u64 *src, u64 *dst, int nl, int prime0, int pstep, int round = 0) override {
     for (int done = 0; done < nl;) {
       int chunk = nl - done;
       int cap = L * (L - 1);
       if (chunk > cap) chunk = cap;
       ArgsInttB a{};
       a.T = T, a.src = src + (size_t)done * N, a.dst = sc.s2, a.nl = chunk, a.prime0 = prime0 + done * pstep, a.pstep = pstep;
-      la.template intt_B<LD_PLAIN>(a, chunk * ROWS);
+      la.template intt_B<LOGA, LD_PLAIN>(a, chunk * ROWS);
       ArgsInttA b{};
       b.T = T, b.src = sc.s2, b.dst = dst + (size_t)done * N, b.nl = chunk, b.prime0 = a.prime0, b.pstep = pstep, b.round = round;
-      la.intt_A(b, chunk * TILES_A);
+      la.template intt_A<LOGA>(b, chunk * TILES_A);
       done += chunk;
     }
   }
@@ -85,24 +95,24 @@ template <class LA> struct HeOps {
   // mode LD_PRODUCT: dst = (a0 b0, a0 b1 + a1 b0) + KS(a1 b1)           (multiply + relinearize)
   // `pitch` = words between the two polys of every ciphertext operand.  dst may alias a or b.
   // Five launches: B' | A'+mod-up+A | B+MAC(+B' of the special limb) | A'+round+A | B+mod-down epilogue
-  void keyswitch(int mode, const u64 *a, const u64 *b, u64 *dst, size_t pitch, int l, const u64 *key, u32 elt) {
+  void keyswitch(int mode, const u64 *a, const u64 *b, u64 *dst, size_t pitch, int l, const u64 *key, u32 elt) override {
     // 1. inverse pass B of the target, fused with the Galois gather / the tensor product d2
     {
       ArgsInttB x{};
       x.T = T, x.dst = sc.s1, x.nl = l, x.prime0 = 0, x.pstep = 1, x.elt = elt;
       if (mode == LD_GALOIS) {
         x.src = a + pitch, x.c0 = a, x.pc0 = sc.pc0;
-        la.template intt_B<LD_GALOIS>(x, l * ROWS);
+        la.template intt_B<LOGA, LD_GALOIS>(x, l * ROWS);
       } else {
         x.src = a + pitch, x.src2 = b + pitch;
-        la.template intt_B<LD_PRODUCT>(x, l * ROWS);
+        la.template intt_B<LOGA, LD_PRODUCT>(x, l * ROWS);
       }
     }
     // 2. inverse pass A -> coefficient digits t_J (registers only) -> (t_J mod q_I) -> forward pass A
     {
       ArgsInvFwdA x{};
       x.T = T, x.src = sc.s1, x.dst = sc.s2, x.nsrc = l, x.l = l, x.sp = sp(), x.ngroups = pick_groups(l, l + 1);
-      la.template invA_fwdA<PRE_MODUP>(x, l * x.ngroups * TILES_A);
+      la.template invA_fwdA<LOGA, PRE_MODUP>(x, l * x.ngroups * TILES_A);
     }
     // 3. forward pass B + inner product with the key over all digits; the special-prime CTAs also run the
     //    inverse pass B of their accumulator rows (first step of the mod-down) into s1[0..1]
@@ -111,13 +121,13 @@ template <class LA> struct HeOps {
       x.T = T, x.src = sc.s2, x.dst = sc.acc, x.l = l, x.sp = sp(), x.key = key, x.Ltot = L, x.ld = mode, x.elt = elt;
       x.tgt = a + pitch, x.tgt2 = (mode == LD_PRODUCT) ? b + pitch : nullptr;
       x.sp_rows = sc.s1;
-      la.mac(x, (l + 1) * ROWS);
+      la.template mac<LOGA>(x, (l + 1) * ROWS);
     }
     // 4. mod-down: inverse pass A of the special limb + rounding + per-target fix-up + forward pass A
     {
       ArgsInvFwdA x{};
       x.T = T, x.src = sc.s1, x.dst = sc.s4, x.nsrc = 2, x.l = l, x.plast = sp(), x.ngroups = pick_groups(2, l);
-      la.template invA_fwdA<PRE_ROUND>(x, 2 * x.ngroups * TILES_A);
+      la.template invA_fwdA<LOGA, PRE_ROUND>(x, 2 * x.ngroups * TILES_A);
     }
     // 5. forward pass B + (acc - u) * p^-1 + addend
     {
@@ -125,26 +135,26 @@ template <class LA> struct HeOps {
       w.T = T, w.src = sc.s4, w.dst = dst, w.l = l, w.sp = sp(), w.acc = sc.acc, w.pitch = pitch, w.plast = sp();
       if (mode == LD_GALOIS) {
         w.add0 = sc.pc0;
-        la.template fwd_B<EPI_MODDOWN_GALOIS>(w, 2 * l * ROWS);
+        la.template fwd_B<LOGA, EPI_MODDOWN_GALOIS>(w, 2 * l * ROWS);
       } else {
         w.add0 = a, w.add1 = b;
-        la.template fwd_B<EPI_MODDOWN_RELIN>(w, l * ROWS);
+        la.template fwd_B<LOGA, EPI_MODDOWN_RELIN>(w, l * ROWS);
       }
     }
   }
 
   // ---- rescale: 2 polys with l limbs -> l-1 limbs (divide by q_{l-1} and round); three launches -------
   // src/dst poly pitches may differ (encrypt uses a compact (l)-limb temporary).
-  void rescale(const u64 *src, size_t src_pitch, u64 *dst, size_t dst_pitch, int l) {
+  void rescale(const u64 *src, size_t src_pitch, u64 *dst, size_t dst_pitch, int l) override {
     {
       ArgsInttB x{};
       x.T = T, x.src = src + (size_t)(l - 1) * N, x.sstride = src_pitch, x.dst = sc.s1, x.nl = 2, x.prime0 = l - 1, x.pstep = 0;
-      la.template intt_B<LD_PLAIN>(x, 2 * ROWS);
+      la.template intt_B<LOGA, LD_PLAIN>(x, 2 * ROWS);
     }
     {
       ArgsInvFwdA x{};
       x.T = T, x.src = sc.s1, x.dst = sc.s4, x.nsrc = 2, x.l = l - 1, x.plast = l - 1, x.ngroups = pick_groups(2, l - 1);
-      la.template invA_fwdA<PRE_ROUND>(x, 2 * x.ngroups * TILES_A);
+      la.template invA_fwdA<LOGA, PRE_ROUND>(x, 2 * x.ngroups * TILES_A);
     }
     if (src_pitch != dst_pitch) {
       // epilogue addresses input and output with one pitch: run per poly
@@ -152,12 +162,22 @@ template <class LA> struct HeOps {
         ArgsFwdB w{};
         w.T = T, w.src = sc.s4 + (size_t)K * (l - 1) * N, w.dst = dst + (size_t)K * dst_pitch, w.l = l - 1, w.add0 = src + (size_t)K * src_pitch;
         w.pitch = 0, w.plast = l - 1;
-        la.template fwd_B<EPI_RESCALE>(w, (l - 1) * ROWS);
+        la.template fwd_B<LOGA, EPI_RESCALE>(w, (l - 1) * ROWS);
       }
     } else {
       ArgsFwdB w{};
       w.T = T, w.src = sc.s4, w.dst = dst, w.l = l - 1, w.add0 = src, w.pitch = dst_pitch, w.plast = l - 1;
-      la.template fwd_B<EPI_RESCALE>(w, 2 * (l - 1) * ROWS);
+      la.template fwd_B<LOGA, EPI_RESCALE>(w, 2 * (l - 1) * ROWS);
     }
   }
 };
+
+// ring-size dispatch: N = 2^(LOGA+8)
+template <class LA> OpsIface *make_ops(LA &la, const NttTables *tab, int logN, int nprimes) {
+  switch (logN) {
+  case 14: return new HeOps<LA, 6>(la, tab, nprimes);
+  case 15: return new HeOps<LA, 7>(la, tab, nprimes);
+  case 16: return new HeOps<LA, 8>(la, tab, nprimes);
+  }
+  return nullptr;
+}

@@ -82,7 +82,7 @@ struct DecTabs {
 struct Lane {
   cudaStream_t stream = nullptr;
   GpuLauncher la;
-  HeOps<GpuLauncher> *ops = nullptr;
+  OpsIface *ops = nullptr;
   double2 *d_work = nullptr;
   unsigned long long *d_maxbits = nullptr;
   double *d_vals = nullptr, *d_vals_in = nullptr;
@@ -130,7 +130,7 @@ struct VM {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) die("no CUDA device visible: libB200_HEVM.so has no CPU path");
     if (const char *e = std::getenv("HEVM_DEVICE")) CUDA_CHECK(cudaSetDevice(std::atoi(e)));
-    if (pf.logN != 15) die("this build supports N = 2^15 only (HEVM_LOGN=15); other ring sizes are planned (DESIGN.md)");
+    if (pf.logN < 14 || pf.logN > 16) die("supported ring sizes: N = 2^14, 2^15, 2^16 (HEVM_LOGN = 14..16)");
     if (pf.L < 2 || pf.L > HEVM_MAXL) die("number of primes out of range");
     logN = (int)pf.logN, L = (int)pf.L, N = (size_t)1 << logN, seed = pf.seed;
     pitch = (size_t)(L - 1) * N;
@@ -149,7 +149,7 @@ struct VM {
     for (Lane &l : lanes) {
       CUDA_CHECK(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
       l.la.stream = l.stream;
-      l.ops = new HeOps<GpuLauncher>(l.la, dT, logN, L);
+      l.ops = make_ops(l.la, dT, logN, L);
       l.ops->sc.carve(dalloc<u64>(Scratch::words(L, N)), L, N);
       l.d_work = dalloc<double2>(N);
       l.d_maxbits = dalloc<unsigned long long>(1);

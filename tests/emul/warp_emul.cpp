@@ -11,56 +11,56 @@
 #include <cstring>
 
 struct EmuLauncher {
-  template <int LD> void intt_B(const ArgsInttB &a, int njobs) {
+  template <int LOGA, int LD> void intt_B(const ArgsInttB &a, int njobs) {
     for (int j = 0; j < njobs; j++) {
       LaneB8 st[32];
-      alignas(16) u64 sm[WARP_SMEM_WORDS];
-      body_intt_B<LD>(a, j, st, sm);
+      alignas(16) u64 sm[Geo<LOGA>::WARP_WORDS];
+      body_intt_B<LOGA, LD>(a, j, st, sm);
     }
   }
-  void intt_A(const ArgsInttA &a, int njobs) {
+  template <int LOGA> void intt_A(const ArgsInttA &a, int njobs) {
     for (int j = 0; j < njobs; j++) {
       LaneA st[32];
-      alignas(16) u64 sm[WARP_SMEM_WORDS];
-      body_intt_A(a, j, st, sm);
+      alignas(16) u64 sm[Geo<LOGA>::WARP_WORDS];
+      body_intt_A<LOGA>(a, j, st, sm);
     }
   }
-  template <int PRE> void fwd_A(const ArgsFwdA &a, int njobs) {
+  template <int LOGA, int PRE> void fwd_A(const ArgsFwdA &a, int njobs) {
     for (int j = 0; j < njobs; j++) {
       LaneA st[32];
-      alignas(16) u64 sm[WARP_SMEM_WORDS];
-      body_fwd_A<PRE>(a, j, st, sm);
+      alignas(16) u64 sm[Geo<LOGA>::WARP_WORDS];
+      body_fwd_A<LOGA, PRE>(a, j, st, sm);
     }
   }
-  template <int EPI> void fwd_B(const ArgsFwdB &a, int njobs) {
+  template <int LOGA, int EPI> void fwd_B(const ArgsFwdB &a, int njobs) {
     for (int j = 0; j < njobs; j++) {
       LaneB8 st[32];
-      alignas(16) u64 sm[WARP_SMEM_WORDS];
-      body_fwd_B<EPI>(a, j, st, sm);
+      alignas(16) u64 sm[Geo<LOGA>::WARP_WORDS];
+      body_fwd_B<LOGA, EPI>(a, j, st, sm);
     }
   }
-  template <int PRE> void invA_fwdA(const ArgsInvFwdA &a, int njobs) {
+  template <int LOGA, int PRE> void invA_fwdA(const ArgsInvFwdA &a, int njobs) {
     for (int j = 0; j < njobs; j++) {
       LaneA st[32];
-      alignas(16) u64 sm[WARP_SMEM_WORDS];
-      body_invA_fwdA<PRE>(a, j, st, sm);
+      alignas(16) u64 sm[Geo<LOGA>::WARP_WORDS];
+      body_invA_fwdA<LOGA, PRE>(a, j, st, sm);
     }
   }
-  void mac(const ArgsFwdB &a, int njobs) { // one CTA of MAC_WARPS warps per job; CTA barriers = phase boundaries
+  template <int LOGA> void mac(const ArgsFwdB &a, int njobs) { // one CTA of MAC_WARPS warps per job; CTA barriers = phase boundaries
     for (int j = 0; j < njobs; j++) {
       alignas(16) u64 sm[MAC_SMEM_WORDS];
       Tw *tw_s = reinterpret_cast<Tw *>(sm);
       u64 *tiles = sm + MAC_TW_WORDS, *parts = tiles + MAC_WARPS * TILE_B_WORDS;
-      for (int tid = 0; tid < MAC_WARPS * 32; tid++) body_mac_stage(a, j, tid, tw_s);
+      for (int tid = 0; tid < MAC_WARPS * 32; tid++) body_mac_stage<LOGA>(a, j, tid, tw_s);
       for (int w = 0; w < MAC_WARPS; w++) {
         LaneB8 st[32];
-        body_mac_warp(a, j, w, st, tiles + w * TILE_B_WORDS, tw_s, parts + w * MAC_PART_WORDS);
+        body_mac_warp<LOGA>(a, j, w, st, tiles + w * TILE_B_WORDS, tw_s, parts + w * MAC_PART_WORDS);
       }
-      for (int tid = 0; tid < MAC_WARPS * 32; tid++) body_mac_reduce(a, j, tid, parts, tiles);
-      if (mac_Iidx(a, j) == a.l)
+      for (int tid = 0; tid < MAC_WARPS * 32; tid++) body_mac_reduce<LOGA>(a, j, tid, parts, tiles);
+      if (mac_Iidx<LOGA>(a, j) == a.l)
         for (int K = 0; K < 2; K++) {
           LaneB8 st[32];
-          body_mac_tail(a, j, K, st, parts + K * MAC_PART_WORDS, tw_s, tiles);
+          body_mac_tail<LOGA>(a, j, K, st, parts + K * MAC_PART_WORDS, tw_s, tiles);
         }
     }
   }
@@ -69,7 +69,7 @@ struct EmuLauncher {
 struct Emu {
   hp::HostParams P;
   EmuLauncher la;
-  HeOps<EmuLauncher> *ops;
+  OpsIface *ops;
   std::vector<u64> scratch;
 };
 
@@ -79,7 +79,8 @@ void *emul_create(int logN, int L, int bits) {
   e->P.build(logN, L, bits);
   e->P.tab.tw = e->P.tw.data();
   e->P.tab.itw = e->P.itw.data();
-  e->ops = new HeOps<EmuLauncher>(e->la, &e->P.tab, logN, L);
+  e->ops = make_ops(e->la, &e->P.tab, logN, L);
+  if (!e->ops) return nullptr;
   e->scratch.resize(Scratch::words(L, e->P.N));
   e->ops->sc.carve(e->scratch.data(), L, e->P.N);
   return e;

@@ -339,3 +339,32 @@ def test_scheduler_random_program_bit_exact(pair, tmp_path, seed):
         assert np.array_equal(c, b)
     for vm in pair:
         vm.lib.hevmx_resize(vm.vm, 8, 4)
+
+
+@pytest.mark.parametrize("logn,npr", [(14, 5), (16, 6)])
+def test_other_ring_sizes_bit_exact(oracle_lib, b200_lib, tmp_path_factory, logn, npr):
+    """N is a run-time parameter: same kernels with 64 / 256 rows x 256 columns."""
+    d = str(tmp_path_factory.mktemp(f"keys{logn}"))
+    g = VM(b200_lib, logn, npr, keydir=d, nct=6, npt=2)
+    o = VM(oracle_lib, logn, npr, keydir=d, nct=6, npt=2)
+    assert g.primes == o.primes and g.roots == o.roots
+    assert np.array_equal(g.key(2), o.key(2))
+    lvl = npr - 1
+    f = np.random.default_rng(1).integers(0, o.primes[1], size=(2, o.N), dtype=np.uint64)
+    assert np.array_equal(g.ntt(f, 1), o.ntt(f, 1))
+    a, b = o.random_ct(lvl, 1), o.random_ct(lvl, 2)
+    x = np.random.default_rng(3).uniform(-1, 1, o.N // 2)
+    for vm in (g, o):
+        vm.ct_write(0, a)
+        vm.ct_write(1, b)
+        vm.exec(asm.MULCC, 2, 0, 1)
+        vm.exec(asm.ROTATE, 3, 2, 5)
+        vm.exec(asm.ROTATE, 3, 3, -(o.N // 4 + 3))
+        vm.exec(asm.RESCALE, 4, 3)
+        vm.encode(0, x, lvl, 40)
+        vm.encrypt_pt(0, 5, counter=3)
+        vm.exec(asm.BOOTSTRAP, 5, 5, lvl)
+    for r in (2, 3, 4, 5):
+        assert np.array_equal(g.ct_read(r), o.ct_read(r)), r
+    assert np.array_equal(g.decrypt_decode(5, 1), o.decrypt_decode(5, 1))
+    assert np.max(np.abs(g.decrypt_decode(5, 1) - x)) < 1e-5

@@ -1,6 +1,6 @@
 """CPU tier: the CUDA warp-job bodies, replayed lane-by-lane by the test-only warp emulator
-(tests/emul/warp_emul.cpp), must reproduce the oracle bit-for-bit at the real ring size
-N = 2^15.  This checks the kernels' index maths / fusion logic without a GPU; the `-m gpu`
+(tests/emul/warp_emul.cpp), must reproduce the oracle bit-for-bit at the real ring sizes
+N = 2^14, 2^15 and 2^16.  This checks the kernels' index maths / fusion logic without a GPU; the `-m gpu`
 tests then check the same kernels on the device through the C ABI.
 """
 import ctypes as C
@@ -15,11 +15,16 @@ from util import VM
 
 HERE = Path(__file__).resolve().parent
 u64p = C.POINTER(C.c_uint64)
-LOGN, NPR = 15, 4
+NPR = 4
+
+
+@pytest.fixture(scope="module", params=[15, 14, 16])
+def LOGN(request):
+    return request.param
 
 
 @pytest.fixture(scope="module")
-def emul():
+def emul(LOGN):
     so = HERE / "emul" / "libwarp_emul.so"
     subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", str(so), str(HERE / "emul" / "warp_emul.cpp")], check=True)
     lib = C.CDLL(str(so))
@@ -33,7 +38,7 @@ def emul():
 
 
 @pytest.fixture(scope="module")
-def vm(oracle_lib):
+def vm(oracle_lib, LOGN):
     return VM(oracle_lib, LOGN, NPR, nct=4, npt=1)
 
 
