@@ -1,0 +1,31 @@
+"""GPU tier: the reference-facing Python driver (`dacapo_b200.runner.HEVM`, mirror of
+python/hecate/hecate/runner.py:174-271) end to end, in the style of the reference's examples/tests."""
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+REPO = Path(__file__).resolve().parent.parent
+pytestmark = pytest.mark.gpu
+
+
+def test_example_script_runs_and_is_accurate(tmp_path):
+    env = {**__import__("os").environ, "HOME": str(tmp_path)}  # keys go to $HOME/.hevm/b200
+    r = subprocess.run([sys.executable, str(REPO / "examples" / "poly_regression.py"), "dacapo", "40", "B200", "GPU"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "library: B200" in r.stdout and "device: GPU" in r.stdout and "benchname: poly" in r.stdout
+    rms = float([l for l in r.stdout.splitlines() if l.startswith("rms:")][0].split()[1])
+    assert rms < 1e-3, rms  # the reference reports ~1e-3 on ResNet (README.md:187)
+
+
+def test_setlibnhw_argument_forms():
+    sys.path.insert(0, str(REPO))
+    from dacapo_b200 import runner
+    for argv in (["x", "dacapo", "40", "B200", "GPU"], ["x", "dacapo", "40", "GPU", "B200"], ["x", "dacapo", "40", "B200"], ["x"]):
+        runner.setLibnHW(argv)
+        assert (runner.run_library, runner.run_hardware) == ("B200", "GPU")
+    with pytest.raises(SystemExit):
+        runner.setLibnHW(["x", "dacapo", "40", "SEAL", "CPU"])  # not provided by this backend
