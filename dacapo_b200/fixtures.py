@@ -1,0 +1,31 @@
+"""Access to the committed ResNet-20 fixture (tests/golden/resnet20, made by tests/golden/make_resnet_fixture.py)."""
+import json
+import lzma
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+FIXTURE = Path(__file__).resolve().parent.parent / "tests" / "golden" / "resnet20"
+
+
+def resnet20_files(tmpdir=None):
+    """Decompress the constants next to a copy of the program; returns (cst_path, hevm_path, input, expected, meta).
+
+    The directory layout mimics the reference's `optimized/<compiler>/<bench>.<waterline>._hecate_<bench>.hevm`
+    so that HEVM.printer (runner.py:256-271) can parse it."""
+    tmp = Path(tmpdir or tempfile.mkdtemp(prefix="resnet20_"))
+    cst = tmp / "traced" / "_hecate_ResNet.cst"
+    hv = tmp / "optimized" / "b200c" / "ResNet.40._hecate_ResNet.hevm"
+    cst.parent.mkdir(parents=True, exist_ok=True)
+    hv.parent.mkdir(parents=True, exist_ok=True)
+    if not cst.is_file():
+        with lzma.open(FIXTURE / "resnet20.cst.xz") as f, open(cst, "wb") as o:
+            while True:
+                b = f.read(1 << 24)
+                if not b:
+                    break
+                o.write(b)
+    hv.write_bytes((FIXTURE / "resnet20.hevm").read_bytes())
+    meta = json.loads((FIXTURE / "meta.json").read_text())
+    return str(cst), str(hv), np.load(FIXTURE / "input.npy"), np.load(FIXTURE / "expected.npy"), meta

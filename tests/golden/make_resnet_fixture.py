@@ -1,0 +1,77 @@
+"""Generates tests/golden/resnet20/* : the REAL encrypted ResNet-20 workload of BASELINE.json configs[0].
+
+Runs ONLY in the build container (it imports the reference's Python from /root/reference, which does not
+exist on the GPU box): the reference benchmark script examples/benchmarks/ResNet.py is executed unmodified
+(except for the documented `nt = 2**14` edit, README.md:170-171) against `dacapo_b200.frontend` registered
+as the `hecate` module, which records the op graph the reference would hand to libHecateFrontend.so.
+The graph is compiled with dacapo_b200.compiler (waterline 40, N = 2^15, 14 primes) and stored with
+ - resnet20.hevm           the program (reference container format)
+ - resnet20.cst.xz         the 4 000+ plaintext constants (525 MB raw, ~4 MB compressed: <= 17 distinct values per row)
+ - input.npy               the packed, seeded synthetic input (CIFAR-10 cannot be downloaded offline)
+ - expected.npy            the plaintext torch model's logits for that input (the reference test's `process`)
+ - meta.json               post-processing (x32, first 10 slots: examples/tests/ResNet.py:76-82) and statistics
+
+    python tests/golden/make_resnet_fixture.py
+"""
+import json
+import lzma
+import os
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+REPO = HERE.parent.parent
+REF = Path("/root/reference")
+sys.path.insert(0, str(REPO))
+sys.path.insert(0, str(REF / "python" / "poly"))
+
+from dacapo_b200 import compiler, frontend  # noqa: E402
+
+sys.modules["hecate"] = frontend  # the reference scripts do `import hecate as hc`
+
+
+def main():
+    import torch
+    out = HERE / "resnet20"
+    out.mkdir(exist_ok=True)
+    bench = REF / "examples" / "benchmarks" / "ResNet.py"
+    src = bench.read_text().replace('"nt" : 2**16,', '"nt" : 2**14,')
+    g = {"__name__": "__main__", "__file__": str(bench)}
+    t0 = time.time()
+    frontend.reset()
+    exec(compile(src, str(bench), "exec"), g)
+    graph = g["modName"]  # frontend.save() returns the recorded Graph
+    print(f"traced {len(graph.nodes)} nodes, {len(graph.consts)} constants in {time.time() - t0:.1f}s")
+
+    prog, c = compiler.compile_graph(graph, compiler.Options(logN=15, num_primes=14, waterline=40))
+    print("lowered ops:", c.stats, "ct regs", prog.num_ct, "pt regs", prog.num_pt, "pool", len(prog.constants))
+    (out / "resnet20.hevm").write_bytes(prog.hevm_bytes())
+    raw = prog.cst_bytes()
+    (out / "resnet20.cst.xz").write_bytes(lzma.compress(raw, preset=6))
+    print("cst raw MB", len(raw) / 1e6, "xz MB", (out / "resnet20.cst.xz").stat().st_size / 1e6)
+
+    # seeded synthetic input, plaintext reference and packing -- with the reference's own code
+    model = g["getModel"]()
+    torch.manual_seed(1)
+    x = torch.randn(1, 3, 32, 32).clamp(-2.0, 2.0)
+    with torch.no_grad():
+        logits = model(x).cpu().numpy()[0].astype(np.float64)
+    shapes = {"nt": 2 ** 14, "bb": 32, "ko": 1, "ho": 32, "wo": 32}
+    conv1_shapes = g["CascadeConv"](shapes, model.module.conv1)
+    close = g["shapeClosure"](**conv1_shapes)
+    packed = np.asarray(close["MPP"](x)[0], dtype=np.float64).ravel()
+    np.save(out / "input.npy", packed)
+    np.save(out / "expected.npy", logits)
+    meta = {"post_scale": 32.0, "n_out": 10, "lowered_ops": c.stats, "traced_nodes": len(graph.nodes),
+            "ct_registers": prog.num_ct, "pt_registers": prog.num_pt, "hevm_ops": len(prog.ops),
+            "source": "examples/benchmarks/ResNet.py (nt=2^14) traced with dacapo_b200.frontend, compiled with dacapo_b200.compiler",
+            "weights": "examples/data/resnet20.silu.model", "input": "torch.manual_seed(1); randn(1,3,32,32).clamp(-2,2)"}
+    (out / "meta.json").write_text(json.dumps(meta, indent=1))
+    print("logits", logits)
+
+
+if __name__ == "__main__":
+    main()

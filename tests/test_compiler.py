@@ -1,0 +1,100 @@
+"""CPU tier: tracing front end + compiler (dacapo_b200.frontend / compiler) -> HEVM program -> oracle.
+
+The compiled program must decrypt to what plain numpy computes; this exercises scale management
+(lazy rescale, upscale, modswitch alignment), automatic bootstrap insertion, constant folding and
+register reuse, on a small ring so that the CPU oracle runs it in seconds."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from dacapo_b200 import compiler, frontend as hc
+from dacapo_b200 import hevm_asm as asm
+from util import make_vm
+
+LOGN, NPR = 11, 8  # 1024 slots, 7 data levels
+f64p = C.POINTER(C.c_double)
+
+
+def run_on(lib, prog, inputs, tmp_path):
+    vm, _ = make_vm(lib, LOGN, NPR)
+    cst, hv = tmp_path / "c.cst", tmp_path / "c.hevm"
+    prog.save(cst, hv)
+    lib.load(vm, str(cst).encode(), str(hv).encode())
+    lib.preprocess(vm)
+    n = 1 << (LOGN - 1)
+    for i, x in enumerate(inputs):
+        lib.encrypt(vm, i, np.ascontiguousarray(x).ctypes.data_as(f64p), n)
+    lib.run(vm)
+    out = np.zeros((lib.getResLen(vm), n))
+    for i in range(out.shape[0]):
+        lib.decrypt_result(vm, i, out[i].ctypes.data_as(f64p))
+    return out
+
+
+def test_polynomial_with_rotations(oracle_lib, tmp_path):
+    hc.reset()
+    n = 1 << (LOGN - 1)
+    w = np.linspace(-1, 1, n)
+
+    @hc.func("c")
+    def f(x):
+        y = x * w + 0.25            # ct*pt, ct+scalar
+        z = y * y - x               # ct*ct, sub
+        acc = hc.Empty()
+        for k in (1, -3, 17):       # Empty accumulation + rotations
+            acc = acc + z.rotate(k) * 0.5
+        return acc * acc + z * 1.0  # mul by one is folded
+
+    g = hc.save()
+    prog, c = compiler.compile_graph(g, compiler.Options(logN=LOGN, num_primes=NPR))
+    assert c.stats.get("mulcc", 0) == 2 and c.stats.get("rotate", 0) == 3
+    x = np.random.default_rng(0).uniform(-1, 1, n)
+    out = run_on(oracle_lib, prog, [x], tmp_path)[0]
+    y = x * w + 0.25
+    z = y * y - x
+    acc = sum(np.roll(z, -k) * 0.5 for k in (1, -3, 17))
+    assert np.max(np.abs(out - (acc * acc + z))) < 1e-4
+
+
+def test_deep_chain_inserts_bootstraps(oracle_lib, tmp_path):
+    hc.reset()
+
+    @hc.func("c")
+    def f(x):
+        y = x
+        for i in range(12):         # 12 multiplicative levels > 7 available
+            y = y * y * 0.9 + 0.05
+        return y
+
+    g = hc.save()
+    prog, c = compiler.compile_graph(g, compiler.Options(logN=LOGN, num_primes=NPR))
+    assert c.stats.get("bootstrap", 0) >= 1
+    n = 1 << (LOGN - 1)
+    x = np.random.default_rng(1).uniform(-1, 1, n)
+    out = run_on(oracle_lib, prog, [x], tmp_path)[0]
+    y = x.copy()
+    for i in range(12):
+        y = y * y * 0.9 + 0.05
+    assert np.max(np.abs(out - y)) < 1e-3
+
+
+def test_constant_folding_and_residual_alignment(oracle_lib, tmp_path):
+    hc.reset()
+    n = 1 << (LOGN - 1)
+
+    @hc.func("c")
+    def f(x):
+        k = hc.Plain([2.0]) * hc.Plain([0.25]) + hc.Plain([0.5])     # plain (op) plain -> 1.0
+        a = x * k                                                       # folded away
+        b = (x * [0.5, -0.5]) * (x * 0.3)                               # scale 2^80-ish after products
+        return a + b + (x.rotate(2) - 0.125)                            # operands at different scales / levels
+
+    g = hc.save()
+    prog, c = compiler.compile_graph(g, compiler.Options(logN=LOGN, num_primes=NPR))
+    x = np.random.default_rng(2).uniform(-1, 1, n)
+    out = run_on(oracle_lib, prog, [x], tmp_path)[0]
+    ref = x + (x * np.resize([0.5, -0.5], n)) * (x * 0.3) + (np.roll(x, -2) - 0.125)
+    assert np.max(np.abs(out - ref)) < 1e-4
+    text = asm.disassemble(prog)
+    assert "rotate" in text and "mulcc" in text
