@@ -214,6 +214,40 @@ def workload_config(batch, note=None):
     return c
 
 
+def resnet20_real(lib, vm, tmp, reps=3):
+    """The real encrypted ResNet-20 (BASELINE.json configs[0]) from the committed fixture: program traced from the
+    reference's examples/benchmarks/ResNet.py, compiled by dacapo_b200.compiler; rms against the plaintext torch
+    logits exactly like examples/tests/ResNet.py:113-118 (hc-test times run() only)."""
+    from dacapo_b200 import fixtures
+    cst, hv, x, expected, meta = fixtures.resnet20_files(tmp)
+    t0 = time.perf_counter()
+    lib.load(vm, cst.encode(), hv.encode())
+    lib.preprocess(vm)
+    t_pre = time.perf_counter() - t0
+    out = np.zeros(SLOTS)
+    lat, e2e = [], []
+    for i in range(reps + 1):
+        t0 = time.perf_counter()
+        lib.encrypt(vm, 0, x.ctypes.data_as(f64p), x.size)
+        t1 = time.perf_counter()
+        lib.run(vm)
+        t2 = time.perf_counter()
+        lib.decrypt_result(vm, 0, out.ctypes.data_as(f64p))
+        t3 = time.perf_counter()
+        if i:
+            lat.append(t2 - t1)
+            e2e.append(t3 - t0)
+    res = out[:meta["n_out"]] * meta["post_scale"]
+    err = res - expected
+    return {"what": "encrypted ResNet-20 (SiLU, nt=2^14 slots, N=2^15, 14x60-bit primes, waterline 40), synthetic seeded input, "
+                    "weights examples/data/resnet20.silu.model; program compiled by dacapo_b200.compiler (not hecate-opt)",
+            "run_latency_s": float(np.median(lat)), "first_run_s": None, "e2e_latency_s": float(np.median(e2e)), "load_preprocess_s": t_pre,
+            "rms": float(np.sqrt(np.sum(err * err) / res.shape[-1])), "argmax_ok": bool(np.argmax(res) == np.argmax(expected)),
+            "lowered_ops": meta["lowered_ops"], "hevm_ops": meta["hevm_ops"],
+            "reference_README": {"latency_s": 53.726, "rms": 9.515e-4, "hardware": "unspecified CPU, SEAL single thread (README.md:186-187)"},
+            "speedup_vs_README_latency": 53.726 / float(np.median(lat))}
+
+
 def resnet_mix(lib, vm, tmp, cpu=True, reps=3):
     """ResNet-20 op-mix replay (SURVEY 8d fallback; dacapo_b200/workloads.py): run() latency on the GPU and the
     CPU port's time for the same op mix, estimated from its per-op / per-level timings."""
@@ -426,6 +460,7 @@ def main():
     }
 
     if rank == 0 and world == 1 and not args.no_resnet_mix:
+        line["resnet20"] = resnet20_real(lib, vm, tmp)
         line["resnet20_opmix"] = resnet_mix(lib, vm, tmp, cpu=not args.no_cpu_baseline)
 
     if (args.op_table or world == 1) and not args.no_op_table and rank == 0:

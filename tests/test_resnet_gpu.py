@@ -24,6 +24,8 @@ def test_encrypted_resnet20_matches_plaintext_model(b200_lib, tmp_path):
     lib.preprocess(vm)
     f64p = C.POINTER(C.c_double)
     lib.encrypt(vm, 0, x.ctypes.data_as(f64p), x.size)
+    lib.run(vm)                       # first run builds the schedule / CUDA graph
+    lib.encrypt(vm, 0, x.ctypes.data_as(f64p), x.size)
     t = time.perf_counter()
     lib.run(vm)
     latency = time.perf_counter() - t
