@@ -70,7 +70,8 @@ class Options:
     rescale_bits: int = 60
     margin_bits: int = 10      # head room for |value| and noise: scale_bits + margin <= 60*level - 1
     boot_target: int = 0       # level after a greedy (in-segment) bootstrap (0 = top level)
-    min_plain_bits: int = 30   # smallest scale a plaintext factor is encoded at (encoding error ~ sqrt(N/12) / scale)
+    plain_bits: int = 40       # default scale of a plaintext factor (encoding error ~ sqrt(N/12) / 2^bits per slot)
+    min_plain_bits: int = 30   # smallest scale a plaintext factor is encoded at
     waist_bootstrap: bool = True  # place bootstraps at single-ciphertext program points, sized to the next segment
     fold_tolerance: float = 0.0
 
@@ -195,9 +196,10 @@ class Compiler:
     def mulcp(self, a, cid):
         W, R = self.o.waterline, self.o.rescale_bits
         a = self.normalize(a)
-        # plaintext scale: waterline when the product stays below the rescaling threshold (two plaintext
-        # multiplications then share one level), otherwise just enough to land on waterline + R
-        k = W if a.bits + W <= W + R + 0.5 else max(self.o.min_plain_bits, int(round(W + R - a.bits)))
+        # plaintext scale: R/2 = 30 bits while the product stays below the rescaling threshold (two plaintext
+        # multiplications then cost exactly one level), otherwise just enough to land on waterline + R
+        P = self.o.plain_bits
+        k = P if a.bits + P <= W + R + 0.5 else max(self.o.min_plain_bits, int(round(W + R - a.bits)))
         if not self.valid(a.level, a.bits + k):
             a = self.normalize(self.bootstrap(a))
         pt = self.plain(cid, a.level, k)
