@@ -93,15 +93,16 @@ template <int LOGA, int PRE> __global__ void __launch_bounds__(CTA_THREADS, (LOG
 #define MAC_MIN_CTAS 4
 #endif
 template <int LOGA> __global__ void __launch_bounds__(MAC_WARPS * 32, MAC_MIN_CTAS) k_mac(ArgsFwdB a) {
-  __shared__ __align__(16) u64 sm[MAC_SMEM_WORDS];
+  u64 *sm = dyn_smem;
   Tw *tw_s = reinterpret_cast<Tw *>(sm);
   u64 *tiles = sm + MAC_TW_WORDS;
   u64 *parts = tiles + MAC_WARPS * TILE_B_WORDS;
+  u64 *rowbufs = parts + MAC_WARPS * MAC_PART_WORDS;
   const int job = blockIdx.x, warp = threadIdx.x >> 5;
   body_mac_stage<LOGA>(a, job, threadIdx.x, tw_s);
   __syncthreads();
   LaneB8 st[1];
-  body_mac_warp<LOGA>(a, job, warp, st, tiles + warp * TILE_B_WORDS, tw_s, parts + warp * MAC_PART_WORDS);
+  body_mac_warp<LOGA>(a, job, warp, st, tiles + warp * TILE_B_WORDS, tw_s, parts + warp * MAC_PART_WORDS, rowbufs + warp * MAC_ROW_WORDS);
   __syncthreads();
   body_mac_reduce<LOGA>(a, job, threadIdx.x, parts, tiles);
   if (mac_Iidx<LOGA>(a, job) == a.l) { // special prime: continue with the inverse pass B of the two accumulator rows
@@ -172,7 +173,12 @@ template <int LOGA, int EPI> void GpuLauncher::fwd_B(const ArgsFwdB &a, int njob
 template <int LOGA> void GpuLauncher::mac(const ArgsFwdB &a, int njobs) {
   if (njobs <= 0) return;
   PRE_LAUNCH(stream, KC_FWD_B_MAC);
-  launch_pdl(k_mac<LOGA>, njobs, MAC_WARPS * 32, 0, stream, a);
+  static bool optin = false; // per LOGA instantiation
+  if (!optin) {
+    CUDA_CHECK(cudaFuncSetAttribute((const void *)k_mac<LOGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MAC_SMEM_WORDS * sizeof(u64))));
+    optin = true;
+  }
+  launch_pdl(k_mac<LOGA>, njobs, MAC_WARPS * 32, MAC_SMEM_WORDS * sizeof(u64), stream, a);
   POST_LAUNCH_S(stream);
 }
 template <int LOGA, int PRE> void GpuLauncher::invA_fwdA(const ArgsInvFwdA &a, int njobs) {

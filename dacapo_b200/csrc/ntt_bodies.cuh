@@ -27,10 +27,11 @@ enum { EPI_CANON = 0, EPI_MAC = 1, EPI_MODDOWN_GALOIS = 2, EPI_MODDOWN_RELIN = 3
 // shared memory of one MAC CTA (words): staged twiddles | MAC_WARPS tiles | MAC_WARPS partial-sum blocks
 #define TILE_B_WORDS 272 // 256 values + 256/16 padding
 #define MAC_TW_WORDS 512  // 256 staged twiddles
-#define MAC_SMEM_WORDS (MAC_TW_WORDS + MAC_WARPS * TILE_B_WORDS + MAC_WARPS * MAC_PART_WORDS)
+#define MAC_ROW_WORDS 256 // per warp: staged pass-A row of the next digit
+#define MAC_SMEM_WORDS (MAC_TW_WORDS + MAC_WARPS * TILE_B_WORDS + MAC_WARPS * MAC_PART_WORDS + MAC_WARPS * MAC_ROW_WORDS)
 
 HD Tw *warp_tw(u64 *sm) { return reinterpret_cast<Tw *>(sm + WARP_TILE_WORDS); }
-template <int LOGA> constexpr bool pass_a_needs_fold(int pre) { return pre == 2 /*PRE_ROUND*/ || LOGA >= 8; }
+template <int LOGA> HD constexpr bool pass_a_needs_fold(int pre) { return pre == 2 /*PRE_ROUND*/ || LOGA >= 8; }
 
 HD void load8_stream(const u64 *p, u64 (&v)[8]) {
   ldg_stream4(p, v[0], v[1], v[2], v[3]);
@@ -313,12 +314,32 @@ template <int LOGA> HD void body_mac_stage(const ArgsFwdB &a, int job, int tid, 
   const int N = 1 << T.logN;
   const int r = job & (Geo<LOGA>::ROWS - 1), Iidx = mac_Iidx<LOGA>(a, job), I = (Iidx == a.l) ? a.sp : Iidx;
   grid_dep_launch();
+  // the CTA's whole key footprint (2 rows of 2 KB per digit, constant data) starts moving HBM -> L2 right away,
+  // even while the predecessor kernel drains; the per-digit cp.async staging then only sees L2 latency
+#ifdef MAC_L2_PREFETCH
+  if (tid < 2 * a.l) {
+    const int J = tid >> 1, K = tid & 1;
+    prefetch_l2_bulk(a.key + (((size_t)J * 2 + K) * a.Ltot + I) * N + r * 256, 2048);
+  }
+#endif
   stage_tw_B<LOGA>(tw_s, T.tw + (size_t)I * N, r, tid, MAC_WARPS * 32);
   grid_dep_wait();
   cp_async_wait();
 }
-// phase 1 (per warp): digits J = w, w + MAC_WARPS, ...; partial sums -> part[(K*256 + e*32 + lane)*2 + {lo,hi}]
-template <int LOGA> HD void body_mac_warp(const ArgsFwdB &a, int job, int w, LaneB8 *st, u64 *tile, const Tw *tw_s, u64 *part) {
+// phase 1 (per warp): digits p = w, w + MAC_WARPS, ... of a rotated digit order (data primes: J = (I + p) mod l, so the
+// cheap diagonal term always falls to warp 0, the warp with one digit more); partial sums ->
+// part[(K*256 + e*32 + lane)*2 + {lo,hi}].
+// Operands of the NEXT digit (the pass-A row of s2 and the two key rows) are staged into shared memory with
+// cp.async while the current digit is transformed, so no butterfly stage or MAC waits on L2/HBM latency.
+//   rowbuf : 256 words, layout = global (values e*32+lane are conflict-free 64-bit reads)
+//   keybuf : two buffers of 512 words inside `part` (free until the partial sums are written);
+//            16-byte chunk g of a key row (values 2g, 2g+1) sits at slot (g&3)*32 + (g>>2), so that lane's j-th
+//            LDS.128 (values lane*8+2j, +1) reads slot j*32 + lane: conflict-free
+#ifndef MAC_ABLATE
+#define MAC_ABLATE 0
+#endif
+HD int mac_key_slot(int g) { return ((g & 3) << 5) + (g >> 2); }
+template <int LOGA> HD void body_mac_warp(const ArgsFwdB &a, int job, int w, LaneB8 *st, u64 *tile, const Tw *tw_s, u64 *part, u64 *rowbuf) {
   const NttTables &T = *a.T;
   const int N = 1 << T.logN;
   const int r = job & (Geo<LOGA>::ROWS - 1), Iidx = mac_Iidx<LOGA>(a, job), I = (Iidx == a.l) ? a.sp : Iidx;
@@ -331,14 +352,43 @@ template <int LOGA> HD void body_mac_warp(const ArgsFwdB &a, int job, int w, Lan
     _Pragma("unroll")
     for (int e = 0; e < 8; e++) lo0[li][e] = hi0[li][e] = lo1[li][e] = hi1[li][e] = 0;
   });
-  for (int J = w; J < a.l; J += MAC_WARPS) {
+  auto digit_of = [&](int p) { // p-th digit of the rotated order
+    if (Iidx == a.l) return p;
+    const int J = p + I;
+    return J >= a.l ? J - a.l : J;
+  };
+  auto stage = [&](int J, int b) {
     const u64 *k0 = a.key + (((size_t)J * 2 + 0) * a.Ltot + I) * N + r * 256;
     const u64 *k1 = a.key + (((size_t)J * 2 + 1) * a.Ltot + I) * N + r * 256;
+    const u64 *src = a.src + ((size_t)Iidx * a.l + J) * N + r * 256;
+    u64 *kb = part + b * 512;
+    FOR_LANES(S, st, {
+      (void)S;
+      _Pragma("unroll")
+      for (int i = 0; i < 4; i++) {
+        const int g = i * 32 + lane;
+        cp_async16_cg(kb + 2 * mac_key_slot(g), k0 + 2 * g);
+        cp_async16_cg(kb + 256 + 2 * mac_key_slot(g), k1 + 2 * g);
+        if (J != I) cp_async16_cg(rowbuf + 2 * g, src + 2 * g);
+      }
+    });
+  };
+  int p = w, it = 0;
+  if (p < a.l) stage(digit_of(p), 0);
+  for (; p < a.l; p += MAC_WARPS, it++) {
+    const int J = digit_of(p);
+    FOR_LANES(S, st, {
+      (void)S;
+      cp_async_wait();
+    });
     if (J == I) {
       // diagonal: NTT-form target limb J, layout C, canonical
       FOR_LANES(S, st, {
         const int base = r * 256 + lane * 8;
-        if (a.ld == LD_PLAIN) {
+        if (MAC_ABLATE & 8) {
+          _Pragma("unroll")
+          for (int e = 0; e < 8; e++) S.x[e] = base + e;
+        } else if (a.ld == LD_PLAIN) {
           load8_stream(a.tgt + (size_t)J * N + base, S.x);
         } else if (a.ld == LD_GALOIS) {
           const u64 *t = a.tgt + (size_t)J * N;
@@ -353,11 +403,13 @@ template <int LOGA> HD void body_mac_warp(const ArgsFwdB &a, int job, int w, Lan
         }
       });
     } else {
-      const u64 *src = a.src + ((size_t)Iidx * a.l + J) * N + r * 256;
       FOR_LANES(S, st, {
         _Pragma("unroll")
-        for (int e = 0; e < 8; e++) S.x[e] = ldg_stream(src + idxH(lane, e));
+        for (int e = 0; e < 8; e++) S.x[e] = rowbuf[idxH(lane, e)];
       });
+    }
+    if (p + MAC_WARPS < a.l) stage(digit_of(p + MAC_WARPS), (it + 1) & 1); // every lane has drained rowbuf / the other key buffer
+    if (J != I && !(MAC_ABLATE & 2)) {
       warp_fwdB8_regs(st, tile, tw_s, m);
       if (a.l > 20) { // sum of l products (< 12q * q each) stays below 2^128 up to l = 20
         FOR_LANES(S, st, {
@@ -366,26 +418,23 @@ template <int LOGA> HD void body_mac_warp(const ArgsFwdB &a, int job, int w, Lan
         });
       }
     }
+    const u64 *kb = part + (it & 1) * 512;
     FOR_LANES(S, st, {
       const int li = (NLANE_STATE == 1) ? 0 : lane;
-#ifdef MAC_SPLIT_KEYS
-      u64 ka[8];
-      load8_ro(k0 + lane * 8, ka);
       _Pragma("unroll")
-      for (int e = 0; e < 8; e++) mac128(lo0[li][e], hi0[li][e], S.x[e], ka[e]);
-      load8_ro(k1 + lane * 8, ka);
-      _Pragma("unroll")
-      for (int e = 0; e < 8; e++) mac128(lo1[li][e], hi1[li][e], S.x[e], ka[e]);
-#else
-      u64 ka[8], kb[8];
-      load8_ro(k0 + lane * 8, ka);
-      load8_ro(k1 + lane * 8, kb);
-      _Pragma("unroll")
-      for (int e = 0; e < 8; e++) {
-        mac128(lo0[li][e], hi0[li][e], S.x[e], ka[e]);
-        mac128(lo1[li][e], hi1[li][e], S.x[e], kb[e]);
+      for (int j = 0; j < 4; j++) {
+        const Tw ka = ldtw(reinterpret_cast<const Tw *>(kb) + j * 32 + lane);
+        const Tw kc = ldtw(reinterpret_cast<const Tw *>(kb + 256) + j * 32 + lane);
+        if (MAC_ABLATE & 1) {
+          lo0[li][2 * j] ^= S.x[2 * j] ^ ka.w, lo0[li][2 * j + 1] ^= S.x[2 * j + 1] ^ ka.wq;
+          lo1[li][2 * j] ^= S.x[2 * j] ^ kc.w, lo1[li][2 * j + 1] ^= S.x[2 * j + 1] ^ kc.wq;
+          continue;
+        }
+        mac128(lo0[li][2 * j], hi0[li][2 * j], S.x[2 * j], ka.w);
+        mac128(lo0[li][2 * j + 1], hi0[li][2 * j + 1], S.x[2 * j + 1], ka.wq);
+        mac128(lo1[li][2 * j], hi1[li][2 * j], S.x[2 * j], kc.w);
+        mac128(lo1[li][2 * j + 1], hi1[li][2 * j + 1], S.x[2 * j + 1], kc.wq);
       }
-#endif
     });
   }
   FOR_LANES(S, st, {
@@ -420,6 +469,7 @@ template <int LOGA> HD void body_mac_reduce(const ArgsFwdB &a, int job, int tid,
       hi += ph + (lo < pl ? 1 : 0);
     }
     const int K = slot >> 8, e = (slot >> 5) & 7, lane = slot & 31;
+    if ((MAC_ABLATE & 16) && lo != 12345) continue;
     const u64 v = reduce128(lo, hi, m);
     if (Iidx == a.l)
       rows[K * 256 + lane * 8 + e] = v;

@@ -58,6 +58,14 @@ HD void cp_async16(void *smem_dst, const void *gsrc) { // LDGSTS: global -> shar
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
 }
+HD void cp_async16_cg(void *smem_dst, const void *gsrc) { // L2-only (coherent with a still-draining predecessor kernel)
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+// bulk L2 prefetch of `bytes` (multiple of 16) contiguous bytes: one instruction per row, no registers, no smem
+HD void prefetch_l2_bulk(const void *gsrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
 HD void cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 HD void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 HD void cp_async_wait_keep1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); } // all but the newest group
@@ -98,6 +106,8 @@ HD void stg4(u64 *p, u64 a, u64 b, u64 c, u64 d) {
 #define NLANE_STATE 32
 HD Tw ldtw(const Tw *p) { return *p; }
 HD void cp_async16(void *smem_dst, const void *gsrc) { *(Tw *)smem_dst = *(const Tw *)gsrc; }
+HD void cp_async16_cg(void *smem_dst, const void *gsrc) { *(Tw *)smem_dst = *(const Tw *)gsrc; }
+HD void prefetch_l2_bulk(const void *, unsigned) {}
 HD void cp_async_wait() {}
 HD void cp_async_commit() {}
 HD void cp_async_wait_keep1() {}

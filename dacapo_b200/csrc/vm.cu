@@ -16,6 +16,7 @@
 #include <cstring>
 #include <fstream>
 #include <functional>
+#include <algorithm>
 #include <map>
 #include <random>
 #include <string>
@@ -557,6 +558,7 @@ struct VM {
     struct BufState { // dependency state of one PHYSICAL buffer
       cudaEvent_t wr = nullptr;
       int wr_lane = -1;
+      double ready = 0; // modelled time at which the last write lands
       std::vector<std::pair<int, cudaEvent_t>> readers;
     };
     std::map<u64 *, BufState> bs;
@@ -590,13 +592,26 @@ struct VM {
         exec(op);
         continue;
       }
-      // lane choice: least loaded; near-ties prefer the producer of the first source (no wait needed)
-      int best = 0;
-      for (int i = 1; i < nl; i++)
-        if (lanes[i].load < lanes[best].load) best = i;
+      // lane choice = list scheduling on a modelled clock: an op can start when its sources are ready and the lane
+      // is free (lane.load = time at which the lane drains); take the lane with the earliest start, preferring
+      // on ties the producer of a source (no cross-stream wait) and otherwise the lane that has been idle longest
+      // -- an op never queues behind unrelated work that is itself still waiting for its inputs
       u64 *src_buf[2] = {ct[rd[0]].d, nrd > 1 ? ct[rd[1]].d : nullptr};
-      const int pl = bs[src_buf[0]].wr_lane;
-      if (pl >= 0 && lanes[pl].load <= lanes[best].load + 30.0) best = pl;
+      double dep_ready = 0;
+      for (int k = 0; k < nrd; k++) dep_ready = std::max(dep_ready, bs[src_buf[k]].ready);
+      double min_start = 1e300;
+      for (int i = 0; i < nl; i++) min_start = std::min(min_start, std::max(lanes[i].load, dep_ready));
+      int best = -1;
+      for (int k = 0; k < nrd && best < 0; k++) { // a producer lane that is (almost) as early as any
+        const int pl = bs[src_buf[k]].wr_lane;
+        if (pl >= 0 && std::max(lanes[pl].load, dep_ready) <= min_start + 2.0) best = pl;
+      }
+      if (best < 0)
+        for (int i = 0; i < nl; i++) { // best fit: the busiest lane among those that can start at min_start
+          if (std::max(lanes[i].load, dep_ready) > min_start + 1e-9) continue;
+          if (best < 0 || lanes[i].load > lanes[best].load) best = i;
+        }
+      const double best_start = std::max(lanes[best].load, dep_ready);
       Lane &L0 = lanes[best];
       auto wait_on = [&](int lane, cudaEvent_t e) {
         if (e && lane != best) CUDA_CHECK(cudaStreamWaitEvent(L0.stream, e, 0));
@@ -639,7 +654,8 @@ struct VM {
         if (src_buf[k] != dst_buf) bs[src_buf[k]].readers.emplace_back(best, done);
       BufState &D2 = bs[dst_buf];
       D2.wr = done, D2.wr_lane = best, D2.readers.clear();
-      L0.load += op_cost(op, lvl);
+      L0.load = best_start + op_cost(op, lvl);
+      D2.ready = L0.load;
     }
     final_map.resize(home.size());
     for (size_t r = 0; r < home.size(); r++) final_map[r] = ct[r].d;

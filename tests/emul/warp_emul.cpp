@@ -50,11 +50,11 @@ struct EmuLauncher {
     for (int j = 0; j < njobs; j++) {
       alignas(16) u64 sm[MAC_SMEM_WORDS];
       Tw *tw_s = reinterpret_cast<Tw *>(sm);
-      u64 *tiles = sm + MAC_TW_WORDS, *parts = tiles + MAC_WARPS * TILE_B_WORDS;
+      u64 *tiles = sm + MAC_TW_WORDS, *parts = tiles + MAC_WARPS * TILE_B_WORDS, *rowbufs = parts + MAC_WARPS * MAC_PART_WORDS;
       for (int tid = 0; tid < MAC_WARPS * 32; tid++) body_mac_stage<LOGA>(a, j, tid, tw_s);
       for (int w = 0; w < MAC_WARPS; w++) {
         LaneB8 st[32];
-        body_mac_warp<LOGA>(a, j, w, st, tiles + w * TILE_B_WORDS, tw_s, parts + w * MAC_PART_WORDS);
+        body_mac_warp<LOGA>(a, j, w, st, tiles + w * TILE_B_WORDS, tw_s, parts + w * MAC_PART_WORDS, rowbufs + w * MAC_ROW_WORDS);
       }
       for (int tid = 0; tid < MAC_WARPS * 32; tid++) body_mac_reduce<LOGA>(a, j, tid, parts, tiles);
       if (mac_Iidx<LOGA>(a, j) == a.l)
