@@ -96,18 +96,18 @@ template <int LOGA> __global__ void __launch_bounds__(MAC_WARPS * 32, MAC_MIN_CT
   u64 *sm = dyn_smem;
   Tw *tw_s = reinterpret_cast<Tw *>(sm);
   u64 *tiles = sm + MAC_TW_WORDS;
-  u64 *parts = tiles + MAC_WARPS * TILE_B_WORDS;
-  u64 *rowbufs = parts + MAC_WARPS * MAC_PART_WORDS;
+  u64 *rowbufs = tiles + MAC_WARPS * TILE_B_WORDS;
+  u64 *xbuf = rowbufs + MAC_WARPS * MAC_ROW_WORDS;
   const int job = blockIdx.x, warp = threadIdx.x >> 5;
   body_mac_stage<LOGA>(a, job, threadIdx.x, tw_s);
   __syncthreads();
   LaneB8 st[1];
-  body_mac_warp<LOGA>(a, job, warp, st, tiles + warp * TILE_B_WORDS, tw_s, parts + warp * MAC_PART_WORDS, rowbufs + warp * MAC_ROW_WORDS);
+  body_mac_warp<LOGA>(a, job, warp, st, tiles + warp * TILE_B_WORDS, tw_s, rowbufs + warp * MAC_ROW_WORDS, xbuf);
   __syncthreads();
-  body_mac_reduce<LOGA>(a, job, threadIdx.x, parts, tiles);
+  body_mac_dot<LOGA>(a, job, threadIdx.x, xbuf, tiles);
   if (mac_Iidx<LOGA>(a, job) == a.l) { // special prime: continue with the inverse pass B of the two accumulator rows
     __syncthreads();
-    if (warp < 2) body_mac_tail<LOGA>(a, job, warp, st, parts + warp * MAC_PART_WORDS, tw_s, tiles);
+    if (warp < 2) body_mac_tail<LOGA>(a, job, warp, st, rowbufs + warp * 2 * MAC_ROW_WORDS, tw_s, tiles);
   }
 }
 
@@ -175,10 +175,10 @@ template <int LOGA> void GpuLauncher::mac(const ArgsFwdB &a, int njobs) {
   PRE_LAUNCH(stream, KC_FWD_B_MAC);
   static bool optin = false; // per LOGA instantiation
   if (!optin) {
-    CUDA_CHECK(cudaFuncSetAttribute((const void *)k_mac<LOGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MAC_SMEM_WORDS * sizeof(u64))));
+    CUDA_CHECK(cudaFuncSetAttribute((const void *)k_mac<LOGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(mac_smem_words(HEVM_MAXL) * sizeof(u64))));
     optin = true;
   }
-  launch_pdl(k_mac<LOGA>, njobs, MAC_WARPS * 32, MAC_SMEM_WORDS * sizeof(u64), stream, a);
+  launch_pdl(k_mac<LOGA>, njobs, MAC_WARPS * 32, mac_smem_words(a.l) * sizeof(u64), stream, a);
   POST_LAUNCH_S(stream);
 }
 template <int LOGA, int PRE> void GpuLauncher::invA_fwdA(const ArgsInvFwdA &a, int njobs) {
@@ -331,6 +331,11 @@ __global__ void k_ksk_finish(const NttTables *T, int logN, int L, u64 *c0, const
     c0[v] = r;
   }
 }
+// canonical key-switch key -> radix-2^30 split storage (the only consumer is the key inner product, body_mac_dot)
+__global__ void k_key_split(u64 *key, size_t words) {
+  for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < words; v += (size_t)gridDim.x * blockDim.x) key[v] = split30(key[v]);
+}
+void launch_key_split(cudaStream_t s, u64 *key, size_t words) { k_key_split<<<ew_grid(words), 256, 0, s>>>(key, words); }
 void launch_ksk_finish(cudaStream_t s, const NttTables *T, int logN, int L, u64 *c0, const u64 *c1, const u64 *sk,
                        const u64 *e, const u64 *newkey, int digit) {
   k_ksk_finish<<<ew_grid((size_t)L << logN), 256, 0, s>>>(T, logN, L, c0, c1, sk, e, newkey, digit);

@@ -23,12 +23,20 @@ enum { PRE_NONE = 0, PRE_MODUP = 1, PRE_ROUND = 2 };
 enum { EPI_CANON = 0, EPI_MAC = 1, EPI_MODDOWN_GALOIS = 2, EPI_MODDOWN_RELIN = 3, EPI_RESCALE = 4 };
 
 #define MAC_WARPS 4
-#define MAC_PART_WORDS 1024 // per warp: 2 keys x 256 values x (lo,hi)
-// shared memory of one MAC CTA (words): staged twiddles | MAC_WARPS tiles | MAC_WARPS partial-sum blocks
+// shared memory of one MAC CTA (words): staged twiddles | MAC_WARPS NTT tiles | MAC_WARPS staged rows | l transformed digit rows
 #define TILE_B_WORDS 272 // 256 values + 256/16 padding
 #define MAC_TW_WORDS 512  // 256 staged twiddles
 #define MAC_ROW_WORDS 256 // per warp: staged pass-A row of the next digit
-#define MAC_SMEM_WORDS (MAC_TW_WORDS + MAC_WARPS * TILE_B_WORDS + MAC_WARPS * MAC_PART_WORDS + MAC_WARPS * MAC_ROW_WORDS)
+#define MAC_FIXED_WORDS (MAC_TW_WORDS + MAC_WARPS * TILE_B_WORDS + MAC_WARPS * MAC_ROW_WORDS)
+HD size_t mac_smem_words(int l) { return MAC_FIXED_WORDS + (size_t)256 * l; }
+// radix-2^30 split of a value < 2^60 + 2^36: low 30 bits in the low word, the rest in the high word.  Key-switch keys
+// are stored this way, and the transformed digits are converted to it, so that the key inner product is four
+// 32x32->64 multiply-adds per term into four 64-bit column accumulators with no carries at all
+// (every partial product is < 2^60 + 2^31, 15 of them fit in 64 bits).
+#define RADIX30_MASK 0x3FFFFFFFull
+HD u64 split30(u64 v) { return (v & RADIX30_MASK) | ((v >> 30) << 32); }
+HD u64 join30(u64 w) { return (w & 0xFFFFFFFFull) + ((w >> 32) << 30); }
+#define MAC_FLUSH_DIGITS 15
 
 HD Tw *warp_tw(u64 *sm) { return reinterpret_cast<Tw *>(sm + WARP_TILE_WORDS); }
 template <int LOGA> HD constexpr bool pass_a_needs_fold(int pre) { return pre == 2 /*PRE_ROUND*/ || LOGA >= 8; }
@@ -314,81 +322,54 @@ template <int LOGA> HD void body_mac_stage(const ArgsFwdB &a, int job, int tid, 
   const int N = 1 << T.logN;
   const int r = job & (Geo<LOGA>::ROWS - 1), Iidx = mac_Iidx<LOGA>(a, job), I = (Iidx == a.l) ? a.sp : Iidx;
   grid_dep_launch();
-  // the CTA's whole key footprint (2 rows of 2 KB per digit, constant data) starts moving HBM -> L2 right away,
-  // even while the predecessor kernel drains; the per-digit cp.async staging then only sees L2 latency
-#ifdef MAC_L2_PREFETCH
-  if (tid < 2 * a.l) {
-    const int J = tid >> 1, K = tid & 1;
-    prefetch_l2_bulk(a.key + (((size_t)J * 2 + K) * a.Ltot + I) * N + r * 256, 2048);
-  }
+#ifndef MAC_PREFETCH
+#define MAC_PREFETCH 0
 #endif
+  if (MAC_PREFETCH == 1) { // the CTA's key rows (constant data) start moving HBM -> L2 now; phase 2 then sees L2 latency only
+    for (int line = tid; line < 2 * a.l * 16; line += MAC_WARPS * 32) {
+      const int JK = line >> 4;
+      prefetch_l2_line(a.key + ((size_t)JK * a.Ltot + I) * N + r * 256 + (line & 15) * 16);
+    }
+  } else if (MAC_PREFETCH == 2) {
+    if (tid < 2 * a.l) prefetch_l2_bulk(a.key + ((size_t)tid * a.Ltot + I) * N + r * 256, 2048);
+  }
   stage_tw_B<LOGA>(tw_s, T.tw + (size_t)I * N, r, tid, MAC_WARPS * 32);
   grid_dep_wait();
   cp_async_wait();
 }
 // phase 1 (per warp): digits p = w, w + MAC_WARPS, ... of a rotated digit order (data primes: J = (I + p) mod l, so the
-// cheap diagonal term always falls to warp 0, the warp with one digit more); partial sums ->
-// part[(K*256 + e*32 + lane)*2 + {lo,hi}].
-// Operands of the NEXT digit (the pass-A row of s2 and the two key rows) are staged into shared memory with
-// cp.async while the current digit is transformed, so no butterfly stage or MAC waits on L2/HBM latency.
-//   rowbuf : 256 words, layout = global (values e*32+lane are conflict-free 64-bit reads)
-//   keybuf : two buffers of 512 words inside `part` (free until the partial sums are written);
-//            16-byte chunk g of a key row (values 2g, 2g+1) sits at slot (g&3)*32 + (g>>2), so that lane's j-th
-//            LDS.128 (values lane*8+2j, +1) reads slot j*32 + lane: conflict-free
-#ifndef MAC_ABLATE
-#define MAC_ABLATE 0
-#endif
-HD int mac_key_slot(int g) { return ((g & 3) << 5) + (g >> 2); }
-template <int LOGA> HD void body_mac_warp(const ArgsFwdB &a, int job, int w, LaneB8 *st, u64 *tile, const Tw *tw_s, u64 *part, u64 *rowbuf) {
+// cheap diagonal term always falls to warp 0, the warp with one digit more).  Forward pass B of digit J, then the
+// result (folded below 2^60 + 2^36, radix-2^30 split) goes to xbuf[J][coefficient] in shared memory.
+// The pass-A row of the warp's NEXT digit is staged into `rowbuf` with cp.async while the current one is transformed.
+template <int LOGA> HD void body_mac_warp(const ArgsFwdB &a, int job, int w, LaneB8 *st, u64 *tile, const Tw *tw_s, u64 *rowbuf, u64 *xbuf) {
   const NttTables &T = *a.T;
   const int N = 1 << T.logN;
   const int r = job & (Geo<LOGA>::ROWS - 1), Iidx = mac_Iidx<LOGA>(a, job), I = (Iidx == a.l) ? a.sp : Iidx;
   const ModQ m = T.mod[I];
   LANE_DECL;
-  u64 lo0[NLANE_STATE][8], hi0[NLANE_STATE][8], lo1[NLANE_STATE][8], hi1[NLANE_STATE][8];
-  FOR_LANES(S, st, {
-    (void)S;
-    const int li = (NLANE_STATE == 1) ? 0 : lane;
-    _Pragma("unroll")
-    for (int e = 0; e < 8; e++) lo0[li][e] = hi0[li][e] = lo1[li][e] = hi1[li][e] = 0;
-  });
   auto digit_of = [&](int p) { // p-th digit of the rotated order
     if (Iidx == a.l) return p;
     const int J = p + I;
     return J >= a.l ? J - a.l : J;
   };
-  auto stage = [&](int J, int b) {
-    const u64 *k0 = a.key + (((size_t)J * 2 + 0) * a.Ltot + I) * N + r * 256;
-    const u64 *k1 = a.key + (((size_t)J * 2 + 1) * a.Ltot + I) * N + r * 256;
+  auto stage = [&](int J) {
+    if (J == I) return;
     const u64 *src = a.src + ((size_t)Iidx * a.l + J) * N + r * 256;
-    u64 *kb = part + b * 512;
     FOR_LANES(S, st, {
       (void)S;
       _Pragma("unroll")
-      for (int i = 0; i < 4; i++) {
-        const int g = i * 32 + lane;
-        cp_async16_cg(kb + 2 * mac_key_slot(g), k0 + 2 * g);
-        cp_async16_cg(kb + 256 + 2 * mac_key_slot(g), k1 + 2 * g);
-        if (J != I) cp_async16_cg(rowbuf + 2 * g, src + 2 * g);
-      }
+      for (int i = 0; i < 4; i++) cp_async16_cg(rowbuf + 2 * (i * 32 + lane), src + 2 * (i * 32 + lane));
     });
   };
-  int p = w, it = 0;
-  if (p < a.l) stage(digit_of(p), 0);
-  for (; p < a.l; p += MAC_WARPS, it++) {
+  int p = w;
+  if (p < a.l) stage(digit_of(p));
+  for (; p < a.l; p += MAC_WARPS) {
     const int J = digit_of(p);
-    FOR_LANES(S, st, {
-      (void)S;
-      cp_async_wait();
-    });
     if (J == I) {
       // diagonal: NTT-form target limb J, layout C, canonical
       FOR_LANES(S, st, {
         const int base = r * 256 + lane * 8;
-        if (MAC_ABLATE & 8) {
-          _Pragma("unroll")
-          for (int e = 0; e < 8; e++) S.x[e] = base + e;
-        } else if (a.ld == LD_PLAIN) {
+        if (a.ld == LD_PLAIN) {
           load8_stream(a.tgt + (size_t)J * N + base, S.x);
         } else if (a.ld == LD_GALOIS) {
           const u64 *t = a.tgt + (size_t)J * N;
@@ -404,77 +385,114 @@ template <int LOGA> HD void body_mac_warp(const ArgsFwdB &a, int job, int w, Lan
       });
     } else {
       FOR_LANES(S, st, {
+        cp_async_wait();
+        (void)S;
+      });
+      FOR_LANES(S, st, {
         _Pragma("unroll")
         for (int e = 0; e < 8; e++) S.x[e] = rowbuf[idxH(lane, e)];
       });
     }
-    if (p + MAC_WARPS < a.l) stage(digit_of(p + MAC_WARPS), (it + 1) & 1); // every lane has drained rowbuf / the other key buffer
-    if (J != I && !(MAC_ABLATE & 2)) {
-      warp_fwdB8_regs(st, tile, tw_s, m);
-      if (a.l > 20) { // sum of l products (< 12q * q each) stays below 2^128 up to l = 20
-        FOR_LANES(S, st, {
-          _Pragma("unroll")
-          for (int e = 0; e < 8; e++) S.x[e] = fold60(S.x[e], m.delta);
-        });
-      }
-    }
-    const u64 *kb = part + (it & 1) * 512;
+    if (p + MAC_WARPS < a.l) stage(digit_of(p + MAC_WARPS)); // every lane has drained rowbuf
+    if (J != I) warp_fwdB8_regs(st, tile, tw_s, m);
+    u64 *xo = xbuf + (size_t)J * 256;
     FOR_LANES(S, st, {
-      const int li = (NLANE_STATE == 1) ? 0 : lane;
       _Pragma("unroll")
-      for (int j = 0; j < 4; j++) {
-        const Tw ka = ldtw(reinterpret_cast<const Tw *>(kb) + j * 32 + lane);
-        const Tw kc = ldtw(reinterpret_cast<const Tw *>(kb + 256) + j * 32 + lane);
-        if (MAC_ABLATE & 1) {
-          lo0[li][2 * j] ^= S.x[2 * j] ^ ka.w, lo0[li][2 * j + 1] ^= S.x[2 * j + 1] ^ ka.wq;
-          lo1[li][2 * j] ^= S.x[2 * j] ^ kc.w, lo1[li][2 * j + 1] ^= S.x[2 * j + 1] ^ kc.wq;
-          continue;
-        }
-        mac128(lo0[li][2 * j], hi0[li][2 * j], S.x[2 * j], ka.w);
-        mac128(lo0[li][2 * j + 1], hi0[li][2 * j + 1], S.x[2 * j + 1], ka.wq);
-        mac128(lo1[li][2 * j], hi1[li][2 * j], S.x[2 * j], kc.w);
-        mac128(lo1[li][2 * j + 1], hi1[li][2 * j + 1], S.x[2 * j + 1], kc.wq);
-      }
+      for (int e = 0; e < 8; e++) xo[lane * 8 + e] = split30(fold60(S.x[e], m.delta));
     });
   }
-  FOR_LANES(S, st, {
-    (void)S;
-    const int li = (NLANE_STATE == 1) ? 0 : lane;
-    _Pragma("unroll")
-    for (int e = 0; e < 8; e++) {
-      u64 *p0 = part + (size_t)(0 * 256 + e * 32 + lane) * 2;
-      u64 *p1 = part + (size_t)(1 * 256 + e * 32 + lane) * 2;
-      p0[0] = lo0[li][e], p0[1] = hi0[li][e];
-      p1[0] = lo1[li][e], p1[1] = hi1[li][e];
-    }
-  });
 }
-// phase 2 (all threads, after a CTA barrier): sum the per-warp partials, Barrett.
+// phase 2 (all threads, after a CTA barrier): thread t owns coefficients 2t, 2t+1 of the row for both key polys and
+// runs over all digits: x from shared memory, the two key rows straight from HBM (one 16-byte load each, issued
+// MAC_KEY_BATCH digits ahead), four 32x32->64 multiply-adds per term.  Then Barrett and a 16-byte store.
 // Data primes: store acc[K][Iidx][row].  Special prime: keep the two rows in shared memory (`rows`,
 // [2][256]) for phase 3 instead -- nobody else reads them.
-template <int LOGA> HD void body_mac_reduce(const ArgsFwdB &a, int job, int tid, const u64 *parts, u64 *rows) {
+#ifndef MAC_KEY_BATCH
+#define MAC_KEY_BATCH 4
+#endif
+struct U2 {
+  u64 a, b;
+};
+HD U2 ldg_key2(const u64 *p) { // 16 bytes of key material (read-only for the life of the VM)
+#if defined(__CUDA_ARCH__)
+  const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(p));
+  return U2{v.x, v.y};
+#else
+  return U2{p[0], p[1]};
+#endif
+}
+HD void mac30(u64 (&c)[4], u64 xw, u64 kw) {
+  const u32 x0 = (u32)xw, x1 = (u32)(xw >> 32), k0 = (u32)kw, k1 = (u32)(kw >> 32);
+  c[0] += (u64)x0 * k0;
+  c[1] += (u64)x0 * k1;
+  c[2] += (u64)x1 * k0;
+  c[3] += (u64)x1 * k1;
+}
+// (lo,hi) += c0 + (c1 + c2) * 2^30 + c3 * 2^60 ; columns cleared
+HD void flush30(u64 &lo, u64 &hi, u64 (&c)[4]) {
+  const u64 mid_lo = c[1] + c[2];
+  const u64 mid_hi = mid_lo < c[1] ? 1 : 0; // 65-bit sum
+  u64 add_lo = c[0], add_hi = 0;
+  u64 t = mid_lo << 30;
+  add_lo += t, add_hi += (add_lo < t ? 1 : 0) + (mid_lo >> 34) + (mid_hi << 30);
+  t = c[3] << 60;
+  add_lo += t, add_hi += (add_lo < t ? 1 : 0) + (c[3] >> 4);
+  lo += add_lo;
+  hi += add_hi + (lo < add_lo ? 1 : 0);
+  c[0] = c[1] = c[2] = c[3] = 0;
+}
+template <int LOGA> HD void body_mac_dot(const ArgsFwdB &a, int job, int tid, const u64 *xbuf, u64 *rows) {
   const NttTables &T = *a.T;
   const int N = 1 << T.logN;
   const int r = job & (Geo<LOGA>::ROWS - 1), Iidx = mac_Iidx<LOGA>(a, job), I = (Iidx == a.l) ? a.sp : Iidx;
   const ModQ m = T.mod[I];
+  const size_t kstride = (size_t)a.Ltot * N; // words between key[J][0] and key[J][1]
+  const u64 *kp = a.key + (size_t)I * N + r * 256 + 2 * tid;
+  u64 c[2][2][4]; // [key poly][coefficient][column]
+  u64 lo[2][2], hi[2][2];
   _Pragma("unroll")
-  for (int it = 0; it < 512 / (MAC_WARPS * 32); it++) {
-    const int slot = tid + it * MAC_WARPS * 32; // K*256 + e*32 + lane
-    u64 lo = 0, hi = 0;
+  for (int K = 0; K < 2; K++)
     _Pragma("unroll")
-    for (int w = 0; w < MAC_WARPS; w++) {
-      const u64 *p = parts + (size_t)w * MAC_PART_WORDS + (size_t)slot * 2;
-      const u64 pl = p[0], ph = p[1];
-      lo += pl;
-      hi += ph + (lo < pl ? 1 : 0);
+    for (int j = 0; j < 2; j++) {
+      lo[K][j] = hi[K][j] = 0;
+      c[K][j][0] = c[K][j][1] = c[K][j][2] = c[K][j][3] = 0;
     }
-    const int K = slot >> 8, e = (slot >> 5) & 7, lane = slot & 31;
-    if ((MAC_ABLATE & 16) && lo != 12345) continue;
-    const u64 v = reduce128(lo, hi, m);
-    if (Iidx == a.l)
-      rows[K * 256 + lane * 8 + e] = v;
-    else
-      a.dst[((size_t)K * (a.l + 1) + Iidx) * N + r * 256 + lane * 8 + e] = v;
+  int since_flush = 0;
+  for (int J0 = 0; J0 < a.l; J0 += MAC_KEY_BATCH) {
+    U2 k[MAC_KEY_BATCH][2];
+    _Pragma("unroll")
+    for (int b = 0; b < MAC_KEY_BATCH; b++)
+      if (J0 + b < a.l) {
+        k[b][0] = ldg_key2(kp + (size_t)(J0 + b) * 2 * kstride);
+        k[b][1] = ldg_key2(kp + (size_t)(J0 + b) * 2 * kstride + kstride);
+      }
+    _Pragma("unroll")
+    for (int b = 0; b < MAC_KEY_BATCH; b++)
+      if (J0 + b < a.l) {
+        const u64 xa = xbuf[(size_t)(J0 + b) * 256 + 2 * tid], xb = xbuf[(size_t)(J0 + b) * 256 + 2 * tid + 1];
+        mac30(c[0][0], xa, k[b][0].a);
+        mac30(c[0][1], xb, k[b][0].b);
+        mac30(c[1][0], xa, k[b][1].a);
+        mac30(c[1][1], xb, k[b][1].b);
+        if (++since_flush == MAC_FLUSH_DIGITS) {
+          since_flush = 0;
+          _Pragma("unroll")
+          for (int K = 0; K < 2; K++)
+            _Pragma("unroll")
+            for (int j = 0; j < 2; j++) flush30(lo[K][j], hi[K][j], c[K][j]);
+        }
+      }
+  }
+  _Pragma("unroll")
+  for (int K = 0; K < 2; K++) {
+    u64 v[2];
+    _Pragma("unroll")
+    for (int j = 0; j < 2; j++) {
+      flush30(lo[K][j], hi[K][j], c[K][j]);
+      v[j] = reduce128(lo[K][j], hi[K][j], m);
+    }
+    u64 *o = (Iidx == a.l) ? rows + K * 256 + 2 * tid : a.dst + ((size_t)K * (a.l + 1) + Iidx) * N + r * 256 + 2 * tid;
+    o[0] = v[0], o[1] = v[1];
   }
 }
 // phase 3 (special-prime CTAs only, warps K = 0,1, after a CTA barrier): inverse pass B of row r of the

@@ -251,6 +251,7 @@ struct VM {
       u64 *c0 = key + ((size_t)J * 2 + 0) * L * N, *c1 = key + ((size_t)J * 2 + 1) * L * N;
       enc_zero_sym(ksk_stream(key_id, J, 0, 0), ksk_stream(key_id, J, 1, 0), c0, c1, newkey, J);
     }
+    launch_key_split(ln->stream, key, (size_t)(L - 1) * 2 * L * N); // storage format of the key inner product
     return key;
   }
   u64 galois_elt_from_step(int step) const {
@@ -951,6 +952,8 @@ int64_t hevmx_key_read(void *h, int which, uint64_t elt, uint64_t *out) {
   if (out) {
     CUDA_CHECK(cudaMemcpyAsync(out, src, w * 8, cudaMemcpyDeviceToHost, vm->ln->stream));
     CUDA_CHECK(cudaStreamSynchronize(vm->ln->stream));
+    if (which >= 2) // key-switch keys live in radix-2^30 split form on the device: hand back canonical residues
+      for (size_t i = 0; i < w; i++) out[i] = join30(out[i]);
   }
   return (int64_t)w;
 }

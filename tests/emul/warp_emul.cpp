@@ -47,20 +47,21 @@ struct EmuLauncher {
     }
   }
   template <int LOGA> void mac(const ArgsFwdB &a, int njobs) { // one CTA of MAC_WARPS warps per job; CTA barriers = phase boundaries
+    std::vector<u64> smv(mac_smem_words(a.l) + 2);
+    u64 *sm = smv.data() + ((reinterpret_cast<uintptr_t>(smv.data()) & 8) ? 1 : 0); // 16-byte aligned
     for (int j = 0; j < njobs; j++) {
-      alignas(16) u64 sm[MAC_SMEM_WORDS];
       Tw *tw_s = reinterpret_cast<Tw *>(sm);
-      u64 *tiles = sm + MAC_TW_WORDS, *parts = tiles + MAC_WARPS * TILE_B_WORDS, *rowbufs = parts + MAC_WARPS * MAC_PART_WORDS;
+      u64 *tiles = sm + MAC_TW_WORDS, *rowbufs = tiles + MAC_WARPS * TILE_B_WORDS, *xbuf = rowbufs + MAC_WARPS * MAC_ROW_WORDS;
       for (int tid = 0; tid < MAC_WARPS * 32; tid++) body_mac_stage<LOGA>(a, j, tid, tw_s);
       for (int w = 0; w < MAC_WARPS; w++) {
         LaneB8 st[32];
-        body_mac_warp<LOGA>(a, j, w, st, tiles + w * TILE_B_WORDS, tw_s, parts + w * MAC_PART_WORDS, rowbufs + w * MAC_ROW_WORDS);
+        body_mac_warp<LOGA>(a, j, w, st, tiles + w * TILE_B_WORDS, tw_s, rowbufs + w * MAC_ROW_WORDS, xbuf);
       }
-      for (int tid = 0; tid < MAC_WARPS * 32; tid++) body_mac_reduce<LOGA>(a, j, tid, parts, tiles);
+      for (int tid = 0; tid < MAC_WARPS * 32; tid++) body_mac_dot<LOGA>(a, j, tid, xbuf, tiles);
       if (mac_Iidx<LOGA>(a, j) == a.l)
         for (int K = 0; K < 2; K++) {
           LaneB8 st[32];
-          body_mac_tail<LOGA>(a, j, K, st, parts + K * MAC_PART_WORDS, tw_s, tiles);
+          body_mac_tail<LOGA>(a, j, K, st, rowbufs + K * 2 * MAC_ROW_WORDS, tw_s, tiles);
         }
     }
   }
@@ -99,7 +100,11 @@ void emul_ntt(void *h, u64 *data, int prime, int count, int inverse) {
 // ciphertext operands: compact [2][l][N]; dst may alias a or b
 void emul_keyswitch(void *h, int mode, const u64 *a, const u64 *b, u64 *dst, int l, const u64 *key, u32 elt) {
   auto e = (Emu *)h;
-  e->ops->keyswitch(mode, a, b, dst, (size_t)l * e->P.N, l, key, elt);
+  // the product stores key-switch keys in radix-2^30 split form (ntt_bodies.cuh split30); `key` is the oracle's canonical key
+  const size_t kw = (size_t)(e->P.L - 1) * 2 * e->P.L * e->P.N;
+  std::vector<u64> ks(kw);
+  for (size_t i = 0; i < kw; i++) ks[i] = split30(key[i]);
+  e->ops->keyswitch(mode, a, b, dst, (size_t)l * e->P.N, l, ks.data(), elt);
 }
 void emul_rescale(void *h, const u64 *src, u64 *dst, int l) {
   auto e = (Emu *)h;
