@@ -23,7 +23,8 @@ EXT_SYMBOLS = [
     "hevmx_set_enc_counter", "hevmx_key_read", "hevmx_galois_elt", "hevmx_backend",
 ]
 
-B200_ONLY_SYMBOLS = ["hevmx_timer", "hevmx_profile", "hevmx_profile_read", "hevmx_profiler_range"]
+B200_ONLY_SYMBOLS = ["hevmx_timer", "hevmx_profile", "hevmx_profile_read", "hevmx_profiler_range",
+                     "hevmx_ks_shard_stage", "hevmx_dev_ptr", "hevmx_stream"]
 
 _u64p = C.POINTER(C.c_uint64)
 _f64p = C.POINTER(C.c_double)
@@ -95,4 +96,9 @@ def bind(path):
         lw.hevmx_profiler_range.argtypes = [C.c_void_p, C.c_int]
         lw.hevmx_profile_read.argtypes = [C.c_void_p, C.c_int, _f64p, _i64p]
         lw.hevmx_profile_read.restype = C.c_char_p
+        lw.hevmx_ks_shard_stage.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64]
+        lw.hevmx_dev_ptr.argtypes = [C.c_void_p, C.c_int64]
+        lw.hevmx_dev_ptr.restype = C.c_void_p
+        lw.hevmx_stream.argtypes = [C.c_void_p]
+        lw.hevmx_stream.restype = C.c_void_p
     return lw

@@ -193,6 +193,8 @@ template <int LOGA, int PRE> void GpuLauncher::invA_fwdA(const ArgsInvFwdA &a, i
   template void GpuLauncher::intt_B<LOGA, LD_PRODUCT>(const ArgsInttB &, int);                                         \
   template void GpuLauncher::intt_A<LOGA>(const ArgsInttA &, int);                                                     \
   template void GpuLauncher::fwd_A<LOGA, PRE_NONE>(const ArgsFwdA &, int);                                             \
+  template void GpuLauncher::fwd_A<LOGA, PRE_MODUP>(const ArgsFwdA &, int);                                            \
+  template void GpuLauncher::fwd_A<LOGA, PRE_ROUND>(const ArgsFwdA &, int);                                            \
   template void GpuLauncher::fwd_B<LOGA, EPI_CANON>(const ArgsFwdB &, int);                                            \
   template void GpuLauncher::fwd_B<LOGA, EPI_MODDOWN_GALOIS>(const ArgsFwdB &, int);                                   \
   template void GpuLauncher::fwd_B<LOGA, EPI_MODDOWN_RELIN>(const ArgsFwdB &, int);                                    \

@@ -166,6 +166,8 @@ struct ArgsFwdA {
   int l;     // MODUP: level ; ROUND: nlim (number of target limbs)
   int sp;    // MODUP: special prime index
   int plast; // ROUND: prime index of the divided-out modulus
+  // limb-sharded key switching: only the targets [t0, t0 + nt) are produced (nt = 0: all of them)
+  int t0, nt;
 };
 template <int LOGA, int PRE> HD void body_fwd_A(const ArgsFwdA &a, int job, LaneA *st, u64 *sm) {
   const NttTables &T = *a.T;
@@ -176,17 +178,20 @@ template <int LOGA, int PRE> HD void body_fwd_A(const ArgsFwdA &a, int job, Lane
     sl = d;
     ps = pd = a.prime0 + d * a.pstep;
   } else if (PRE == PRE_MODUP) {
-    const int Iidx = d / a.l;
-    sl = d - Iidx * a.l;
+    const int Iidx = d / a.l + a.t0; // job rows enumerate the owned targets only
+    sl = d - (Iidx - a.t0) * a.l;
     ps = sl;
     pd = (Iidx == a.l) ? a.sp : Iidx;
     if (pd == ps) return; // diagonal: the NTT-form input is used directly by the MAC kernel
   } else {
-    const int K = d / a.l;
+    const int nt = a.nt ? a.nt : a.l;
+    const int K = d / nt;
     sl = K;
     ps = a.plast;
-    pd = d - K * a.l;
+    pd = a.t0 + d - K * nt;
   }
+  // row of the destination matrix: s2[Iidx][J] (MODUP), s4[K][i] (ROUND), limb d (NONE)
+  const int drow = (PRE == PRE_MODUP) ? ((pd == a.sp ? a.l : pd) * a.l + sl) : (PRE == PRE_ROUND) ? (sl * a.l + pd) : d;
   const ModQ m = T.mod[pd];
   const u64 *src = a.src + (size_t)sl * N + tile * Geo<LOGA>::C;
   u64 fix = 0;
@@ -206,7 +211,7 @@ template <int LOGA, int PRE> HD void body_fwd_A(const ArgsFwdA &a, int job, Lane
     cp_async_wait();
   });
   (void)ps;
-  warp_fwdA_from_regs<LOGA, pass_a_needs_fold<LOGA>(PRE)>(st, sm, a.dst + (size_t)d * N, tile * Geo<LOGA>::C, tw, m);
+  warp_fwdA_from_regs<LOGA, pass_a_needs_fold<LOGA>(PRE)>(st, sm, a.dst + (size_t)drow * N, tile * Geo<LOGA>::C, tw, m);
 }
 
 
@@ -311,12 +316,15 @@ struct ArgsFwdB {
   size_t pitch;      // poly pitch (words) of ct operands / output
   int plast;         // prime divided out (sp for MODDOWN, l_in-1 for RESCALE)
   u64 *sp_rows;      // MAC: [2][N] inverse pass-B output of the special-prime accumulators (mod-down input)
+  // limb-sharded key switching: MAC jobs cover the targets Iidx in (i_top - count, i_top] (i_top = 0: l);
+  // MODDOWN_GALOIS jobs cover the limbs [t0, t0 + nt) (nt = 0: all l)
+  int i_top, t0, nt;
 };
 
 // ---- key-switch inner product: one CTA of MAC_WARPS warps per (Iidx, row) ----------------------
 // phase 0 (all threads of the CTA): stage the row's twiddles of prime I
 // job -> (Iidx, row): the special prime (Iidx = l) comes first because its CTAs carry the extra tail
-template <int LOGA> HD int mac_Iidx(const ArgsFwdB &a, int job) { return a.l - (job >> LOGA); }
+template <int LOGA> HD int mac_Iidx(const ArgsFwdB &a, int job) { return (a.i_top ? a.i_top : a.l) - (job >> LOGA); }
 template <int LOGA> HD void body_mac_stage(const ArgsFwdB &a, int job, int tid, Tw *tw_s) {
   const NttTables &T = *a.T;
   const int N = 1 << T.logN;
@@ -597,12 +605,13 @@ template <int LOGA, int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, Lane
     });
     return;
   }
-  // MODDOWN_GALOIS / RESCALE: d = K*l + i
+  // MODDOWN_GALOIS / RESCALE: d = K*nt + (i - t0)
   {
-    const int K = d / a.l, i = d - K * a.l;
+    const int nt = a.nt ? a.nt : a.l;
+    const int K = d / nt, i = a.t0 + d - K * nt;
     const ModQ m = T.mod[i];
     const u64 q = m.q;
-    const u64 *src = a.src + (size_t)d * N + r * 256;
+    const u64 *src = a.src + ((size_t)K * a.l + i) * N + r * 256;
     FOR_LANES(S, st, {
       grid_dep_launch();
       stage_tw_B<LOGA>(tw, T.tw + (size_t)i * N, r, lane);

@@ -16,7 +16,8 @@ struct Scratch {      // device (or emulator-host) buffers, sized for the top le
   u64 *acc = nullptr; // [2][L][N]   key-switch accumulators
   u64 *s4 = nullptr;  // [2][L][N]   forward pass-A output of the rounding terms
   u64 *pc0 = nullptr; // [L][N]      permuted c0 (rotate)
-  static size_t words(int L, size_t N) { return ((size_t)L + L + (size_t)L * (L - 1) + 2 * L + 2 * L + L) * N; }
+  u64 *rnd = nullptr; // [2][N]      limb-sharded key switch: rounded special-limb coefficients (broadcast by their owner)
+  static size_t words(int L, size_t N) { return ((size_t)L + L + (size_t)L * (L - 1) + 2 * L + 2 * L + L + 2) * N; }
   void carve(u64 *base, int L, size_t N) {
     s1 = base;
     t = s1 + (size_t)L * N;
@@ -24,6 +25,7 @@ struct Scratch {      // device (or emulator-host) buffers, sized for the top le
     acc = s2 + (size_t)L * (L - 1) * N;
     s4 = acc + (size_t)2 * L * N;
     pc0 = s4 + (size_t)2 * L * N;
+    rnd = pc0 + (size_t)L * N;
   }
 };
 
@@ -35,6 +37,9 @@ struct OpsIface {
   virtual void ntt_inv(const u64 *src, u64 *dst, int nl, int prime0, int pstep, int round = 0) = 0;
   virtual void keyswitch(int mode, const u64 *a, const u64 *b, u64 *dst, size_t pitch, int l, const u64 *key, u32 elt) = 0;
   virtual void rescale(const u64 *src, size_t src_pitch, u64 *dst, size_t dst_pitch, int l) = 0;
+  // limb-sharded rotation key switch: this rank owns the key-switch targets [tlo, thi) of [0, l]
+  // (target l = the special prime); between the stages the caller exchanges sc.t (all-gather) and sc.rnd (broadcast)
+  virtual void ks_shard_stage(int stage, const u64 *a, u64 *dst, size_t pitch, int l, const u64 *key, u32 elt, int tlo, int thi) = 0;
 };
 
 template <class LA, int LOGA> struct HeOps : OpsIface {
@@ -140,6 +145,54 @@ template <class LA, int LOGA> struct HeOps : OpsIface {
         w.add0 = a, w.add1 = b;
         la.template fwd_B<LOGA, EPI_MODDOWN_RELIN>(w, l * ROWS);
       }
+    }
+  }
+
+  // ---- limb-sharded rotation key switch ------------------------------------------------------------
+  // The output limbs (targets) of SEAL's switch_key are partitioned over ranks; a rank holds / reads only its limbs
+  // of the key and of the ciphertext.  Same arithmetic as keyswitch(LD_GALOIS), cut where data must cross ranks:
+  //   stage 1  own data limbs of perm(c1): inverse NTT -> coefficient digits sc.t[J], perm(c0) -> sc.pc0[J]
+  //            <all-gather of sc.t rows over the ranks>
+  //   stage 2  own targets I: (t_J mod q_I) forward NTT for every digit J, inner product with key[J][.][I];
+  //            owner of the special limb: inverse NTT + rounding of its two accumulator rows -> sc.rnd
+  //            <broadcast of sc.rnd from the special limb's owner>
+  //   stage 3  own data limbs: NTT of the rounding term, (acc - u) * p^-1 + perm(c0) -> dst limbs
+  void ks_shard_stage(int stage, const u64 *a, u64 *dst, size_t pitch, int l, const u64 *key, u32 elt, int tlo, int thi) override {
+    const int dhi = thi < l ? thi : l, nd = dhi - tlo; // owned data limbs [tlo, dhi)
+    const bool own_sp = thi == l + 1;
+    if (stage == 1) {
+      if (nd <= 0) return;
+      ArgsInttB x{};
+      x.T = T, x.src = a + pitch + (size_t)tlo * N, x.c0 = a + (size_t)tlo * N, x.pc0 = sc.pc0 + (size_t)tlo * N;
+      x.dst = sc.s1 + (size_t)tlo * N, x.nl = nd, x.prime0 = tlo, x.pstep = 1, x.elt = elt;
+      la.template intt_B<LOGA, LD_GALOIS>(x, nd * ROWS);
+      ArgsInttA y{};
+      y.T = T, y.src = sc.s1 + (size_t)tlo * N, y.dst = sc.t + (size_t)tlo * N, y.nl = nd, y.prime0 = tlo, y.pstep = 1, y.round = 0;
+      la.template intt_A<LOGA>(y, nd * TILES_A);
+    } else if (stage == 2) {
+      const int nt = thi - tlo;
+      if (nt <= 0) return;
+      ArgsFwdA x{};
+      x.T = T, x.src = sc.t, x.dst = sc.s2, x.l = l, x.sp = sp(), x.t0 = tlo, x.nt = nt;
+      la.template fwd_A<LOGA, PRE_MODUP>(x, nt * l * TILES_A);
+      ArgsFwdB m{};
+      m.T = T, m.src = sc.s2, m.dst = sc.acc, m.l = l, m.sp = sp(), m.key = key, m.Ltot = L, m.ld = LD_GALOIS, m.elt = elt;
+      m.tgt = a + pitch, m.sp_rows = sc.s1, m.i_top = thi - 1;
+      la.template mac<LOGA>(m, nt * ROWS);
+      if (own_sp) {
+        ArgsInttA y{};
+        y.T = T, y.src = sc.s1, y.dst = sc.rnd, y.nl = 2, y.prime0 = sp(), y.pstep = 0, y.round = 1;
+        la.template intt_A<LOGA>(y, 2 * TILES_A);
+      }
+    } else {
+      if (nd <= 0) return;
+      ArgsFwdA x{};
+      x.T = T, x.src = sc.rnd, x.dst = sc.s4, x.l = l, x.plast = sp(), x.t0 = tlo, x.nt = nd;
+      la.template fwd_A<LOGA, PRE_ROUND>(x, 2 * nd * TILES_A);
+      ArgsFwdB w{};
+      w.T = T, w.src = sc.s4, w.dst = dst, w.l = l, w.sp = sp(), w.acc = sc.acc, w.pitch = pitch, w.plast = sp(), w.add0 = sc.pc0;
+      w.t0 = tlo, w.nt = nd;
+      la.template fwd_B<LOGA, EPI_MODDOWN_GALOIS>(w, 2 * nd * ROWS);
     }
   }
 

@@ -977,6 +977,26 @@ double hevmx_timer(void *h, int which) {
   return (double)ms;
 }
 // cudaProfilerStart/Stop so that `ncu --profile-from-start off` skips key generation
+void hevmx_ks_shard_stage(void *h, int stage, int64_t dst, int64_t src, int64_t step, int64_t tlo, int64_t thi) {
+  VM *vm = V(h);
+  vm->ln = &vm->lanes[0];
+  CtReg &s = vm->ctr((size_t)src), &d = vm->ctr((size_t)dst);
+  if (s.level < 1) die("ks_shard: empty source register");
+  if (tlo < 0 || thi > s.level + 1 || tlo > thi) die("ks_shard: bad target range");
+  const u64 elt = vm->galois_elt_from_step((int)step);
+  auto it = vm->d_gal.find(elt);
+  if (it == vm->d_gal.end()) die("ks_shard: no Galois key for this step (use a power of two)");
+  vm->ln->ops->ks_shard_stage(stage, s.d, d.d, vm->pitch, s.level, it->second, (u32)elt, (int)tlo, (int)thi);
+  if (stage == 3) d.level = s.level, d.scale = s.scale;
+}
+void *hevmx_dev_ptr(void *h, int64_t which) {
+  VM *vm = V(h);
+  if (which == 0) return vm->lanes[0].ops->sc.t;
+  if (which == 1) return vm->lanes[0].ops->sc.rnd;
+  if (which >= 16) return vm->ctr((size_t)(which - 16)).d;
+  return nullptr;
+}
+void *hevmx_stream(void *h) { return (void *)V(h)->lanes[0].stream; }
 void hevmx_profiler_range(void *h, int on) {
   CUDA_CHECK(cudaStreamSynchronize(V(h)->ln->stream));
   if (on)

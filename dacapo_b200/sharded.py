@@ -1,0 +1,94 @@
+"""Limb-sharded rotation key switch across the GPUs of one node (BASELINE.json configs[4]).
+
+SEAL's switch_key (reference: the `rotate` opcode, lib/Runtime/SEAL_HEVM.cpp:269-274 -> Evaluator::rotate_vector ->
+switch_key_inplace) produces every output limb I from ALL digits J of the operand:
+
+    acc[K][I] = sum_J  NTT_I(INTT_J(c1[J]) mod q_I) * key[J][K][I]
+
+so the natural partition is by OUTPUT limb ("target"): rank g owns a contiguous range of the l+1 targets (data limbs
+0..l-1 and the special limb, target l), reads only those limbs of the key and writes only those limbs of the result.
+Two exchanges are needed per key switch and they are the only collectives on the path:
+
+    stage 1   own data limbs of perm(c1) -> coefficient digits                 (libB200_HEVM: hevmx_ks_shard_stage 1)
+    exchange  all-gather of the digits: l * N * 8 bytes in total                (NCCL over NVLink)
+    stage 2   mod-up + key inner product for the own targets; the owner of the
+              special limb also runs its inverse NTT and the rounding            (stage 2)
+    exchange  broadcast of the two rounded special-limb rows: 2 * N * 8 bytes   (NCCL)
+    stage 3   mod-down of the own data limbs                                    (stage 3)
+
+The collectives are issued on the VM's own CUDA stream (wrapped as a torch ExternalStream), so there is no host
+synchronisation between stages and exchanges.  Results are bit-identical to the single-GPU rotate.
+In this first version every rank still holds the whole key and ciphertext in memory; only the limbs it owns are read.
+"""
+from typing import List, Tuple
+
+
+def partition_targets(level: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous, balanced ranges [tlo, thi) of the level+1 key-switch targets; the last rank owns the special limb."""
+    n = level + 1
+    return [(n * g // world, n * (g + 1) // world) for g in range(world)]
+
+
+def digit_exchange_plan(level: int, world: int) -> List[Tuple[int, int, int]]:
+    """(owner rank, first row, end row) of the coefficient-digit rows each rank contributes to the all-gather."""
+    plan = []
+    for g, (tlo, thi) in enumerate(partition_targets(level, world)):
+        hi = min(thi, level)
+        if hi > tlo:
+            plan.append((g, tlo, hi))
+    return plan
+
+
+def special_owner(level: int, world: int) -> int:
+    for g, (_, thi) in enumerate(partition_targets(level, world)):
+        if thi == level + 1:
+            return g
+    raise AssertionError
+
+
+class _DevMem:
+    """Zero-copy view of device memory for torch.as_tensor (CUDA array interface v2, int64 words)."""
+
+    def __init__(self, ptr: int, nwords: int):
+        self.__cuda_array_interface__ = {"shape": (nwords,), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
+
+
+class ShardedRotate:
+    """One instance per rank (one process per GPU).  `lib`/`vm`: a bound libB200_HEVM.so and its VM on this rank's GPU."""
+
+    def __init__(self, lib, vm, rank: int, world: int, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.lib, self.vm, self.rank, self.world, self.group = lib, vm, rank, world, group
+        self.N = 1 << lib.hevmx_param(vm, 0)
+        self.L = lib.hevmx_param(vm, 1)
+        self.stream = torch.cuda.ExternalStream(lib.hevmx_stream(vm))
+        self.digits = torch.as_tensor(_DevMem(lib.hevmx_dev_ptr(vm, 0), self.L * self.N), device="cuda").view(self.L, self.N)
+        self.rnd = torch.as_tensor(_DevMem(lib.hevmx_dev_ptr(vm, 1), 2 * self.N), device="cuda").view(2, self.N)
+
+    def ct_tensor(self, reg: int):
+        """[2][L-1][N] int64 view of a ciphertext register's limb storage."""
+        t = self.torch.as_tensor(_DevMem(self.lib.hevmx_dev_ptr(self.vm, 16 + reg), 2 * (self.L - 1) * self.N), device="cuda")
+        return t.view(2, self.L - 1, self.N)
+
+    def rotate(self, dst: int, src: int, step: int, level: int):
+        """dst <- rotate(src, step) with the key switch sharded over the ranks; every rank ends up holding the limbs
+        it owns in register `dst` (use `gather` to replicate them)."""
+        lib, vm, dist = self.lib, self.vm, self.dist
+        tlo, thi = partition_targets(level, self.world)[self.rank]
+        with self.torch.cuda.stream(self.stream):
+            lib.hevmx_ks_shard_stage(vm, 1, dst, src, step, tlo, thi)
+            for owner, a, b in digit_exchange_plan(level, self.world):
+                dist.broadcast(self.digits[a:b], src=owner, group=self.group)
+            lib.hevmx_ks_shard_stage(vm, 2, dst, src, step, tlo, thi)
+            dist.broadcast(self.rnd, src=special_owner(level, self.world), group=self.group)
+            lib.hevmx_ks_shard_stage(vm, 3, dst, src, step, tlo, thi)
+
+    def gather(self, reg: int, level: int):
+        """Replicate a limb-sharded register: every owner broadcasts its data limbs of both polynomials."""
+        ct = self.ct_tensor(reg)
+        with self.torch.cuda.stream(self.stream):
+            for owner, a, b in digit_exchange_plan(level, self.world):
+                for k in range(2):
+                    self.dist.broadcast(ct[k, a:b], src=owner, group=self.group)

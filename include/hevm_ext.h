@@ -44,6 +44,16 @@ double hevmx_timer(void *vm, int which);        /* CUDA events on the VM stream:
 void hevmx_profiler_range(void *vm, int on);  /* cudaProfilerStart/Stop (ncu --profile-from-start off) */
 void hevmx_profile(void *vm, int on);           /* per-kernel-class CUDA-event timing */
 const char *hevmx_profile_read(void *vm, int cls, double *ms, int64_t *count); /* NULL past the last class */
+/* --- limb-sharded rotation key switch across GPUs (host side: dacapo_b200/sharded.py) ---
+ * The l+1 key-switch targets (data limbs 0..l-1, special limb = target l) are partitioned over ranks; this rank owns
+ * [tlo, thi).  stage 1: own limbs of perm(c1) -> coefficient digits; <all-gather digits>; stage 2: mod-up + key inner
+ * product for the own targets, owner of the special limb also rounds it; <broadcast rounding rows>; stage 3: mod-down
+ * of the own data limbs into `dst`.  `step` must have a Galois key of its own (one key switch). */
+void hevmx_ks_shard_stage(void *vm, int stage, int64_t dst, int64_t src, int64_t step, int64_t tlo, int64_t thi);
+/* device addresses for the exchanges: which 0 = coefficient digits [L][N] u64, 1 = rounding rows [2][N] u64,
+ * 16 + r = limb data of ciphertext register r ([2][L-1][N] u64) */
+void *hevmx_dev_ptr(void *vm, int64_t which);
+void *hevmx_stream(void *vm);                   /* the cudaStream_t the VM issues hevmx_* work on */
 
 #ifdef __cplusplus
 }

@@ -46,3 +46,56 @@ def test_shard_balanced():
             parts = [D.shard(list(range(n)), r, w) for r in range(w)]
             assert sum(parts, []) == list(range(n))
             assert max(map(len, parts)) - min(map(len, parts)) <= 1
+
+
+SHARD_WORKER = r"""
+import os, sys
+sys.path.insert(0, os.environ["REPO"])
+import torch, torch.distributed as dist
+from dacapo_b200.sharded import partition_targets, digit_exchange_plan, special_owner
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+level, N = 13, 64
+tlo, thi = partition_targets(level, world)[rank]
+# the exchange wiring of ShardedRotate.rotate on CPU tensors: every rank fills the digit rows it owns ...
+digits = torch.full((level + 1, N), -1, dtype=torch.int64)
+digits[tlo:min(thi, level)] = rank
+for owner, a, b in digit_exchange_plan(level, world):
+    dist.broadcast(digits[a:b], src=owner)
+# ... and afterwards every rank sees every digit row tagged by its owner
+for g, (a, b) in enumerate(partition_targets(level, world)):
+    assert (digits[a:min(b, level)] == g).all()
+rnd = torch.full((2, N), rank, dtype=torch.int64)
+dist.broadcast(rnd, src=special_owner(level, world))
+assert (rnd == world - 1).all()
+dist.barrier()
+dist.destroy_process_group()
+os.write(1, f"shard{rank}ok\n".encode())
+"""
+
+
+def test_sharded_keyswitch_exchange_plan_gloo(tmp_path):
+    """world_size-2 gloo run of the two exchanges of the limb-sharded key switch (all-gather of digits, broadcast of the rounding rows)."""
+    script = tmp_path / "shard_worker.py"
+    script.write_text(SHARD_WORKER)
+    env = dict(os.environ, REPO=str(REPO))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29543", str(script)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "shard0ok" in r.stdout and "shard1ok" in r.stdout
+
+
+def test_target_partition_properties():
+    sys.path.insert(0, str(REPO))
+    from dacapo_b200.sharded import partition_targets, digit_exchange_plan, special_owner
+    for level in (1, 2, 7, 13, 29):
+        for w in (1, 2, 3, 4, 8):
+            parts = partition_targets(level, w)
+            assert parts[0][0] == 0 and parts[-1][1] == level + 1
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) <= 1
+            assert special_owner(level, w) == max(g for g, (a, b) in enumerate(parts) if b > a)
+            rows = sorted(r for _, a, b in digit_exchange_plan(level, w) for r in range(a, b))
+            assert rows == list(range(level))

@@ -34,6 +34,7 @@ def emul(LOGN):
     lib.emul_ntt.argtypes = [C.c_void_p, u64p, C.c_int, C.c_int, C.c_int]
     lib.emul_keyswitch.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p, C.c_int, u64p, C.c_uint32]
     lib.emul_rescale.argtypes = [C.c_void_p, u64p, u64p, C.c_int]
+    lib.emul_keyswitch_sharded.argtypes = [C.c_void_p, u64p, u64p, C.c_int, u64p, C.c_uint32, C.c_int]
     return lib, lib.emul_create(LOGN, NPR, 60)
 
 
@@ -113,4 +114,20 @@ def test_rotate_kernels_vs_oracle(emul, vm, step):
     key = vm.key(3, elt)
     got = a.copy()  # in place
     lib.emul_keyswitch(h, 1, _p(got), None, _p(got), lvl, _p(key), elt)
+    assert np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize("ranks", [1, 2, 3])
+def test_sharded_rotate_kernels_vs_oracle(emul, vm, ranks):
+    """Limb-sharded key switch (targets partitioned over `ranks`, stages separated by the exchanges) == SEAL rotate."""
+    lib, h = emul
+    lvl, step = 3, 2
+    a = vm.random_ct(lvl, 11)
+    vm.ct_write(0, a)
+    vm.exec(asm.ROTATE, 1, 0, step)
+    exp = vm.ct_read(1)
+    elt = vm.lib.hevmx_galois_elt(vm.vm, step)
+    key = vm.key(3, elt)
+    got = np.zeros_like(a)
+    lib.emul_keyswitch_sharded(h, _p(a), _p(got), lvl, _p(key), elt, ranks)
     assert np.array_equal(got, exp)
