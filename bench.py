@@ -323,6 +323,7 @@ def main():
     ap.add_argument("--op-table", action="store_true", help="(default at N=1) measure the per-op/per-level table and emit profiled_B200_GPU.json")
     ap.add_argument("--no-op-table", action="store_true")
     ap.add_argument("--no-resnet-mix", action="store_true", help="skip the ResNet-20 op-mix replay (N=1 only)")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the limb-sharded key-switch section (N>1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -499,6 +500,12 @@ def main():
         line["cpu_baseline"] = {"value": ops * reps / t, "unit": "ops/s", "cores": 1, "kind": "port",
                                 "sample": f"1 ciphertext chain ({ops} HEVM ops, levels 13..1) x {reps} repetitions on one host core "
                                           f"(the reference's SEAL evaluator is single-threaded); host has {os.cpu_count()} cores"}
+    if world > 1 and not args.no_sharded:
+        # BASELINE.json configs[4]: RNS-limb-sharded key switch at N = 2^16 over the N GPUs (NCCL all-gather of the digits
+        # + broadcast of the rounded special limb); not part of `value`, reported beside it
+        from dacapo_b200 import sharded
+        sk = sharded.measure(lib, rank, world, logn=16, nprimes=30)
+        line["sharded_keyswitch"] = sk
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -92,3 +92,71 @@ class ShardedRotate:
             for owner, a, b in digit_exchange_plan(level, self.world):
                 for k in range(2):
                     self.dist.broadcast(ct[k, a:b], src=owner, group=self.group)
+
+
+def measure(lib, rank: int, world: int, logn: int = 16, nprimes: int = 30, levels=None, reps: int = 20, seed: int = 0xDACA90):
+    """Bit-exactness and device-time of the sharded rotate against the single-GPU rotate on this node's GPUs.
+    Every rank derives the same keys from `seed`.  Returns a dict (identical on all ranks).  Needs torch.distributed
+    (NCCL) initialised and the current CUDA device set."""
+    import ctypes as C
+    import os
+    import tempfile
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from . import hevm_asm as asm
+    keydir = tempfile.mkdtemp(prefix=f"hevm_shard_keys_r{rank}_")
+    old = {k: os.environ.get(k) for k in ("HEVM_LOGN", "HEVM_NUM_PRIMES", "HEVM_SEED", "HEVM_PRIME_BITS")}
+    os.environ.update(HEVM_LOGN=str(logn), HEVM_NUM_PRIMES=str(nprimes), HEVM_SEED=str(seed), HEVM_PRIME_BITS="60")
+    try:
+        lib.create_context(keydir.encode())
+    finally:
+        for k, v in old.items():
+            os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+    vm = lib.initFullVM(keydir.encode(), True)
+    lib.hevmx_resize(vm, 4, 1)
+    N, u64p = 1 << logn, C.POINTER(C.c_uint64)
+    primes = np.zeros(nprimes, dtype=np.uint64)
+    lib.hevmx_primes(vm, primes.ctypes.data_as(u64p))
+    sr = ShardedRotate(lib, vm, rank, world)
+    step = 4
+    out = {"ring": f"N=2^{logn}, {nprimes} x 60-bit primes", "world": world, "rotate_step": step, "levels": {}}
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        lib.hevmx_sync(vm)
+        dist.barrier()
+        torch.cuda.synchronize()
+        lib.hevmx_timer(vm, 0)
+        for _ in range(reps):
+            fn()
+        t = torch.tensor([lib.hevmx_timer(vm, 1) / reps], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) * 1e3
+
+    for lvl in levels or (nprimes - 1, (nprimes - 1) // 2):
+        rng = np.random.default_rng(1000 + lvl)  # same ciphertext on every rank
+        a = np.zeros((2, lvl, N), dtype=np.uint64)
+        for i in range(lvl):
+            a[:, i, :] = rng.integers(0, int(primes[i]), size=(2, N), dtype=np.uint64)
+        lib.hevmx_ct_write(vm, 0, a.ctypes.data_as(u64p), lvl, 2.0 ** 40)
+        lib.hevmx_ct_write(vm, 2, np.zeros_like(a).ctypes.data_as(u64p), lvl, 2.0 ** 40)
+        lib.hevmx_exec(vm, asm.ROTATE, 1, 0, step)
+        exp = np.zeros_like(a)
+        lib.hevmx_ct_read(vm, 1, exp.ctypes.data_as(u64p))
+        sr.rotate(2, 0, step, lvl)
+        sr.gather(2, lvl)
+        lib.hevmx_sync(vm)
+        got = np.zeros_like(a)
+        lib.hevmx_ct_read(vm, 2, got.ctypes.data_as(u64p))
+        ok = torch.tensor([1 if np.array_equal(got, exp) else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        t_sh = timed(lambda: sr.rotate(2, 0, step, lvl))
+        t_1 = timed(lambda: lib.hevmx_exec(vm, asm.ROTATE, 1, 0, step))
+        out["levels"][str(lvl)] = {"bit_exact_vs_single_gpu": bool(ok.item()), "sharded_us": round(t_sh, 1), "single_gpu_us": round(t_1, 1),
+                                   "speedup": round(t_1 / t_sh, 3), "targets_per_rank": [b - a_ for a_, b in partition_targets(lvl, world)],
+                                   "allgather_bytes": lvl * N * 8, "broadcast_bytes": 2 * N * 8}
+    return out

@@ -120,6 +120,24 @@ def test_rotate(pair, lvl, step):
         assert np.array_equal(g.ct_read(dst), o.ct_read(dst)), (lvl, step, dst)
 
 
+@pytest.mark.parametrize("lvl,step,ranks", [(13, 1, 1), (13, -8192, 2), (7, 64, 3), (2, 1, 4), (1, 1, 2)])
+def test_sharded_keyswitch_stages_bit_exact(pair, lvl, step, ranks):
+    """Limb-sharded rotate (hevm_ext.h hevmx_ks_shard_stage): `ranks` target partitions executed stage by stage on ONE
+    GPU -- sharing the scratch buffers stands in for the NCCL all-gather / broadcast -- equals the oracle's rotate."""
+    from dacapo_b200.sharded import partition_targets
+    g, o = pair
+    a = o.random_ct(lvl, 900 + lvl)
+    o.ct_write(0, a, 2.0 ** 40)
+    o.exec(asm.ROTATE, 1, 0, step)
+    g.ct_write(0, a, 2.0 ** 40)
+    g.ct_write(1, np.zeros_like(a), 2.0 ** 40)
+    for stage in (1, 2, 3):
+        for tlo, thi in partition_targets(lvl, ranks):
+            g.lib.hevmx_ks_shard_stage(g.vm, stage, 1, 0, step, tlo, thi)
+    g.lib.hevmx_sync(g.vm)
+    assert np.array_equal(g.ct_read(1), o.ct_read(1)), (lvl, step, ranks)
+
+
 def test_encode_decode_bit_exact(pair):
     g, o = pair
     rng = np.random.default_rng(7)
