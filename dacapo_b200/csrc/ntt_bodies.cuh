@@ -316,15 +316,15 @@ struct ArgsFwdB {
   size_t pitch;      // poly pitch (words) of ct operands / output
   int plast;         // prime divided out (sp for MODDOWN, l_in-1 for RESCALE)
   u64 *sp_rows;      // MAC: [2][N] inverse pass-B output of the special-prime accumulators (mod-down input)
-  // limb-sharded key switching: MAC jobs cover the targets Iidx in (i_top - count, i_top] (i_top = 0: l);
+  // limb-sharded key switching: MAC jobs cover the targets Iidx = i_end-1, i_end-2, ... (i_end = 0: l+1, i.e. all);
   // MODDOWN_GALOIS jobs cover the limbs [t0, t0 + nt) (nt = 0: all l)
-  int i_top, t0, nt;
+  int i_end, t0, nt;
 };
 
 // ---- key-switch inner product: one CTA of MAC_WARPS warps per (Iidx, row) ----------------------
 // phase 0 (all threads of the CTA): stage the row's twiddles of prime I
 // job -> (Iidx, row): the special prime (Iidx = l) comes first because its CTAs carry the extra tail
-template <int LOGA> HD int mac_Iidx(const ArgsFwdB &a, int job) { return (a.i_top ? a.i_top : a.l) - (job >> LOGA); }
+template <int LOGA> HD int mac_Iidx(const ArgsFwdB &a, int job) { return (a.i_end ? a.i_end - 1 : a.l) - (job >> LOGA); }
 template <int LOGA> HD void body_mac_stage(const ArgsFwdB &a, int job, int tid, Tw *tw_s) {
   const NttTables &T = *a.T;
   const int N = 1 << T.logN;

@@ -177,7 +177,7 @@ template <class LA, int LOGA> struct HeOps : OpsIface {
       la.template fwd_A<LOGA, PRE_MODUP>(x, nt * l * TILES_A);
       ArgsFwdB m{};
       m.T = T, m.src = sc.s2, m.dst = sc.acc, m.l = l, m.sp = sp(), m.key = key, m.Ltot = L, m.ld = LD_GALOIS, m.elt = elt;
-      m.tgt = a + pitch, m.sp_rows = sc.s1, m.i_top = thi - 1;
+      m.tgt = a + pitch, m.sp_rows = sc.s1, m.i_end = thi;
       la.template mac<LOGA>(m, nt * ROWS);
       if (own_sp) {
         ArgsInttA y{};

@@ -117,7 +117,7 @@ def test_rotate_kernels_vs_oracle(emul, vm, step):
     assert np.array_equal(got, exp)
 
 
-@pytest.mark.parametrize("ranks", [1, 2, 3])
+@pytest.mark.parametrize("ranks", [1, 2, 3, 5])
 def test_sharded_rotate_kernels_vs_oracle(emul, vm, ranks):
     """Limb-sharded key switch (targets partitioned over `ranks`, stages separated by the exchanges) == SEAL rotate."""
     lib, h = emul
