@@ -431,10 +431,18 @@ HD U2 ldg_key2(const u64 *p) { // 16 bytes of key material (read-only for the li
 }
 HD void mac30(u64 (&c)[4], u64 xw, u64 kw) {
   const u32 x0 = (u32)xw, x1 = (u32)(xw >> 32), k0 = (u32)kw, k1 = (u32)(kw >> 32);
+#if defined(__CUDA_ARCH__)
+  // one IMAD.WIDE.U32 each (the compiler's own lowering of the C form below splits the 64-bit accumulation)
+  asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c[0]) : "r"(x0), "r"(k0));
+  asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c[1]) : "r"(x0), "r"(k1));
+  asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c[2]) : "r"(x1), "r"(k0));
+  asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c[3]) : "r"(x1), "r"(k1));
+#else
   c[0] += (u64)x0 * k0;
   c[1] += (u64)x0 * k1;
   c[2] += (u64)x1 * k0;
   c[3] += (u64)x1 * k1;
+#endif
 }
 // (lo,hi) += c0 + (c1 + c2) * 2^30 + c3 * 2^60 ; columns cleared
 HD void flush30(u64 &lo, u64 &hi, u64 (&c)[4]) {
@@ -456,49 +464,56 @@ template <int LOGA> HD void body_mac_dot(const ArgsFwdB &a, int job, int tid, co
   const ModQ m = T.mod[I];
   const size_t kstride = (size_t)a.Ltot * N; // words between key[J][0] and key[J][1]
   const u64 *kp = a.key + (size_t)I * N + r * 256 + 2 * tid;
-  u64 c[2][2][4]; // [key poly][coefficient][column]
-  u64 lo[2][2], hi[2][2];
-  _Pragma("unroll")
-  for (int K = 0; K < 2; K++)
+  const size_t dstride = 2 * kstride; // words between consecutive digits of the key
+  const u64 pol = 0;
+  (void)pol;
+  // digits [Jb, Je), Je - Jb <= MAC_FLUSH_DIGITS: a straight multiply-add loop over batches of MAC_KEY_BATCH digits
+  // (key rows of a batch are loaded together; digits past Je contribute a zero key), then one recombination
+  auto chunk = [&](int Jb, int Je, u64 (&lo)[2][2], u64 (&hi)[2][2]) {
+    u64 c[2][2][4]; // [key poly][coefficient][column]
     _Pragma("unroll")
-    for (int j = 0; j < 2; j++) {
-      lo[K][j] = hi[K][j] = 0;
-      c[K][j][0] = c[K][j][1] = c[K][j][2] = c[K][j][3] = 0;
-    }
-  int since_flush = 0;
-  for (int J0 = 0; J0 < a.l; J0 += MAC_KEY_BATCH) {
-    U2 k[MAC_KEY_BATCH][2];
-    _Pragma("unroll")
-    for (int b = 0; b < MAC_KEY_BATCH; b++)
-      if (J0 + b < a.l) {
-        k[b][0] = ldg_key2(kp + (size_t)(J0 + b) * 2 * kstride);
-        k[b][1] = ldg_key2(kp + (size_t)(J0 + b) * 2 * kstride + kstride);
+    for (int K = 0; K < 2; K++)
+      _Pragma("unroll")
+      for (int j = 0; j < 2; j++) c[K][j][0] = c[K][j][1] = c[K][j][2] = c[K][j][3] = 0;
+    for (int J0 = Jb; J0 < Je; J0 += MAC_KEY_BATCH) {
+      U2 k[MAC_KEY_BATCH][2];
+      _Pragma("unroll")
+      for (int b = 0; b < MAC_KEY_BATCH; b++) {
+        const u64 *p = kp + (size_t)(J0 + b) * dstride;
+        if (J0 + b < Je) {
+          k[b][0] = ldg_key2(p);
+          k[b][1] = ldg_key2(p + kstride);
+        } else {
+          k[b][0] = k[b][1] = U2{0, 0};
+        }
       }
-    _Pragma("unroll")
-    for (int b = 0; b < MAC_KEY_BATCH; b++)
-      if (J0 + b < a.l) {
-        const u64 xa = xbuf[(size_t)(J0 + b) * 256 + 2 * tid], xb = xbuf[(size_t)(J0 + b) * 256 + 2 * tid + 1];
+      _Pragma("unroll")
+      for (int b = 0; b < MAC_KEY_BATCH; b++) {
+        const int J = J0 + b < Je ? J0 + b : Je - 1; // stay inside xbuf; the key is zero there
+        const u64 *xp = xbuf + (size_t)J * 256 + 2 * tid;
+        const u64 xa = xp[0], xb = xp[1];
         mac30(c[0][0], xa, k[b][0].a);
         mac30(c[0][1], xb, k[b][0].b);
         mac30(c[1][0], xa, k[b][1].a);
         mac30(c[1][1], xb, k[b][1].b);
-        if (++since_flush == MAC_FLUSH_DIGITS) {
-          since_flush = 0;
-          _Pragma("unroll")
-          for (int K = 0; K < 2; K++)
-            _Pragma("unroll")
-            for (int j = 0; j < 2; j++) flush30(lo[K][j], hi[K][j], c[K][j]);
-        }
       }
+    }
+    _Pragma("unroll")
+    for (int K = 0; K < 2; K++)
+      _Pragma("unroll")
+      for (int j = 0; j < 2; j++) flush30(lo[K][j], hi[K][j], c[K][j]);
+  };
+  u64 lo[2][2] = {{0, 0}, {0, 0}}, hi[2][2] = {{0, 0}, {0, 0}};
+  if (a.l <= MAC_FLUSH_DIGITS) {
+    chunk(0, a.l, lo, hi);
+  } else {
+    for (int Jc = 0; Jc < a.l; Jc += MAC_FLUSH_DIGITS) chunk(Jc, a.l < Jc + MAC_FLUSH_DIGITS ? a.l : Jc + MAC_FLUSH_DIGITS, lo, hi);
   }
   _Pragma("unroll")
   for (int K = 0; K < 2; K++) {
     u64 v[2];
     _Pragma("unroll")
-    for (int j = 0; j < 2; j++) {
-      flush30(lo[K][j], hi[K][j], c[K][j]);
-      v[j] = reduce128(lo[K][j], hi[K][j], m);
-    }
+    for (int j = 0; j < 2; j++) v[j] = reduce128(lo[K][j], hi[K][j], m);
     u64 *o = (Iidx == a.l) ? rows + K * 256 + 2 * tid : a.dst + ((size_t)K * (a.l + 1) + Iidx) * N + r * 256 + 2 * tid;
     o[0] = v[0], o[1] = v[1];
   }
