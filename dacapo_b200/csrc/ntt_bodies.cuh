@@ -143,11 +143,12 @@ template <int LOGA> HD void body_intt_A(const ArgsInttA &a, int job, LaneA *st, 
   u64 *dst = a.dst + (size_t)limb * N + tile * Geo<LOGA>::C;
   const u64 half = q >> 1;
   FOR_LANES(S, st, {
+    u64 *dstR = dst + ((size_t)rowR<LOGA>(lane, 0) << 8) + colA<LOGA>(lane);
     _Pragma("unroll")
     for (int e = 0; e < 16; e++) {
       u64 v = S.x[e];
       if (a.round) v = csub(v + half, q);
-      dst[((size_t)rowR<LOGA>(lane, e) << 8) + colA<LOGA>(lane)] = v;
+      dstR[(size_t)e * (Geo<LOGA>::ROWS / 16) << 8] = v; // row rowR(lane, e)
     }
   });
 }
@@ -203,7 +204,7 @@ template <int LOGA, int PRE> HD void body_fwd_A(const ArgsFwdA &a, int job, Lane
     stage_tw_A<LOGA>(tw, T.tw + (size_t)pd * N, lane);
     grid_dep_wait();
     _Pragma("unroll")
-    for (int e = 0; e < 16; e++) S.y[e] = ldg_stream(src + ((size_t)rowR<LOGA>(lane, e) << 8) + colA<LOGA>(lane));
+    for (int e = 0; e < 16; e++) S.y[e] = ldg_stream(src + ((size_t)rowR<LOGA>(lane, 0) << 8) + colA<LOGA>(lane) + ((size_t)e * (Geo<LOGA>::ROWS / 16) << 8));
     // No modular reduction: every prime is 2^60 - delta with delta < 2^32, so a canonical residue of
     // ANY prime is < 2^60 < 2*q_dst, i.e. already a valid lazy representative mod q_dst.
     _Pragma("unroll")

@@ -348,11 +348,12 @@ HD void warp_fwdA_from_regs(LaneA *st, u64 *sm, u64 *dst, int c0, const Tw *tw, 
     for (int e = 0; e < 16; e++) sm[padx(idxR(lane, e))] = FOLD ? fold60(S.y[e], dl) : S.y[e];
   });
   FOR_LANES(S, st, {
+    u64 *dstS = dst + ((size_t)rowS<LOGA>(lane, 0) << 8) + c0 + colA<LOGA>(lane);
     _Pragma("unroll")
     for (int e = 0; e < 16; e++) S.y[e] = sm[padx(idxS<LOGA>(lane, e))];
     fwdA_stages_S<LOGA>(S.y, lane, tw, q, q2);
     _Pragma("unroll")
-    for (int e = 0; e < 16; e++) dst[((size_t)rowS<LOGA>(lane, e) << 8) + c0 + colA<LOGA>(lane)] = S.y[e];
+    for (int e = 0; e < 16; e++) dstS[e << 8] = S.y[e]; // row rowS(lane, e): one base + compile-time offsets
   });
 }
 
@@ -362,8 +363,9 @@ HD void warp_invA_to_regs(LaneA *st, u64 *sm, const u64 *src, int c0, const Tw *
   const u64 q = m.q, q2 = 2 * m.q, dl = m.delta;
   LANE_DECL;
   FOR_LANES(S, st, {
+    const u64 *srcS = src + ((size_t)rowS<LOGA>(lane, 0) << 8) + c0 + colA<LOGA>(lane);
     _Pragma("unroll")
-    for (int e = 0; e < 16; e++) S.x[e] = ldg_stream(src + ((size_t)rowS<LOGA>(lane, e) << 8) + c0 + colA<LOGA>(lane));
+    for (int e = 0; e < 16; e++) S.x[e] = ldg_stream(srcS + (e << 8)); // row rowS(lane, e)
     invA_stages_S<LOGA>(S.x, lane, itw, q, q2, dl);
     _Pragma("unroll")
     for (int e = 0; e < 16; e++) sm[padx(idxS<LOGA>(lane, e))] = S.x[e];
