@@ -243,6 +243,13 @@ __global__ void __launch_bounds__(256) k_elementwise(const NttTables *T, int log
       ldg_stream4(p + rem, y[0], y[1], y[2], y[3]);
 #pragma unroll
       for (int e = 0; e < 4; e++) r[e] = mulmod(x[e], y[e], m);
+    } else if (OP == EW_MULP_ADD) { // multiply_plain followed by add of another ciphertext: same canonical values, one HBM pass
+      const ModQ m = T->mod[i];
+      u64 z[4];
+      ldg_stream4(p + rem, y[0], y[1], y[2], y[3]);
+      ldg_stream4(b + off, z[0], z[1], z[2], z[3]);
+#pragma unroll
+      for (int e = 0; e < 4; e++) r[e] = csub(mulmod(x[e], y[e], m) + z[e], q);
     } else {
 #pragma unroll
       for (int e = 0; e < 4; e++) r[e] = x[e];
@@ -265,6 +272,7 @@ void launch_elementwise(cudaStream_t s, int op, const NttTables *T, int logN, u6
   case EW_NEG: k_elementwise<EW_NEG><<<g, 256, 0, s>>>(T, logN, out, a, b, p, pitch, l, nvec); break;
   case EW_ADDP: k_elementwise<EW_ADDP><<<g, 256, 0, s>>>(T, logN, out, a, b, p, pitch, l, nvec); break;
   case EW_MULP: k_elementwise<EW_MULP><<<g, 256, 0, s>>>(T, logN, out, a, b, p, pitch, l, nvec); break;
+  case EW_MULP_ADD: k_elementwise<EW_MULP_ADD><<<g, 256, 0, s>>>(T, logN, out, a, b, p, pitch, l, nvec); break;
   default: k_elementwise<EW_COPY><<<g, 256, 0, s>>>(T, logN, out, a, b, p, pitch, l, nvec); break;
   }
   POST_LAUNCH_S(s);

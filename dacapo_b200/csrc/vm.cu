@@ -408,6 +408,7 @@ struct VM {
     d.level = s.level, d.scale = s.scale;
   }
   u64 boot_index = 0; // encryptions issued so far inside the current run()
+  bool meta_only = false; // exec() of addcc / mulcp updates register metadata only (their kernels were fused by the scheduler)
   void exec(const HevmOp &op) {
     switch (op.opcode) {
     case 1: { // rotate
@@ -461,7 +462,7 @@ struct VM {
       if (a.level != b.level) die("addcc: level mismatch");
       const int l = a.level;
       const double sc = a.scale;
-      launch_elementwise(ln->stream, EW_ADD, dT, logN, d.d, a.d, b.d, nullptr, pitch, l);
+      if (!meta_only) launch_elementwise(ln->stream, EW_ADD, dT, logN, d.d, a.d, b.d, nullptr, pitch, l);
       d.level = l, d.scale = sc;
       break;
     }
@@ -491,7 +492,7 @@ struct VM {
       if (a.level != p.level) die("mulcp: level mismatch");
       const int l = a.level;
       const double sc = a.scale * p.scale;
-      launch_elementwise(ln->stream, EW_MULP, dT, logN, d.d, a.d, nullptr, p.d, pitch, l);
+      if (!meta_only) launch_elementwise(ln->stream, EW_MULP, dT, logN, d.d, a.d, nullptr, p.d, pitch, l);
       d.level = l, d.scale = sc;
       break;
     }
@@ -573,7 +574,83 @@ struct VM {
     cudaEvent_t fork = new_event();
     CUDA_CHECK(cudaEventRecord(fork, lanes[0].stream));
     for (int i = 1; i < nl; i++) CUDA_CHECK(cudaStreamWaitEvent(lanes[i].stream, fork, 0));
-    for (const HevmOp &op : prog) {
+    // peephole: mulcp t <- x * p immediately followed by addcc d <- t + y (either operand order) where t is dead
+    // afterwards becomes ONE kernel d <- x * p + y (same canonical residues; register metadata of both ops is
+    // still applied in order).  Liveness is conservative: every register is live at the end of the program.
+    std::vector<char> fuse(prog.size(), 0);
+    {
+      static const bool on = !(std::getenv("HEVM_FUSE") && std::atoi(std::getenv("HEVM_FUSE")) == 0);
+      std::vector<char> live(ct.size(), 1);
+      for (size_t i = prog.size(); on && i-- > 0;) {
+        const HevmOp &o = prog[i];
+        const bool writes = (o.opcode >= 1 && o.opcode <= 4) || (o.opcode >= 6 && o.opcode <= 10);
+        if (!writes || o.dst >= ct.size()) continue;
+        if (i > 0 && o.opcode == 6 && prog[i - 1].opcode == 9 && o.lhs < ct.size() && o.rhs < ct.size()) {
+          const HevmOp &m = prog[i - 1];
+          const int t = m.dst;
+          const bool t_once = (o.lhs == t) != (o.rhs == t);
+          const bool t_dead = (o.dst == t) || !live[t]; // liveness after the addcc
+          if (t_once && t_dead && m.lhs < ct.size()) fuse[i - 1] = 1;
+        }
+        live[o.dst] = 0;
+        live[o.lhs < ct.size() ? o.lhs : o.dst] = 1;
+        if (o.opcode == 6 || o.opcode == 8) live[o.rhs < ct.size() ? o.rhs : o.dst] = 1;
+      }
+    }
+    for (size_t pc = 0; pc < prog.size(); pc++) {
+      const HevmOp &op = prog[pc];
+      if (fuse[pc]) {
+        const HevmOp &m = op, &ad = prog[pc + 1];
+        const int t = m.dst, y = (ad.lhs == t) ? ad.rhs : ad.lhs, wr = ad.dst;
+        u64 *xb = ct[m.lhs].d, *yb = ct[y].d;
+        const u64 *pb = ptr(m.rhs).d;
+        const int lvl = ct[m.lhs].level;
+        if (ct[y].level != lvl) die("addcc: level mismatch");
+        u64 *srcs[2] = {xb, yb};
+        double dep_ready = std::max(bs[xb].ready, bs[yb].ready), min_start = 1e300;
+        for (int i = 0; i < nl; i++) min_start = std::min(min_start, std::max(lanes[i].load, dep_ready));
+        int best = -1;
+        for (int k = 0; k < 2 && best < 0; k++) {
+          const int pl = bs[srcs[k]].wr_lane;
+          if (pl >= 0 && std::max(lanes[pl].load, dep_ready) <= min_start + 2.0) best = pl;
+        }
+        if (best < 0)
+          for (int i = 0; i < nl; i++) {
+            if (std::max(lanes[i].load, dep_ready) > min_start + 1e-9) continue;
+            if (best < 0 || lanes[i].load > lanes[best].load) best = i;
+          }
+        const double best_start = std::max(lanes[best].load, dep_ready);
+        Lane &L0 = lanes[best];
+        auto wait_on = [&](int lane, cudaEvent_t e) {
+          if (e && lane != best) CUDA_CHECK(cudaStreamWaitEvent(L0.stream, e, 0));
+        };
+        u64 *old_buf = ct[wr].d, *dst_buf = old_buf;
+        if (pool_head < pool.size()) {
+          dst_buf = pool[pool_head++];
+          pool.push_back(old_buf);
+        }
+        for (int k = 0; k < 2; k++) wait_on(bs[srcs[k]].wr_lane, bs[srcs[k]].wr);
+        BufState &D = bs[dst_buf];
+        wait_on(D.wr_lane, D.wr);
+        for (auto &r : D.readers) wait_on(r.first, r.second);
+        ln = &L0;
+        launch_elementwise(L0.stream, EW_MULP_ADD, dT, logN, dst_buf, xb, yb, pb, pitch, lvl);
+        meta_only = true; // both ops' level / scale bookkeeping, in program order (SEAL_HEVM.cpp:297-323)
+        exec(m);
+        exec(ad);
+        meta_only = false;
+        ct[wr].d = dst_buf;
+        cudaEvent_t done = new_event();
+        CUDA_CHECK(cudaEventRecord(done, L0.stream));
+        for (int k = 0; k < 2; k++)
+          if (srcs[k] != dst_buf) bs[srcs[k]].readers.emplace_back(best, done);
+        BufState &D2 = bs[dst_buf];
+        D2.wr = done, D2.wr_lane = best, D2.readers.clear();
+        L0.load = best_start + 5.0;
+        D2.ready = L0.load;
+        pc++;
+        continue;
+      }
       int rd[2], nrd = 0, wr = -1;
       switch (op.opcode) {
       case 1: case 2: case 3: case 10: rd[nrd++] = op.lhs, wr = op.dst; break;

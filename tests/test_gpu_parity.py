@@ -247,6 +247,52 @@ def test_program_through_c_abi(pair, tmp_path):
         vm.lib.hevmx_resize(vm.vm, 8, 4)
 
 
+def test_fused_mulcp_addcc_bit_exact(pair, tmp_path):
+    """The scheduler fuses `mulcp t; addcc d <- t + y` (t dead afterwards) into one kernel: every aliasing form, plus the
+    forms that must NOT be fused (t read again later), against the oracle's sequential interpreter."""
+    g, o = pair
+    lv = 3
+    p = asm.Program(init_level=13)
+    x, y = p.arg(40, lv), p.arg(40, lv)
+    regs = [p.new_ct() for _ in range(6)]
+    c1, c2 = p.const(np.linspace(-0.9, 0.7, 53)), p.const([0.5, -0.25, 0.125])
+    p1, p2 = p.new_pt(), p.new_pt()
+    p.encode(p1, c1, lv, 40)
+    p.encode(p2, c2, lv, 40)
+    t, d, acc, u, w, z = regs
+    p.emit(asm.MULCP, t, x, p1); p.emit(asm.ADDCC, d, t, y)        # t as lhs, fresh destination (t dead: overwritten next)
+    p.emit(asm.MULCP, t, y, p2); p.emit(asm.ADDCC, t, d, t)        # t as rhs, destination = t
+    p.emit(asm.MULCP, acc, x, p2)                                   # plain mulcp (next op is not an addcc of it)
+    p.emit(asm.ROTATE, u, acc, 1)
+    p.emit(asm.MULCP, w, u, p1); p.emit(asm.ADDCC, acc, acc, w)    # in-place accumulation, w dead (overwritten below)
+    p.emit(asm.MULCP, w, w, p2); p.emit(asm.ADDCC, z, w, acc)      # mulcp in place; w is read again below -> not fused
+    p.emit(asm.ADDCC, u, w, z)
+    p.emit(asm.MULCP, w, x, p1); p.emit(asm.ADDCC, w, w, w)        # both operands are the temporary -> not fused
+    for r in (t, d, acc, u, w, z):
+        p.result(r, 80, lv)
+    cst, hv = tmp_path / "f.cst", tmp_path / "f.hevm"
+    p.save(cst, hv)
+    n = o.N // 2
+    rng = np.random.default_rng(77)
+    xs, ys = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    outs = []
+    for vm in pair:
+        lib = vm.lib
+        lib.load(vm.vm, str(cst).encode(), str(hv).encode())
+        lib.preprocess(vm.vm)
+        lib.hevmx_set_enc_counter(vm.vm, 9)
+        for i, dd in enumerate((xs, ys)):
+            lib.encrypt(vm.vm, i, dd.ctypes.data_as(C.POINTER(C.c_double)), n)
+        lib.run(vm.vm)
+        lib.run(vm.vm)  # second run = graph replay on the GPU; inputs are untouched by the program
+        outs.append([(vm.ct_read(r), vm.ct_info(r)) for r in (t, d, acc, u, w, z)])
+    for (a, ia), (b, ib) in zip(*outs):
+        assert ia == ib
+        assert np.array_equal(a, b)
+    for vm in pair:
+        vm.lib.hevmx_resize(vm.vm, 8, 4)
+
+
 def test_full_size_properties(pair):
     """Size-independent properties on the device alone (no oracle): add/negate cancel exactly,
     rotate(k) o rotate(-k) = id up to noise, rotate and multiply commute with decryption."""
