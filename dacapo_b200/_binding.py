@@ -24,7 +24,7 @@ EXT_SYMBOLS = [
 ]
 
 B200_ONLY_SYMBOLS = ["hevmx_timer", "hevmx_profile", "hevmx_profile_read", "hevmx_profiler_range",
-                     "hevmx_ks_shard_stage", "hevmx_dev_ptr", "hevmx_stream"]
+                     "hevmx_ks_shard_stage", "hevmx_mulcc_shard_stage", "hevmx_dev_ptr", "hevmx_stream"]
 
 _u64p = C.POINTER(C.c_uint64)
 _f64p = C.POINTER(C.c_double)
@@ -97,6 +97,7 @@ def bind(path):
         lw.hevmx_profile_read.argtypes = [C.c_void_p, C.c_int, _f64p, _i64p]
         lw.hevmx_profile_read.restype = C.c_char_p
         lw.hevmx_ks_shard_stage.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64]
+        lw.hevmx_mulcc_shard_stage.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64]
         lw.hevmx_dev_ptr.argtypes = [C.c_void_p, C.c_int64]
         lw.hevmx_dev_ptr.restype = C.c_void_p
         lw.hevmx_stream.argtypes = [C.c_void_p]

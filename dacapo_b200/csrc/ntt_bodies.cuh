@@ -572,7 +572,7 @@ template <int LOGA, int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, Lane
   if (EPI == EPI_MODDOWN_RELIN) {
     // d = limb i; both output polys are produced by the same warp so that every input
     // (a0,a1,b0,b1 at this position) is read before either output is written (dst may alias a or b).
-    const int i = d;
+    const int i = d + a.t0; // limb-sharded: jobs enumerate the owned limbs [t0, t0 + nt)
     const ModQ m = T.mod[i];
     const u64 q = m.q;
     const Tw inv = T.qinv[a.plast][i];

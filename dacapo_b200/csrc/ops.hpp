@@ -37,9 +37,10 @@ struct OpsIface {
   virtual void ntt_inv(const u64 *src, u64 *dst, int nl, int prime0, int pstep, int round = 0) = 0;
   virtual void keyswitch(int mode, const u64 *a, const u64 *b, u64 *dst, size_t pitch, int l, const u64 *key, u32 elt) = 0;
   virtual void rescale(const u64 *src, size_t src_pitch, u64 *dst, size_t dst_pitch, int l) = 0;
-  // limb-sharded rotation key switch: this rank owns the key-switch targets [tlo, thi) of [0, l]
+  // limb-sharded key switch: this rank owns the key-switch targets [tlo, thi) of [0, l]
   // (target l = the special prime); between the stages the caller exchanges sc.t (all-gather) and sc.rnd (broadcast)
-  virtual void ks_shard_stage(int stage, const u64 *a, u64 *dst, size_t pitch, int l, const u64 *key, u32 elt, int tlo, int thi) = 0;
+  // mode LD_GALOIS: rotation of ciphertext `a` (b unused); mode LD_PRODUCT: multiply a*b + relinearise
+  virtual void ks_shard_stage(int stage, int mode, const u64 *a, const u64 *b, u64 *dst, size_t pitch, int l, const u64 *key, u32 elt, int tlo, int thi) = 0;
 };
 
 template <class LA, int LOGA> struct HeOps : OpsIface {
@@ -157,15 +158,20 @@ template <class LA, int LOGA> struct HeOps : OpsIface {
   //            owner of the special limb: inverse NTT + rounding of its two accumulator rows -> sc.rnd
   //            <broadcast of sc.rnd from the special limb's owner>
   //   stage 3  own data limbs: NTT of the rounding term, (acc - u) * p^-1 + perm(c0) -> dst limbs
-  void ks_shard_stage(int stage, const u64 *a, u64 *dst, size_t pitch, int l, const u64 *key, u32 elt, int tlo, int thi) override {
+  void ks_shard_stage(int stage, int mode, const u64 *a, const u64 *b, u64 *dst, size_t pitch, int l, const u64 *key, u32 elt, int tlo, int thi) override {
     const int dhi = thi < l ? thi : l, nd = dhi - tlo; // owned data limbs [tlo, dhi)
     const bool own_sp = thi == l + 1;
     if (stage == 1) {
       if (nd <= 0) return;
       ArgsInttB x{};
-      x.T = T, x.src = a + pitch + (size_t)tlo * N, x.c0 = a + (size_t)tlo * N, x.pc0 = sc.pc0 + (size_t)tlo * N;
-      x.dst = sc.s1 + (size_t)tlo * N, x.nl = nd, x.prime0 = tlo, x.pstep = 1, x.elt = elt;
-      la.template intt_B<LOGA, LD_GALOIS>(x, nd * ROWS);
+      x.T = T, x.dst = sc.s1 + (size_t)tlo * N, x.nl = nd, x.prime0 = tlo, x.pstep = 1, x.elt = elt;
+      if (mode == LD_GALOIS) {
+        x.src = a + pitch + (size_t)tlo * N, x.c0 = a + (size_t)tlo * N, x.pc0 = sc.pc0 + (size_t)tlo * N;
+        la.template intt_B<LOGA, LD_GALOIS>(x, nd * ROWS);
+      } else { // d2 = a1 * b1 on the own limbs
+        x.src = a + pitch + (size_t)tlo * N, x.src2 = b + pitch + (size_t)tlo * N;
+        la.template intt_B<LOGA, LD_PRODUCT>(x, nd * ROWS);
+      }
       ArgsInttA y{};
       y.T = T, y.src = sc.s1 + (size_t)tlo * N, y.dst = sc.t + (size_t)tlo * N, y.nl = nd, y.prime0 = tlo, y.pstep = 1, y.round = 0;
       la.template intt_A<LOGA>(y, nd * TILES_A);
@@ -176,8 +182,8 @@ template <class LA, int LOGA> struct HeOps : OpsIface {
       x.T = T, x.src = sc.t, x.dst = sc.s2, x.l = l, x.sp = sp(), x.t0 = tlo, x.nt = nt;
       la.template fwd_A<LOGA, PRE_MODUP>(x, nt * l * TILES_A);
       ArgsFwdB m{};
-      m.T = T, m.src = sc.s2, m.dst = sc.acc, m.l = l, m.sp = sp(), m.key = key, m.Ltot = L, m.ld = LD_GALOIS, m.elt = elt;
-      m.tgt = a + pitch, m.sp_rows = sc.s1, m.i_end = thi;
+      m.T = T, m.src = sc.s2, m.dst = sc.acc, m.l = l, m.sp = sp(), m.key = key, m.Ltot = L, m.ld = mode, m.elt = elt;
+      m.tgt = a + pitch, m.tgt2 = (mode == LD_PRODUCT) ? b + pitch : nullptr, m.sp_rows = sc.s1, m.i_end = thi;
       la.template mac<LOGA>(m, nt * ROWS);
       if (own_sp) {
         ArgsInttA y{};
@@ -190,9 +196,15 @@ template <class LA, int LOGA> struct HeOps : OpsIface {
       x.T = T, x.src = sc.rnd, x.dst = sc.s4, x.l = l, x.plast = sp(), x.t0 = tlo, x.nt = nd;
       la.template fwd_A<LOGA, PRE_ROUND>(x, 2 * nd * TILES_A);
       ArgsFwdB w{};
-      w.T = T, w.src = sc.s4, w.dst = dst, w.l = l, w.sp = sp(), w.acc = sc.acc, w.pitch = pitch, w.plast = sp(), w.add0 = sc.pc0;
+      w.T = T, w.src = sc.s4, w.dst = dst, w.l = l, w.sp = sp(), w.acc = sc.acc, w.pitch = pitch, w.plast = sp();
       w.t0 = tlo, w.nt = nd;
-      la.template fwd_B<LOGA, EPI_MODDOWN_GALOIS>(w, 2 * nd * ROWS);
+      if (mode == LD_GALOIS) {
+        w.add0 = sc.pc0;
+        la.template fwd_B<LOGA, EPI_MODDOWN_GALOIS>(w, 2 * nd * ROWS);
+      } else { // (a0 b0, a0 b1 + a1 b0) + mod-down, own limbs only; dst may alias a or b
+        w.add0 = a, w.add1 = b;
+        la.template fwd_B<LOGA, EPI_MODDOWN_RELIN>(w, nd * ROWS);
+      }
     }
   }
 

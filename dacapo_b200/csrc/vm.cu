@@ -1063,8 +1063,20 @@ void hevmx_ks_shard_stage(void *h, int stage, int64_t dst, int64_t src, int64_t 
   const u64 elt = vm->galois_elt_from_step((int)step);
   auto it = vm->d_gal.find(elt);
   if (it == vm->d_gal.end()) die("ks_shard: no Galois key for this step (use a power of two)");
-  vm->ln->ops->ks_shard_stage(stage, s.d, d.d, vm->pitch, s.level, it->second, (u32)elt, (int)tlo, (int)thi);
+  vm->ln->ops->ks_shard_stage(stage, LD_GALOIS, s.d, nullptr, d.d, vm->pitch, s.level, it->second, (u32)elt, (int)tlo, (int)thi);
   if (stage == 3) d.level = s.level, d.scale = s.scale;
+}
+void hevmx_mulcc_shard_stage(void *h, int stage, int64_t dst, int64_t lhs, int64_t rhs, int64_t tlo, int64_t thi) {
+  VM *vm = V(h);
+  vm->ln = &vm->lanes[0];
+  CtReg &a = vm->ctr((size_t)lhs), &b = vm->ctr((size_t)rhs), &d = vm->ctr((size_t)dst);
+  if (a.level != b.level || a.level < 1) die("mulcc_shard: level mismatch");
+  if (tlo < 0 || thi > a.level + 1 || tlo > thi) die("mulcc_shard: bad target range");
+  const int l = a.level;
+  static double sc = 0; // product scale, fixed at stage 1: dst may alias an operand, and stage 3 may run once per owned range
+  if (stage == 1) sc = a.scale * b.scale;
+  vm->ln->ops->ks_shard_stage(stage, LD_PRODUCT, a.d, b.d, d.d, vm->pitch, l, vm->d_relin, 0, (int)tlo, (int)thi);
+  if (stage == 3) d.level = l, d.scale = sc;
 }
 void *hevmx_dev_ptr(void *h, int64_t which) {
   VM *vm = V(h);

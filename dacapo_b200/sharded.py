@@ -1,4 +1,4 @@
-"""Limb-sharded rotation key switch across the GPUs of one node (BASELINE.json configs[4]).
+"""Limb-sharded key switch (rotation and multiply + relinearise) across the GPUs of one node (BASELINE.json configs[4]).
 
 SEAL's switch_key (reference: the `rotate` opcode, lib/Runtime/SEAL_HEVM.cpp:269-274 -> Evaluator::rotate_vector ->
 switch_key_inplace) produces every output limb I from ALL digits J of the operand:
@@ -85,6 +85,18 @@ class ShardedRotate:
             dist.broadcast(self.rnd, src=special_owner(level, self.world), group=self.group)
             lib.hevmx_ks_shard_stage(vm, 3, dst, src, step, tlo, thi)
 
+    def mulcc(self, dst: int, lhs: int, rhs: int, level: int):
+        """dst <- lhs * rhs with relinearisation, sharded the same way (hevmx_mulcc_shard_stage); dst may alias an operand."""
+        lib, vm, dist = self.lib, self.vm, self.dist
+        tlo, thi = partition_targets(level, self.world)[self.rank]
+        with self.torch.cuda.stream(self.stream):
+            lib.hevmx_mulcc_shard_stage(vm, 1, dst, lhs, rhs, tlo, thi)
+            for owner, a, b in digit_exchange_plan(level, self.world):
+                dist.broadcast(self.digits[a:b], src=owner, group=self.group)
+            lib.hevmx_mulcc_shard_stage(vm, 2, dst, lhs, rhs, tlo, thi)
+            dist.broadcast(self.rnd, src=special_owner(level, self.world), group=self.group)
+            lib.hevmx_mulcc_shard_stage(vm, 3, dst, lhs, rhs, tlo, thi)
+
     def gather(self, reg: int, level: int):
         """Replicate a limb-sharded register: every owner broadcasts its data limbs of both polynomials."""
         ct = self.ct_tensor(reg)
@@ -156,7 +168,21 @@ def measure(lib, rank: int, world: int, logn: int = 16, nprimes: int = 30, level
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         t_sh = timed(lambda: sr.rotate(2, 0, step, lvl))
         t_1 = timed(lambda: lib.hevmx_exec(vm, asm.ROTATE, 1, 0, step))
-        out["levels"][str(lvl)] = {"bit_exact_vs_single_gpu": bool(ok.item()), "sharded_us": round(t_sh, 1), "single_gpu_us": round(t_1, 1),
-                                   "speedup": round(t_1 / t_sh, 3), "targets_per_rank": [b - a_ for a_, b in partition_targets(lvl, world)],
+        # multiply + relinearise, same protocol
+        lib.hevmx_exec(vm, asm.MULCC, 1, 0, 0)
+        lib.hevmx_ct_read(vm, 1, exp.ctypes.data_as(u64p))
+        lib.hevmx_ct_write(vm, 3, np.zeros_like(a).ctypes.data_as(u64p), lvl, 2.0 ** 40)
+        sr.mulcc(3, 0, 0, lvl)
+        sr.gather(3, lvl)
+        lib.hevmx_sync(vm)
+        lib.hevmx_ct_read(vm, 3, got.ctypes.data_as(u64p))
+        ok2 = torch.tensor([1 if np.array_equal(got, exp) else 0], device="cuda")
+        dist.all_reduce(ok2, op=dist.ReduceOp.MIN)
+        m_sh = timed(lambda: sr.mulcc(3, 0, 0, lvl))
+        m_1 = timed(lambda: lib.hevmx_exec(vm, asm.MULCC, 1, 0, 0))
+        out["levels"][str(lvl)] = {"bit_exact_vs_single_gpu": bool(ok.item()) and bool(ok2.item()),
+                                   "rotate": {"sharded_us": round(t_sh, 1), "single_gpu_us": round(t_1, 1), "speedup": round(t_1 / t_sh, 3)},
+                                   "mulcc": {"sharded_us": round(m_sh, 1), "single_gpu_us": round(m_1, 1), "speedup": round(m_1 / m_sh, 3)},
+                                   "targets_per_rank": [b - a_ for a_, b in partition_targets(lvl, world)],
                                    "allgather_bytes": lvl * N * 8, "broadcast_bytes": 2 * N * 8}
     return out

@@ -50,6 +50,9 @@ const char *hevmx_profile_read(void *vm, int cls, double *ms, int64_t *count); /
  * product for the own targets, owner of the special limb also rounds it; <broadcast rounding rows>; stage 3: mod-down
  * of the own data limbs into `dst`.  `step` must have a Galois key of its own (one key switch). */
 void hevmx_ks_shard_stage(void *vm, int stage, int64_t dst, int64_t src, int64_t step, int64_t tlo, int64_t thi);
+/* the same three stages for mulcc (multiply + relinearise): stage 1 forms d2 = a1*b1 on the own limbs, stage 3 adds the
+ * tensor-product terms d0, d1 of the own limbs; dst may alias lhs or rhs */
+void hevmx_mulcc_shard_stage(void *vm, int stage, int64_t dst, int64_t lhs, int64_t rhs, int64_t tlo, int64_t thi);
 /* device addresses for the exchanges: which 0 = coefficient digits [L][N] u64, 1 = rounding rows [2][N] u64,
  * 16 + r = limb data of ciphertext register r ([2][L-1][N] u64) */
 void *hevmx_dev_ptr(void *vm, int64_t which);

@@ -108,7 +108,7 @@ void emul_keyswitch(void *h, int mode, const u64 *a, const u64 *b, u64 *dst, int
 }
 // limb-sharded rotation key switch with `ranks` simulated ranks sharing one scratch area: every stage is run for all
 // ranks before the next one starts, which is exactly what the all-gather / broadcast between the stages provide
-void emul_keyswitch_sharded(void *h, const u64 *a, u64 *dst, int l, const u64 *key, u32 elt, int ranks) {
+void emul_keyswitch_sharded(void *h, int mode, const u64 *a, const u64 *b, u64 *dst, int l, const u64 *key, u32 elt, int ranks) {
   auto e = (Emu *)h;
   const size_t kw = (size_t)(e->P.L - 1) * 2 * e->P.L * e->P.N;
   std::vector<u64> ks(kw);
@@ -116,7 +116,7 @@ void emul_keyswitch_sharded(void *h, const u64 *a, u64 *dst, int l, const u64 *k
   for (int stage = 1; stage <= 3; stage++)
     for (int g = 0; g < ranks; g++) {
       const int tlo = (int)((long)(l + 1) * g / ranks), thi = (int)((long)(l + 1) * (g + 1) / ranks);
-      e->ops->ks_shard_stage(stage, a, dst, (size_t)l * e->P.N, l, ks.data(), elt, tlo, thi);
+      e->ops->ks_shard_stage(stage, mode, a, b, dst, (size_t)l * e->P.N, l, ks.data(), elt, tlo, thi);
     }
 }
 void emul_rescale(void *h, const u64 *src, u64 *dst, int l) {

@@ -138,6 +138,27 @@ def test_sharded_keyswitch_stages_bit_exact(pair, lvl, step, ranks):
     assert np.array_equal(g.ct_read(1), o.ct_read(1)), (lvl, step, ranks)
 
 
+@pytest.mark.parametrize("lvl,ranks,inplace", [(13, 2, False), (6, 3, True), (1, 2, False)])
+def test_sharded_mulcc_stages_bit_exact(pair, lvl, ranks, inplace):
+    """Limb-sharded multiply + relinearise (hevmx_mulcc_shard_stage) on one GPU, partitions back to back, vs the oracle."""
+    from dacapo_b200.sharded import partition_targets
+    g, o = pair
+    a, b = o.random_ct(lvl, 950 + lvl), o.random_ct(lvl, 960 + lvl)
+    for vm in pair:
+        vm.ct_write(0, a, 2.0 ** 40)
+        vm.ct_write(1, b, 2.0 ** 40)
+    dst = 0 if inplace else 2
+    o.exec(asm.MULCC, dst, 0, 1)
+    if not inplace:
+        g.ct_write(2, np.zeros_like(a), 2.0 ** 40)
+    for stage in (1, 2, 3):
+        for tlo, thi in partition_targets(lvl, ranks):
+            g.lib.hevmx_mulcc_shard_stage(g.vm, stage, dst, 0, 1, tlo, thi)
+    g.lib.hevmx_sync(g.vm)
+    assert np.array_equal(g.ct_read(dst), o.ct_read(dst)), (lvl, ranks, inplace)
+    assert g.ct_info(dst) == o.ct_info(dst)
+
+
 def test_encode_decode_bit_exact(pair):
     g, o = pair
     rng = np.random.default_rng(7)

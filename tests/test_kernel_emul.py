@@ -34,7 +34,7 @@ def emul(LOGN):
     lib.emul_ntt.argtypes = [C.c_void_p, u64p, C.c_int, C.c_int, C.c_int]
     lib.emul_keyswitch.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p, C.c_int, u64p, C.c_uint32]
     lib.emul_rescale.argtypes = [C.c_void_p, u64p, u64p, C.c_int]
-    lib.emul_keyswitch_sharded.argtypes = [C.c_void_p, u64p, u64p, C.c_int, u64p, C.c_uint32, C.c_int]
+    lib.emul_keyswitch_sharded.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p, C.c_int, u64p, C.c_uint32, C.c_int]
     return lib, lib.emul_create(LOGN, NPR, 60)
 
 
@@ -129,5 +129,24 @@ def test_sharded_rotate_kernels_vs_oracle(emul, vm, ranks):
     elt = vm.lib.hevmx_galois_elt(vm.vm, step)
     key = vm.key(3, elt)
     got = np.zeros_like(a)
-    lib.emul_keyswitch_sharded(h, _p(a), _p(got), lvl, _p(key), elt, ranks)
+    lib.emul_keyswitch_sharded(h, 1, _p(a), None, _p(got), lvl, _p(key), elt, ranks)
     assert np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize("ranks", [2, 3])
+def test_sharded_mulcc_kernels_vs_oracle(emul, vm, ranks):
+    """Limb-sharded multiply + relinearise == SEAL multiply + relinearize_inplace, also in place."""
+    lib, h = emul
+    lvl = 3
+    a, b = vm.random_ct(lvl, 21), vm.random_ct(lvl, 22)
+    vm.ct_write(0, a)
+    vm.ct_write(1, b)
+    vm.exec(asm.MULCC, 2, 0, 1)
+    exp = vm.ct_read(2)
+    key = vm.key(2)
+    got = np.zeros_like(a)
+    lib.emul_keyswitch_sharded(h, 2, _p(a), _p(b), _p(got), lvl, _p(key), 0, ranks)
+    assert np.array_equal(got, exp)
+    a2 = a.copy()
+    lib.emul_keyswitch_sharded(h, 2, _p(a2), _p(b), _p(a2), lvl, _p(key), 0, ranks)
+    assert np.array_equal(a2, exp)
