@@ -205,6 +205,7 @@ template <int LOGA, int PRE> void GpuLauncher::invA_fwdA(const ArgsInvFwdA &a, i
 INSTANTIATE(6)
 INSTANTIATE(7)
 INSTANTIATE(8)
+INSTANTIATE(9)
 
 // =====================================================================================
 // element-wise kernels.  One thread = 4 consecutive coefficients (256-bit accesses).

@@ -276,7 +276,8 @@ template <int LOGA, int PRE> HD void body_invA_fwdA(const ArgsInvFwdA &a, int jo
     u64 fix = 0;
     if (PRE == PRE_ROUND) fix = m.q - reduce64(ms.q >> 1, m);
     FOR_LANES(S, st, {
-      if (tn < tend) stage_tw_A<LOGA>(tw_fwd + Geo<LOGA>::ROWS * (buf ^ 1), T.tw + (size_t)prime_of(tn) * N, lane); // prefetch next table
+      if (Geo<LOGA>::TW_DOUBLE && tn < tend)
+        stage_tw_A<LOGA>(tw_fwd + Geo<LOGA>::ROWS * (buf ^ 1), T.tw + (size_t)prime_of(tn) * N, lane); // prefetch next table
       cp_async_commit();
       // no modular reduction needed (see body_fwd_A): x < 2^60 < 2*q_dst is a valid lazy representative
       _Pragma("unroll")
@@ -285,7 +286,15 @@ template <int LOGA, int PRE> HD void body_invA_fwdA(const ArgsInvFwdA &a, int jo
     });
     u64 *dst = (PRE == PRE_MODUP) ? a.dst + ((size_t)t * a.l + sl) * N : a.dst + ((size_t)sl * a.l + t) * N;
     warp_fwdA_from_regs<LOGA, pass_a_needs_fold<LOGA>(PRE)>(st, sm, dst, tile * Geo<LOGA>::C, tw_fwd + Geo<LOGA>::ROWS * buf, m);
-    buf ^= 1;
+    if (Geo<LOGA>::TW_DOUBLE) {
+      buf ^= 1;
+    } else if (tn < tend) { // single buffer: the next table can only be staged once this transform is done with it
+      FOR_LANES(S, st, {
+        (void)S;
+        stage_tw_A<LOGA>(tw_fwd, T.tw + (size_t)prime_of(tn) * N, lane);
+        cp_async_commit();
+      });
+    }
     t = tn;
   }
   FOR_LANES(S, st, {

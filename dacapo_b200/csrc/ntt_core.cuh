@@ -124,7 +124,7 @@ HD void stg4(u64 *p, u64 a, u64 b, u64 c, u64 d) { p[0] = a, p[1] = b, p[2] = c,
 HD int padx(int idx) { return idx + (idx >> 4); }
 #define WARP_TILE_WORDS 544  // 512 values + 512/16 padding
 
-// Ring geometry: N = 2^LOGA rows x 256 columns (LOGA = logN - 8; 6, 7, 8 <=> N = 2^14, 2^15, 2^16).
+// Ring geometry: N = 2^LOGA rows x 256 columns (LOGA = logN - 8; 6, 7, 8, 9 <=> N = 2^14 .. 2^17).
 // Pass A tile = 2^LOGA rows x C columns with 2^LOGA * C = 512 values (16 per lane).
 template <int LOGA> struct Geo {
   static constexpr int ROWS = 1 << LOGA;
@@ -132,8 +132,10 @@ template <int LOGA> struct Geo {
   static constexpr int C = 1 << LOGC;
   static constexpr int TILES = 256 / C;      // pass-A tiles per limb
   static constexpr int LOGT = 8 - LOGC;
-  // staged twiddles per warp: pass B 255; fused inverse+forward pass A: ROWS + 2 x ROWS
-  static constexpr int TW = (3 * ROWS > 256) ? 3 * ROWS : 256;
+  // staged twiddles per warp: pass B 255; fused inverse+forward pass A: ROWS + 2 x ROWS (the forward table is
+  // double-buffered up to 256 rows; at 512 rows it is single-buffered to keep two CTAs per SM)
+  static constexpr bool TW_DOUBLE = LOGA <= 8;
+  static constexpr int TW = (TW_DOUBLE ? 3 : 2) * ROWS > 256 ? (TW_DOUBLE ? 3 : 2) * ROWS : 256;
   static constexpr int WARP_WORDS = WARP_TILE_WORDS + 2 * TW;
 };
 
@@ -168,6 +170,34 @@ template <int LOGA> HD int colA(int lane) { return lane & (Geo<LOGA>::C - 1); }
 HD int idxR(int lane, int e) { return e * 32 + lane; }
 template <int LOGA> HD int idxS(int lane, int e) { return rowS<LOGA>(lane, e) * Geo<LOGA>::C + colA<LOGA>(lane); }
 
+// layout X ("middle bits", only for 512 rows x 1 column): x[e] <-> row = (lane>>1)*32 + e*2 + (lane&1), i.e. the
+// register index carries row bits 4..1.  With 9 row bits the 16 registers of layouts R (bits 8..5) and S (bits 3..0)
+// leave bit 4 uncovered; a third round in layout X does the stages with row gaps 16, 8, 4, 2.
+HD int rowX(int lane, int e) { return ((lane >> 1) << 5) | (e << 1) | (lane & 1); }
+// forward stages 4..7 of a 9-stage pass A (row gaps 16, 8, 4, 2); every stage adds 2q to the bound
+template <int LOGA> HD void fwdA_stages_X(u64 (&x)[16], int lane, const Tw *tw, u64 q, u64 q2) {
+  _Pragma("unroll")
+  for (int s = 4; s < 8; s++) {
+    const int half = 8 >> (s - 4);
+    _Pragma("unroll")
+    for (int e = 0; e < 16; e++)
+      if (!(e & half)) {
+        Tw t = ldtw(tw + (1 << s) + (rowX(lane, e) >> (LOGA - s)));
+        ct_bfly_lazy(x[e], x[e + half], t, q, q2);
+      }
+  }
+}
+// inverse: the row gap 16 (j = 4) of a 9-stage pass A; in/out < 2q
+template <int LOGA> HD void invA_stages_X(u64 (&x)[16], int lane, const Tw *itw, u64 q, u64 q2, u64 dl) {
+  const int j = 4, half = 8;
+  _Pragma("unroll")
+  for (int e = 0; e < 16; e++)
+    if (!(e & half)) {
+      Tw t = ldtw(itw + ((Geo<LOGA>::ROWS / 2) >> j) + (rowX(lane, e) >> (j + 1)));
+      gs_bfly_fold(x[e], x[e + half], t, q, q2, dl);
+    }
+}
+
 // in: < 2q   out: < 10q
 HD void fwdA_stages_R(u64 (&x)[16], const Tw *tw, u64 q, u64 q2) {
   _Pragma("unroll")
@@ -185,7 +215,7 @@ HD void fwdA_stages_R(u64 (&x)[16], const Tw *tw, u64 q, u64 q2) {
 template <int LOGA> HD void fwdA_stages_S(u64 (&x)[16], int lane, const Tw *tw, u64 q, u64 q2) {
   const int rbase = (lane >> Geo<LOGA>::LOGC) * 16;
   _Pragma("unroll")
-  for (int s = 4; s < LOGA; s++) {
+  for (int s = (LOGA > 8 ? LOGA - 1 : 4); s < LOGA; s++) { // 512 rows: stages 4..7 were done in layout X
     const int half = 1 << (LOGA - 1 - s);
     _Pragma("unroll")
     for (int e = 0; e < 16; e++)
@@ -199,7 +229,7 @@ template <int LOGA> HD void fwdA_stages_S(u64 (&x)[16], int lane, const Tw *tw, 
 template <int LOGA> HD void invA_stages_S(u64 (&x)[16], int lane, const Tw *itw, u64 q, u64 q2, u64 dl) {
   const int rbase = (lane >> Geo<LOGA>::LOGC) * 16;
   _Pragma("unroll")
-  for (int j = 0; j < LOGA - 4; j++) {
+  for (int j = 0; j < (LOGA - 4 < 4 ? LOGA - 4 : 4); j++) { // at most the four gaps 1, 2, 4, 8 fit the 16 registers
     const int half = 1 << j;
     _Pragma("unroll")
     for (int e = 0; e < 16; e++)
@@ -347,6 +377,15 @@ HD void warp_fwdA_from_regs(LaneA *st, u64 *sm, u64 *dst, int c0, const Tw *tw, 
     _Pragma("unroll")
     for (int e = 0; e < 16; e++) sm[padx(idxR(lane, e))] = FOLD ? fold60(S.y[e], dl) : S.y[e];
   });
+  if (LOGA > 8) { // 512 rows: middle round in layout X (tile index = row, one column)
+    FOR_LANES(S, st, {
+      _Pragma("unroll")
+      for (int e = 0; e < 16; e++) S.y[e] = sm[padx(rowX(lane, e))];
+      fwdA_stages_X<LOGA>(S.y, lane, tw, q, q2);
+      _Pragma("unroll")
+      for (int e = 0; e < 16; e++) sm[padx(rowX(lane, e))] = S.y[e];
+    });
+  }
   FOR_LANES(S, st, {
     u64 *dstS = dst + ((size_t)rowS<LOGA>(lane, 0) << 8) + c0 + colA<LOGA>(lane);
     _Pragma("unroll")
@@ -370,6 +409,15 @@ HD void warp_invA_to_regs(LaneA *st, u64 *sm, const u64 *src, int c0, const Tw *
     _Pragma("unroll")
     for (int e = 0; e < 16; e++) sm[padx(idxS<LOGA>(lane, e))] = S.x[e];
   });
+  if (LOGA > 8) {
+    FOR_LANES(S, st, {
+      _Pragma("unroll")
+      for (int e = 0; e < 16; e++) S.x[e] = sm[padx(rowX(lane, e))];
+      invA_stages_X<LOGA>(S.x, lane, itw, q, q2, dl);
+      _Pragma("unroll")
+      for (int e = 0; e < 16; e++) sm[padx(rowX(lane, e))] = S.x[e];
+    });
+  }
   FOR_LANES(S, st, {
     _Pragma("unroll")
     for (int e = 0; e < 16; e++) S.x[e] = sm[padx(idxR(lane, e))];

@@ -243,6 +243,7 @@ template <class LA> OpsIface *make_ops(LA &la, const NttTables *tab, int logN, i
   case 14: return new HeOps<LA, 6>(la, tab, nprimes);
   case 15: return new HeOps<LA, 7>(la, tab, nprimes);
   case 16: return new HeOps<LA, 8>(la, tab, nprimes);
+  case 17: return new HeOps<LA, 9>(la, tab, nprimes);
   }
   return nullptr;
 }

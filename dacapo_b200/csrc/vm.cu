@@ -131,7 +131,7 @@ struct VM {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) die("no CUDA device visible: libB200_HEVM.so has no CPU path");
     if (const char *e = std::getenv("HEVM_DEVICE")) CUDA_CHECK(cudaSetDevice(std::atoi(e)));
-    if (pf.logN < 14 || pf.logN > 16) die("supported ring sizes: N = 2^14, 2^15, 2^16 (HEVM_LOGN = 14..16)");
+    if (pf.logN < 14 || pf.logN > 17) die("supported ring sizes: N = 2^14 .. 2^17 (HEVM_LOGN = 14..17)");
     if (pf.L < 2 || pf.L > HEVM_MAXL) die("number of primes out of range");
     logN = (int)pf.logN, L = (int)pf.L, N = (size_t)1 << logN, seed = pf.seed;
     pitch = (size_t)(L - 1) * N;

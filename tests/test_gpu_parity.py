@@ -426,7 +426,7 @@ def test_scheduler_random_program_bit_exact(pair, tmp_path, seed):
         vm.lib.hevmx_resize(vm.vm, 8, 4)
 
 
-@pytest.mark.parametrize("logn,npr", [(14, 5), (16, 6)])
+@pytest.mark.parametrize("logn,npr", [(14, 5), (16, 6), (17, 4)])
 def test_other_ring_sizes_bit_exact(oracle_lib, b200_lib, tmp_path_factory, logn, npr):
     """N is a run-time parameter: same kernels with 64 / 256 rows x 256 columns."""
     d = str(tmp_path_factory.mktemp(f"keys{logn}"))

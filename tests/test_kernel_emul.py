@@ -18,7 +18,7 @@ u64p = C.POINTER(C.c_uint64)
 NPR = 4
 
 
-@pytest.fixture(scope="module", params=[15, 14, 16])
+@pytest.fixture(scope="module", params=[15, 14, 16, 17])
 def LOGN(request):
     return request.param
 
