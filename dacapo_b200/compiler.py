@@ -73,6 +73,10 @@ class Options:
     plain_bits: int = 40       # default scale of a plaintext factor (encoding error ~ sqrt(N/12) / 2^bits per slot)
     min_plain_bits: int = 30   # smallest scale a plaintext factor is encoded at
     waist_bootstrap: bool = True  # place bootstraps at single-ciphertext program points, sized to the next segment
+    # per-op latency table (microseconds, index = level - 1) in the schema of profiled_B200_GPU.json / EarthDialect.cpp:130-180
+    # ("latencyTableExact" or "latencyTable"); when given, the level a placed bootstrap returns to is the one that
+    # minimises the estimated latency of the segment it feeds (DaCapo's objective), not merely the lowest feasible one
+    cost_table: dict = None
     fold_tolerance: float = 0.0
 
 
@@ -106,6 +110,26 @@ class Compiler:
         self.cse = {}
         self.min_level_seen = self.top
         self.greedy_forbidden = False
+        self.est_us = 0.0                   # running latency estimate of the emitted ops (cost_table)
+
+    # ---- latency model ---------------------------------------------------------------------------
+    _COST_KEY = {"rotate": "earth.rotate_single", "mulcc": "earth.mul_double", "mulcp": "earth.mul_single",
+                 "addcc": "earth.add_double", "addcp": "earth.add_single", "rescale": "earth.rescale_single",
+                 "modswitch": "earth.modswitch_single", "negate": "earth.negate_single", "bootstrap": "earth.bootstrap_single"}
+
+    def op_cost(self, name, imm, level):
+        """Estimated microseconds of one lowered op whose RESULT is at `level`."""
+        t = self.o.cost_table
+        if not t or name not in self._COST_KEY:
+            return 0.0
+        row = t.get(self._COST_KEY[name]) or [0.0]
+        src = level + 1 if name == "rescale" else level + imm if name == "modswitch" else imm if name == "bootstrap" else level
+        c = row[min(max(src, 1), len(row)) - 1]
+        if name == "rotate":  # SEAL rotates by NAF terms unless the step has a key of its own (a power of two)
+            k = imm % self.slots
+            k = min(k, self.slots - k)
+            c *= max(1, bin(k).count("1") if k & (k - 1) else 1) if k else 0.05
+        return c
 
     # ---- constants -------------------------------------------------------------------------------
     def tile(self, a):
@@ -149,6 +173,8 @@ class Compiler:
         self.nssa += 1
         self.ops.append((name, dst, tuple(srcs), imm))
         self.stats[name] = self.stats.get(name, 0) + 1
+        if level is not None:
+            self.est_us += self.op_cost(name, imm, level)
         return _Ct(dst, level, scale)
 
     def valid(self, level, bits):
@@ -304,10 +330,10 @@ class Compiler:
 
     def _snapshot(self):
         return (len(self.ops), self.nssa, dict(self.stats), dict(self.cse), dict(self.encodes), dict(self.vals),
-                len(self.pool), dict(self.pool_key), self.min_level_seen)
+                len(self.pool), dict(self.pool_key), self.min_level_seen, self.est_us)
 
     def _restore(self, snap):
-        nops, self.nssa, stats, cse, encodes, vals, npool, pool_key, self.min_level_seen = snap
+        nops, self.nssa, stats, cse, encodes, vals, npool, pool_key, self.min_level_seen, self.est_us = snap
         # copies: a snapshot may be restored several times and must stay pristine
         self.stats, self.cse, self.encodes, self.vals, self.pool_key = dict(stats), dict(cse), dict(encodes), dict(vals), dict(pool_key)
         del self.ops[nops:]
@@ -395,8 +421,9 @@ class Compiler:
                 v = self.vals[i]
                 snap = self._snapshot()
 
-                def boots_with(target):
+                def boots_with(target, latency=False):
                     self._restore(snap)
+                    t0 = self.est_us
                     self.vals[i] = self.bootstrap(v, target)
                     b0 = self.stats.get("bootstrap", 0)
                     for j in seg:
@@ -406,8 +433,30 @@ class Compiler:
                             self.normalize(self.vals[o_])
                     else:
                         self.bootstrap(self.vals[stop], self.top)  # the next placed bootstrap must still be possible
-                    return self.stats.get("bootstrap", 0) - b0
+                    return self.est_us - t0 if latency else self.stats.get("bootstrap", 0) - b0
 
+                if self.o.cost_table:
+                    # latency-driven: try every level, keep the cheapest feasible one (extra in-segment bootstraps are
+                    # allowed when the cheaper low-level ops pay for them)
+                    best_t, best_c = self.top, None
+                    saved_bt = self.o.boot_target
+                    for tgt in range(self.top, 1, -1):
+                        try:
+                            self.o.boot_target = tgt  # in-segment bootstraps return to the same level
+                            c_ = boots_with(tgt, latency=True)
+                        except (RuntimeError, _NeedBootstrap):
+                            continue
+                        finally:
+                            self.o.boot_target = saved_bt
+                        if best_c is None or c_ < best_c - 1e-9:
+                            best_t, best_c = tgt, c_
+                    self._restore(snap)
+                    self.seg_targets = getattr(self, "seg_targets", {})
+                    self.seg_targets[i] = best_t
+                    self.o.boot_target = best_t
+                    self.vals[i] = self.bootstrap(v, best_t)
+                    k += 1
+                    continue
                 try:
                     base = boots_with(self.top)
                     lo, hi = 2, self.top

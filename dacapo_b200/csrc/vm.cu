@@ -408,6 +408,7 @@ struct VM {
     d.level = s.level, d.scale = s.scale;
   }
   u64 boot_index = 0; // encryptions issued so far inside the current run()
+  double shard_scale = 0; // hevmx_mulcc_shard_stage: result scale computed at stage 1
   bool meta_only = false; // exec() of addcc / mulcp updates register metadata only (their kernels were fused by the scheduler)
   void exec(const HevmOp &op) {
     switch (op.opcode) {
@@ -1073,10 +1074,10 @@ void hevmx_mulcc_shard_stage(void *h, int stage, int64_t dst, int64_t lhs, int64
   if (a.level != b.level || a.level < 1) die("mulcc_shard: level mismatch");
   if (tlo < 0 || thi > a.level + 1 || tlo > thi) die("mulcc_shard: bad target range");
   const int l = a.level;
-  static double sc = 0; // product scale, fixed at stage 1: dst may alias an operand, and stage 3 may run once per owned range
-  if (stage == 1) sc = a.scale * b.scale;
+  // product scale, fixed at stage 1: dst may alias an operand, and stage 3 may run once per owned range
+  if (stage == 1) vm->shard_scale = a.scale * b.scale;
   vm->ln->ops->ks_shard_stage(stage, LD_PRODUCT, a.d, b.d, d.d, vm->pitch, l, vm->d_relin, 0, (int)tlo, (int)thi);
-  if (stage == 3) d.level = l, d.scale = sc;
+  if (stage == 3) d.level = l, d.scale = vm->shard_scale;
 }
 void *hevmx_dev_ptr(void *h, int64_t which) {
   VM *vm = V(h);

@@ -46,7 +46,9 @@ def main():
     graph = g["modName"]  # frontend.save() returns the recorded Graph
     print(f"traced {len(graph.nodes)} nodes, {len(graph.consts)} constants in {time.time() - t0:.1f}s")
 
-    prog, c = compiler.compile_graph(graph, compiler.Options(logN=15, num_primes=14, waterline=40))
+    # bootstrap levels are chosen against the measured B200 cost profile (profiled_B200_GPU.json at the repo root)
+    cost = json.loads((REPO / "profiled_B200_GPU.json").read_text())["latencyTableExact"]
+    prog, c = compiler.compile_graph(graph, compiler.Options(logN=15, num_primes=14, waterline=40, cost_table=cost))
     print("lowered ops:", c.stats, "ct regs", prog.num_ct, "pt regs", prog.num_pt, "pool", len(prog.constants))
     (out / "resnet20.hevm").write_bytes(prog.hevm_bytes())
     raw = prog.cst_bytes()
