@@ -448,6 +448,73 @@ __global__ void k_fft_ct(int logN, double2 *v, const double2 *roots, int m, int 
     v[off + gap] = csubc(u, w);
   }
 }
+// Up to four consecutive radix-2 stages per launch: a thread owns the 2^K points  base + t * gap_lo  (t < 2^K) that
+// are closed under the stages with gaps gap_lo .. gap_lo * 2^(K-1), keeps them in registers and performs exactly the
+// butterflies of k_fft_gs / k_fft_ct on them, in the same order per point -- so every intermediate value is the same
+// fp64 number and the results stay bit-identical to the stage-by-stage kernels (and to SEAL's loops), with a quarter of
+// the launches and memory passes.
+template <int K, bool GS> __global__ void k_fft_multi(int logN, double2 *v, const double2 *roots, int gap_lo, double fix, int has_last) {
+  constexpr int P = 1 << K;
+  const size_t n = (size_t)1 << logN, sets = n >> K;
+  for (size_t sidx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; sidx < sets; sidx += (size_t)gridDim.x * blockDim.x) {
+    const size_t lo = sidx % (size_t)gap_lo, hi = sidx / (size_t)gap_lo;
+    const size_t base = hi * ((size_t)gap_lo << K) + lo;
+    double2 x[P];
+#pragma unroll
+    for (int t = 0; t < P; t++) x[t] = v[base + (size_t)t * gap_lo];
+#pragma unroll
+    for (int st = 0; st < K; st++) {
+      const int half = GS ? (1 << st) : (P >> 1 >> st);   // register distance of the stage
+      const size_t gap = (size_t)gap_lo * half;            // its distance in the array
+      const size_t m = n / (2 * gap);
+#pragma unroll
+      for (int t = 0; t < P; t++)
+        if (!(t & half)) {
+          const size_t off = base + (size_t)t * gap_lo, g = off / (2 * gap);
+          if (GS) {
+            const double2 r = roots[(n - 2 * m) + 1 + g];
+            const double2 u = x[t], w = x[t + half];
+            if (has_last && m == 1) {
+              const double2 sr = make_double2(__dmul_rn(r.x, fix), __dmul_rn(r.y, fix));
+              const double2 sm_ = cadd(u, w);
+              x[t] = make_double2(__dmul_rn(sm_.x, fix), __dmul_rn(sm_.y, fix));
+              x[t + half] = cmul(csubc(u, w), sr);
+            } else {
+              x[t] = cadd(u, w);
+              x[t + half] = cmul(csubc(u, w), r);
+            }
+          } else {
+            const double2 r = roots[m + g];
+            const double2 u = x[t], w = cmul(x[t + half], r);
+            x[t] = cadd(u, w);
+            x[t + half] = csubc(u, w);
+          }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < P; t++) v[base + (size_t)t * gap_lo] = x[t];
+  }
+}
+// all logN stages: groups of four (the remainder group first for GS -- smallest gaps --, last for CT)
+template <bool GS> static void launch_fft_all(cudaStream_t s, int logN, double2 *work, const double2 *roots, double fix) {
+  const size_t n = (size_t)1 << logN;
+  int done = 0;
+  while (done < logN) {
+    const int k = (logN - done >= 4) ? 4 : logN - done;
+    // GS walks gaps 1, 2, 4, ... upward; CT walks gaps n/2, n/4, ... downward
+    const int gap_lo = GS ? (1 << done) : (int)(n >> (done + k));
+    const size_t sets = n >> k;
+    const int has_last = GS && done + k == logN;
+    switch (k) {
+    case 4: k_fft_multi<4, GS><<<ew_grid(sets), 256, 0, s>>>(logN, work, roots, gap_lo, fix, has_last); break;
+    case 3: k_fft_multi<3, GS><<<ew_grid(sets), 256, 0, s>>>(logN, work, roots, gap_lo, fix, has_last); break;
+    case 2: k_fft_multi<2, GS><<<ew_grid(sets), 256, 0, s>>>(logN, work, roots, gap_lo, fix, has_last); break;
+    default: k_fft_multi<1, GS><<<ew_grid(sets), 256, 0, s>>>(logN, work, roots, gap_lo, fix, has_last); break;
+    }
+    POST_LAUNCH_S(s);
+    done += k;
+  }
+}
 __global__ void k_enc_max(int logN, const double2 *work, unsigned long long *maxbits) {
   const size_t n = (size_t)1 << logN;
   double mx = 0.0;
@@ -496,11 +563,7 @@ void launch_encode(cudaStream_t s, const NttTables *T, const EncoderTables &E, i
   k_enc_scatter<<<ew_grid(n / 2), 256, 0, s>>>(logN, vals, len, E.slot_index, work, maxbits);
   POST_LAUNCH_S(s);
   const double fix = scale / (double)n;
-  int gap = 1;
-  for (size_t m = n >> 1; m >= 1; m >>= 1, gap <<= 1) {
-    k_fft_gs<<<ew_grid(n / 2), 256, 0, s>>>(logN, work, E.inv_root, (int)m, gap, fix, m == 1);
-    POST_LAUNCH_S(s);
-  }
+  launch_fft_all<true>(s, logN, work, E.inv_root, fix);
   k_enc_max<<<ew_grid(n), 256, 0, s>>>(logN, work, maxbits);
   POST_LAUNCH_S(s);
   k_enc_round<<<ew_grid(n), 256, 0, s>>>(T, logN, level, work, maxbits, out);
@@ -602,11 +665,7 @@ void launch_decode(cudaStream_t s, const NttTables *T, const EncoderTables &E, c
   }
   k_dec_compose<<<ew_grid(n), 256, 0, s>>>(T, logN, l, coeff, D, 1.0 / scale, work);
   POST_LAUNCH_S(s);
-  int gap = (int)(n >> 1);
-  for (size_t m = 1; m < n; m <<= 1, gap >>= 1) {
-    k_fft_ct<<<ew_grid(n / 2), 256, 0, s>>>(logN, work, E.fwd_root, (int)m, gap);
-    POST_LAUNCH_S(s);
-  }
+  launch_fft_all<false>(s, logN, work, E.fwd_root, 0.0);
   k_dec_gather<<<ew_grid(n / 2), 256, 0, s>>>(logN, work, E.slot_index, out);
   POST_LAUNCH_S(s);
 }

@@ -542,7 +542,7 @@ struct VM {
     if (home.size() != ct.size()) {
       home.resize(ct.size());
       for (size_t r = 0; r < ct.size(); r++) home[r] = ct[r].d;
-      int nspare = 48;
+      int nspare = 128; // 0.9 GB at N = 2^15: enough for every false dependency of the ResNet-20 program to disappear
       if (const char *e = std::getenv("HEVM_RENAME_POOL")) nspare = std::max(0, std::atoi(e));
       if (lanes.size() == 1) nspare = 0; // nothing to overlap
       while ((int)spare.size() < nspare) spare.push_back(dalloc<u64>(2 * pitch));
