@@ -55,6 +55,17 @@ def main():
     (out / "resnet20.cst.xz").write_bytes(lzma.compress(raw, preset=6))
     print("cst raw MB", len(raw) / 1e6, "xz MB", (out / "resnet20.cst.xz").stat().st_size / 1e6)
 
+    # waterline sweep (BASELINE.json configs[3]): same graph, same constant pool, other scale-management waterlines
+    sweep = {}
+    for W in (30, 35, 45, 50):
+        pw, cw = compiler.compile_graph(graph, compiler.Options(logN=15, num_primes=14, waterline=W, cost_table=cost))
+        if pw.cst_bytes() != raw:
+            print(f"waterline {W}: constant pool differs, skipped")
+            continue
+        (out / f"resnet20_w{W}.hevm").write_bytes(pw.hevm_bytes())
+        sweep[str(W)] = {"lowered_ops": cw.stats, "hevm_ops": len(pw.ops)}
+        print(f"waterline {W}:", cw.stats)
+
     # seeded synthetic input, plaintext reference and packing -- with the reference's own code
     model = g["getModel"]()
     torch.manual_seed(1)
@@ -68,7 +79,8 @@ def main():
     np.save(out / "input.npy", packed)
     np.save(out / "expected.npy", logits)
     meta = {"post_scale": 32.0, "n_out": 10, "lowered_ops": c.stats, "traced_nodes": len(graph.nodes),
-            "ct_registers": prog.num_ct, "pt_registers": prog.num_pt, "hevm_ops": len(prog.ops),
+            "ct_registers": prog.num_ct, "pt_registers": prog.num_pt, "hevm_ops": len(prog.ops), "waterline": 40,
+            "waterline_sweep": sweep,
             "source": "examples/benchmarks/ResNet.py (nt=2^14) traced with dacapo_b200.frontend, compiled with dacapo_b200.compiler",
             "weights": "examples/data/resnet20.silu.model", "input": "torch.manual_seed(1); randn(1,3,32,32).clamp(-2,2)"}
     (out / "meta.json").write_text(json.dumps(meta, indent=1))

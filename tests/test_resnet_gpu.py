@@ -16,8 +16,11 @@ from util import make_vm
 pytestmark = pytest.mark.gpu
 
 
-def test_encrypted_resnet20_matches_plaintext_model(b200_lib, tmp_path):
+@pytest.mark.parametrize("waterline", [40, 35, 50])
+def test_encrypted_resnet20_matches_plaintext_model(b200_lib, tmp_path, waterline):
     cst, hv, x, expected, meta = fixtures.resnet20_files(tmp_path)
+    if waterline != 40:  # waterline sweep programs share the constant pool (tests/golden/make_resnet_fixture.py)
+        hv = str(fixtures.FIXTURE / f"resnet20_w{waterline}.hevm")
     lib = b200_lib
     vm, _ = make_vm(lib, 15, 14)
     lib.load(vm, cst.encode(), hv.encode())
@@ -34,6 +37,6 @@ def test_encrypted_resnet20_matches_plaintext_model(b200_lib, tmp_path):
     res = out[:meta["n_out"]] * meta["post_scale"]
     err = res - expected
     rms = float(np.sqrt(np.sum(err * err) / res.shape[-1]))
-    print(f"encrypted ResNet-20: run() {latency:.3f}s rms {rms:.3e} argmax {int(np.argmax(res))} vs {int(np.argmax(expected))}")
+    print(f"encrypted ResNet-20 (waterline {waterline}): run() {latency:.3f}s rms {rms:.3e} argmax {int(np.argmax(res))} vs {int(np.argmax(expected))}")
     assert np.argmax(res) == np.argmax(expected)
     assert rms < 5e-3, rms
