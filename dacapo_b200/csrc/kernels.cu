@@ -419,40 +419,12 @@ __global__ void k_enc_scatter(int logN, const double *vals, int len, const u32 *
     work[slot_index[slots + i]] = make_double2(v, -0.0);
   }
 }
-// Gentleman-Sande stage with m groups of gap = n/(2m); roots consumed at index (n - 2m) + 1 + group
-__global__ void k_fft_gs(int logN, double2 *v, const double2 *roots, int m, int gap, double fix, int last) {
-  const size_t half = (size_t)1 << (logN - 1), n = half * 2;
-  for (size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x; b < half; b += (size_t)gridDim.x * blockDim.x) {
-    const size_t g = b / gap, j = b - g * gap, off = 2 * g * gap + j;
-    const double2 r = roots[(n - 2 * (size_t)m) + 1 + g];
-    const double2 u = v[off], w = v[off + gap];
-    if (!last) {
-      v[off] = cadd(u, w);
-      v[off + gap] = cmul(csubc(u, w), r);
-    } else {
-      const double2 sr = make_double2(__dmul_rn(r.x, fix), __dmul_rn(r.y, fix));
-      const double2 s = cadd(u, w);
-      v[off] = make_double2(__dmul_rn(s.x, fix), __dmul_rn(s.y, fix));
-      v[off + gap] = cmul(csubc(u, w), sr);
-    }
-  }
-}
-// Cooley-Tukey stage with m groups; root index m + group
-__global__ void k_fft_ct(int logN, double2 *v, const double2 *roots, int m, int gap) {
-  const size_t half = (size_t)1 << (logN - 1);
-  for (size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x; b < half; b += (size_t)gridDim.x * blockDim.x) {
-    const size_t g = b / gap, j = b - g * gap, off = 2 * g * gap + j;
-    const double2 r = roots[(size_t)m + g];
-    const double2 u = v[off], w = cmul(v[off + gap], r);
-    v[off] = cadd(u, w);
-    v[off + gap] = csubc(u, w);
-  }
-}
 // Up to four consecutive radix-2 stages per launch: a thread owns the 2^K points  base + t * gap_lo  (t < 2^K) that
 // are closed under the stages with gaps gap_lo .. gap_lo * 2^(K-1), keeps them in registers and performs exactly the
-// butterflies of k_fft_gs / k_fft_ct on them, in the same order per point -- so every intermediate value is the same
-// fp64 number and the results stay bit-identical to the stage-by-stage kernels (and to SEAL's loops), with a quarter of
-// the launches and memory passes.
+// butterflies of SEAL's stage-by-stage loops on them (Gentleman-Sande with m groups of gap n/(2m), roots consumed at
+// index (n - 2m) + 1 + group; Cooley-Tukey with root index m + group), in the same order per point -- so every
+// intermediate value is the same fp64 number and the results stay bit-identical, with a quarter of the launches and
+// memory passes of one kernel per stage.
 template <int K, bool GS> __global__ void k_fft_multi(int logN, double2 *v, const double2 *roots, int gap_lo, double fix, int has_last) {
   constexpr int P = 1 << K;
   const size_t n = (size_t)1 << logN, sets = n >> K;

@@ -340,17 +340,6 @@ template <int LOGA> HD void body_mac_stage(const ArgsFwdB &a, int job, int tid, 
   const int N = 1 << T.logN;
   const int r = job & (Geo<LOGA>::ROWS - 1), Iidx = mac_Iidx<LOGA>(a, job), I = (Iidx == a.l) ? a.sp : Iidx;
   grid_dep_launch();
-#ifndef MAC_PREFETCH
-#define MAC_PREFETCH 0
-#endif
-  if (MAC_PREFETCH == 1) { // the CTA's key rows (constant data) start moving HBM -> L2 now; phase 2 then sees L2 latency only
-    for (int line = tid; line < 2 * a.l * 16; line += MAC_WARPS * 32) {
-      const int JK = line >> 4;
-      prefetch_l2_line(a.key + ((size_t)JK * a.Ltot + I) * N + r * 256 + (line & 15) * 16);
-    }
-  } else if (MAC_PREFETCH == 2) {
-    if (tid < 2 * a.l) prefetch_l2_bulk(a.key + ((size_t)tid * a.Ltot + I) * N + r * 256, 2048);
-  }
   stage_tw_B<LOGA>(tw_s, T.tw + (size_t)I * N, r, tid, MAC_WARPS * 32);
   grid_dep_wait();
   cp_async_wait();

@@ -62,11 +62,6 @@ HD void cp_async16_cg(void *smem_dst, const void *gsrc) { // L2-only (coherent w
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
 }
-// bulk L2 prefetch of `bytes` (multiple of 16) contiguous bytes: one instruction per row, no registers, no smem
-HD void prefetch_l2_bulk(const void *gsrc, unsigned bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
-}
-HD void prefetch_l2_line(const void *gsrc) { asm volatile("prefetch.global.L2 [%0];" ::"l"(gsrc)); }
 HD void cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 HD void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 HD void cp_async_wait_keep1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); } // all but the newest group
@@ -108,8 +103,6 @@ HD void stg4(u64 *p, u64 a, u64 b, u64 c, u64 d) {
 HD Tw ldtw(const Tw *p) { return *p; }
 HD void cp_async16(void *smem_dst, const void *gsrc) { *(Tw *)smem_dst = *(const Tw *)gsrc; }
 HD void cp_async16_cg(void *smem_dst, const void *gsrc) { *(Tw *)smem_dst = *(const Tw *)gsrc; }
-HD void prefetch_l2_bulk(const void *, unsigned) {}
-HD void prefetch_l2_line(const void *) {}
 HD void cp_async_wait() {}
 HD void cp_async_commit() {}
 HD void cp_async_wait_keep1() {}
