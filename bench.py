@@ -490,6 +490,21 @@ def main():
         line["op_roofline_l13"] = {op: {"us": table[op][13], "frac": profile.algorithmic_bytes(op, 13) / (table[op][13] * 1e-6) / 1e9 / peak}
                                    for op in ("rotate", "mulcc", "rescale", "addcc", "mulcp")}
 
+    if rank == 0 and world == 1 and not args.no_op_table:
+        # stand-alone NTT / INTT throughput on device-resident limbs (metric row "NTT/INTT ops/s vs HBM roofline"):
+        # 182 limbs (one launch pair) under each of the 13 data primes = 2 366 limbs = 620 MB per pass; algorithmic bytes
+        # 2 x 8N per limb
+        nb, npr = NPRIMES * (NPRIMES - 1), TOP
+        ntt = {}
+        for name, inv in (("ntt", 0), ("intt", 1)):
+            ms_pass = lib.hevmx_ntt_bench(vm, nb, npr, inv, 5)
+            rate = nb * npr / (ms_pass * 1e-3)
+            ntt[name] = {"limb_transforms_per_s": rate, "us_per_limb": 1e6 / rate, "achieved_GBps": rate * 2 * BYTES_LIMB / 1e9,
+                         "frac_of_hbm_peak": rate * 2 * BYTES_LIMB / 1e9 / peak,
+                         "frac_of_integer_pipe_ceiling": rate * 0.236e-6}
+        ntt["note"] = ("N = 2^15 limbs, in place, canonical in/out; the integer-pipe ceiling is 0.236 us per limb "
+                       "(tools/pipe_bench.cu, DESIGN.md section 3), the HBM roofline 0.080 us")
+        line["ntt"] = ntt
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         subprocess.run(["make", "-s", "-C", str(REPO / "oracle")], check=True)
         kd = tempfile.mkdtemp(prefix="hevm_cpu_keys_")

@@ -23,7 +23,7 @@ EXT_SYMBOLS = [
     "hevmx_set_enc_counter", "hevmx_key_read", "hevmx_galois_elt", "hevmx_backend",
 ]
 
-B200_ONLY_SYMBOLS = ["hevmx_timer", "hevmx_profile", "hevmx_profile_read", "hevmx_profiler_range",
+B200_ONLY_SYMBOLS = ["hevmx_ntt_bench", "hevmx_timer", "hevmx_profile", "hevmx_profile_read", "hevmx_profiler_range",
                      "hevmx_ks_shard_stage", "hevmx_mulcc_shard_stage", "hevmx_dev_ptr", "hevmx_stream"]
 
 _u64p = C.POINTER(C.c_uint64)
@@ -90,6 +90,8 @@ def bind(path):
     lw.hevmx_backend.argtypes = []
     lw.hevmx_backend.restype = C.c_char_p
     if hasattr(lw, "hevmx_timer"):  # libB200_HEVM.so only
+        lw.hevmx_ntt_bench.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int64]
+        lw.hevmx_ntt_bench.restype = C.c_double
         lw.hevmx_timer.argtypes = [C.c_void_p, C.c_int]
         lw.hevmx_timer.restype = C.c_double
         lw.hevmx_profile.argtypes = [C.c_void_p, C.c_int]

@@ -998,6 +998,39 @@ void hevmx_ntt(void *h, uint64_t *data, int64_t prime_idx, int64_t count, int in
   CUDA_CHECK(cudaStreamSynchronize(vm->ln->stream));
   CUDA_CHECK(cudaFree(d));
 }
+// device-resident NTT throughput: `batch` limbs under each of the first `nprimes` primes, transformed in place `reps`
+// times (forward or inverse); returns the average milliseconds of one pass over all batch * nprimes limbs
+double hevmx_ntt_bench(void *h, int64_t batch, int64_t nprimes, int inverse, int64_t reps) {
+  VM *vm = V(h);
+  vm->ln = &vm->lanes[0];
+  if (nprimes < 1 || nprimes > vm->L || batch < 1) die("ntt_bench: bad arguments");
+  const size_t w = (size_t)batch * nprimes * vm->N;
+  u64 *d = dalloc<u64>(w);
+  CUDA_CHECK(cudaMemsetAsync(d, 0x11, w * 8, vm->ln->stream)); // 0x1111... < q: valid residues
+  auto pass = [&] {
+    for (int64_t i = 0; i < nprimes; i++) {
+      u64 *p = d + (size_t)i * batch * vm->N;
+      if (inverse)
+        vm->ln->ops->ntt_inv(p, p, (int)batch, (int)i, 0);
+      else
+        vm->ln->ops->ntt_fwd(p, p, (int)batch, (int)i, 0);
+    }
+  };
+  pass();
+  cudaEvent_t a, b;
+  CUDA_CHECK(cudaEventCreate(&a));
+  CUDA_CHECK(cudaEventCreate(&b));
+  CUDA_CHECK(cudaEventRecord(a, vm->ln->stream));
+  for (int64_t r = 0; r < reps; r++) pass();
+  CUDA_CHECK(cudaEventRecord(b, vm->ln->stream));
+  CUDA_CHECK(cudaEventSynchronize(b));
+  float ms = 0;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+  CUDA_CHECK(cudaEventDestroy(a));
+  CUDA_CHECK(cudaEventDestroy(b));
+  CUDA_CHECK(cudaFree(d));
+  return (double)ms / (double)reps;
+}
 void hevmx_encode(void *h, int64_t ptreg, const double *vals, int64_t len, int64_t level, int64_t scale_bits) {
   VM *vm = V(h);
   vm->stage_host_values(vals, (size_t)len);

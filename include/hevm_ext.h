@@ -40,6 +40,8 @@ int64_t hevmx_key_read(void *vm, int which, uint64_t elt, uint64_t *out);
 int64_t hevmx_galois_elt(void *vm, int64_t step);
 const char *hevmx_backend(void);
 /* --- libB200_HEVM.so only (measurement; not part of the oracle) --- */
+/* device-resident NTT throughput: batch limbs under each of the first nprimes primes, in place; returns ms per pass */
+double hevmx_ntt_bench(void *vm, int64_t batch, int64_t nprimes, int inverse, int64_t reps);
 double hevmx_timer(void *vm, int which);        /* CUDA events on the VM stream: 0 start, 1 stop -> ms */
 void hevmx_profiler_range(void *vm, int on);  /* cudaProfilerStart/Stop (ncu --profile-from-start off) */
 void hevmx_profile(void *vm, int on);           /* per-kernel-class CUDA-event timing */
