@@ -77,6 +77,7 @@ class Options:
     # ("latencyTableExact" or "latencyTable"); when given, the level a placed bootstrap returns to is the one that
     # minimises the estimated latency of the segment it feeds (DaCapo's objective), not merely the lowest feasible one
     cost_table: dict = None
+    split_rotations: bool = True  # emit composite rotations as their NAF single-key steps (shared prefixes are CSE'd)
     fold_tolerance: float = 0.0
 
 
@@ -130,6 +131,18 @@ class Compiler:
             k = min(k, self.slots - k)
             c *= max(1, bin(k).count("1") if k & (k - 1) else 1) if k else 0.05
         return c
+
+    def naf_terms(self, step):
+        """Non-adjacent form of a rotation step (SEAL util::naf order: increasing powers of two); a power of two is a
+        single term.  Terms of +-slots are whole turns and are dropped like the runtime does."""
+        sign, v, out, i = (-1 if step < 0 else 1), abs(step), [], 0
+        while v:
+            z = 2 - (v & 3) if v & 1 else 0
+            v = (v - z) >> 1
+            if z and (1 << i) != self.slots:
+                out.append(sign * z * (1 << i))
+            i += 1
+        return out
 
     # ---- constants -------------------------------------------------------------------------------
     def tile(self, a):
@@ -305,7 +318,14 @@ class Compiler:
                 vals[i] = a
             else:
                 off = ((off + self.slots // 2) % self.slots) - self.slots // 2  # into [-slots/2, slots/2)
-                vals[i] = self.emit("rotate", [a.ssa], off, a.level, a.scale)
+                # A step without a Galois key of its own is executed by the runtime as SEAL's rotate_internal does: one
+                # key switch per NAF term, least significant first (Evaluator::rotate_internal, SEAL_HEVM.cpp:273).
+                # Emitting those single-key steps explicitly yields the same ciphertext bit for bit and lets the CSE
+                # share common prefixes between the many rotations of one value (convolution taps).
+                v = a
+                for term in (self.naf_terms(off) if self.o.split_rotations else [off]):
+                    v = self.emit("rotate", [v.ssa], term, v.level, v.scale)
+                vals[i] = v
         else:
             a, b = vals[n[1]], vals[n[2]]
             pa, pb = isinstance(a, int), isinstance(b, int)
