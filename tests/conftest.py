@@ -23,5 +23,6 @@ def oracle_lib():
 
 @pytest.fixture(scope="session")
 def b200_lib():
+    import os
     from dacapo_b200 import _binding
-    return _binding.bind(_binding.B200_LIB)
+    return _binding.bind(os.environ.get("HEVM_LIB", _binding.B200_LIB))  # HEVM_LIB: A/B builds of the same library
