@@ -160,3 +160,33 @@ def reset():
     global _G
     _G = Graph()
     _FUNCS.clear()
+
+
+def evaluate(graph: Graph, inputs, nslots: int):
+    """Plaintext semantics of a traced graph on slot vectors (the functional reference of a compiled program):
+    inputs and constants are tiled `src[i % len]` over the `nslots` slots, as the runtime's `encrypt` and `preprocess`
+    both do through `encode_internal` (SEAL_HEVM.cpp:256-261, 439-445); `rot` rotates left.  Returns one vector per
+    graph output."""
+    vals = {}
+    for i, n in enumerate(graph.nodes):
+        k = n[0]
+        if k == "input":
+            v = np.resize(np.asarray(inputs[n[1]], dtype=np.float64).ravel(), nslots)
+        elif k == "const":
+            v = np.resize(np.asarray(graph.consts[n[1]], dtype=np.float64).ravel(), nslots)
+        elif k == "add":
+            v = vals[n[1]] + vals[n[2]]
+        elif k == "sub":
+            v = vals[n[1]] - vals[n[2]]
+        elif k == "mul":
+            v = vals[n[1]] * vals[n[2]]
+        elif k == "neg":
+            v = -vals[n[1]]
+        elif k == "rot":
+            v = np.roll(vals[n[1]], -n[2])
+        elif k == "boot":
+            v = vals[n[1]]
+        else:
+            raise ValueError(k)
+        vals[i] = v
+    return [vals[o] for o in graph.outputs]
