@@ -81,7 +81,7 @@ template <int LOGA, int LD> HD void body_intt_B(const ArgsInttB &a, int job, Lan
   LANE_DECL;
   FOR_LANES(S, st, {
     grid_dep_launch();
-    stage_tw_B<LOGA>(tw, T.itw + (size_t)p * N, r, lane);
+    stage_tw_B<LOGA>(tw, T.itwB + (size_t)p * N, r, lane);
     grid_dep_wait();
     const int base = r * 256 + lane * 8;
     if (LD == LD_PLAIN) {
@@ -340,7 +340,7 @@ template <int LOGA> HD void body_mac_stage(const ArgsFwdB &a, int job, int tid, 
   const int N = 1 << T.logN;
   const int r = job & (Geo<LOGA>::ROWS - 1), Iidx = mac_Iidx<LOGA>(a, job), I = (Iidx == a.l) ? a.sp : Iidx;
   grid_dep_launch();
-  stage_tw_B<LOGA>(tw_s, T.tw + (size_t)I * N, r, tid, MAC_WARPS * 32);
+  stage_tw_B<LOGA>(tw_s, T.twB + (size_t)I * N, r, tid, MAC_WARPS * 32);
   grid_dep_wait();
   cp_async_wait();
 }
@@ -526,7 +526,7 @@ template <int LOGA> HD void body_mac_tail(const ArgsFwdB &a, int job, int K, Lan
   const ModQ m = T.mod[a.sp];
   LANE_DECL;
   FOR_LANES(S, st, {
-    stage_tw_B<LOGA>(tw_s, T.itw + (size_t)a.sp * N, r, lane); // both warps stage the same table (identical bytes)
+    stage_tw_B<LOGA>(tw_s, T.itwB + (size_t)a.sp * N, r, lane); // both warps stage the same table (identical bytes)
     _Pragma("unroll")
     for (int e = 0; e < 8; e++) S.x[e] = rows[K * 256 + lane * 8 + e];
     cp_async_wait();
@@ -551,7 +551,7 @@ template <int LOGA, int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, Lane
     const u64 *src = a.src + (size_t)d * N + r * 256;
     FOR_LANES(S, st, {
       grid_dep_launch();
-      stage_tw_B<LOGA>(tw, T.tw + (size_t)p * N, r, lane);
+      stage_tw_B<LOGA>(tw, T.twB + (size_t)p * N, r, lane);
       grid_dep_wait();
       _Pragma("unroll")
       for (int e = 0; e < 8; e++) S.x[e] = ldg_stream(src + idxH(lane, e));
@@ -580,7 +580,7 @@ template <int LOGA, int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, Lane
       FOR_LANES(S, st, {
         if (K == 0) {
           grid_dep_launch();
-          stage_tw_B<LOGA>(tw, T.tw + (size_t)i * N, r, lane);
+          stage_tw_B<LOGA>(tw, T.twB + (size_t)i * N, r, lane);
           grid_dep_wait();
         }
         if (K == 1) {
@@ -628,7 +628,7 @@ template <int LOGA, int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, Lane
     const u64 *src = a.src + ((size_t)K * a.l + i) * N + r * 256;
     FOR_LANES(S, st, {
       grid_dep_launch();
-      stage_tw_B<LOGA>(tw, T.tw + (size_t)i * N, r, lane);
+      stage_tw_B<LOGA>(tw, T.twB + (size_t)i * N, r, lane);
       grid_dep_wait();
       _Pragma("unroll")
       for (int e = 0; e < 8; e++) S.x[e] = ldg_stream(src + idxH(lane, e));

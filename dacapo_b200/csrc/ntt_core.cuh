@@ -32,6 +32,7 @@ struct NttTables {
   int logN, L;
   const Tw *tw;  // [L][N]  forward twiddles, tw[m+i] for stage with m groups, group i
   const Tw *itw; // [L][N]  inverses of the above
+  const Tw *twB, *itwB; // [L][rows][256] the same values regrouped per pass-B row (host_params.hpp build_rowwise)
   ModQ mod[HEVM_MAXL];
   Tw invn[HEVM_MAXL];           // N^-1
   Tw invn_w[HEVM_MAXL];         // N^-1 * itw[1]
@@ -138,15 +139,14 @@ template <int LOGA> HD void stage_tw_A(Tw *dst, const Tw *table, int lane) {
   _Pragma("unroll")
   for (int i = 0; i < Geo<LOGA>::ROWS / 32; i++) cp_async16(dst + lane + 32 * i, table + lane + 32 * i);
 }
-// pass B, row r: local entry (2^k - 1 + g) <- table[(ROWS << k) + (r << k) + g],  k < 8, g < 2^k
-// (one contiguous run of 2^k entries per local stage).  `tid`/`nthr`: the threads sharing the copy.
-template <int LOGA> HD void stage_tw_B(Tw *dst, const Tw *table, int r, int tid, int nthr = 32) {
+// pass B, row r: local entry (2^k - 1 + g) = table[(ROWS << k) + (r << k) + g],  k < 8, g < 2^k.
+// `tid`/`nthr`: the threads sharing the copy.
+// `tableB` = the prime's row-wise copy (NttTables::twB / itwB): one contiguous 4 KB block per row, eight 16-byte
+// cp.async per lane with immediate offsets
+template <int LOGA> HD void stage_tw_B(Tw *dst, const Tw *tableB, int r, int tid, int nthr = 32) {
+  const Tw *src = tableB + ((size_t)r << 8);
   _Pragma("unroll")
-  for (int k = 0; k < 8; k++) {
-    const Tw *src = table + (Geo<LOGA>::ROWS << k) + (r << k);
-    Tw *d = dst + ((1 << k) - 1);
-    for (int g = tid; g < (1 << k); g += nthr) cp_async16(d + g, src + g);
-  }
+  for (int g = tid; g < 256; g += nthr) cp_async16(dst + g, src + g);
 }
 
 // =====================================================================================

@@ -138,6 +138,9 @@ struct VM {
     P.build(logN, L, (int)pf.bits);
     Tw *d_tw = upload(P.tw), *d_itw = upload(P.itw);
     P.tab.tw = d_tw, P.tab.itw = d_itw;
+    P.build_rowwise();
+    P.tab.twB = upload(P.twB), P.tab.itwB = upload(P.itwB);
+    P.twB.clear(), P.twB.shrink_to_fit(), P.itwB.clear(), P.itwB.shrink_to_fit();
     dT = dalloc<NttTables>(1);
     CUDA_CHECK(cudaMemcpy(dT, &P.tab, sizeof(NttTables), cudaMemcpyHostToDevice));
     d_ctr_base = dalloc<u64>(1);

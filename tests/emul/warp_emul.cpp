@@ -80,6 +80,9 @@ void *emul_create(int logN, int L, int bits) {
   e->P.build(logN, L, bits);
   e->P.tab.tw = e->P.tw.data();
   e->P.tab.itw = e->P.itw.data();
+  e->P.build_rowwise();
+  e->P.tab.twB = e->P.twB.data();
+  e->P.tab.itwB = e->P.itwB.data();
   e->ops = make_ops(e->la, &e->P.tab, logN, L);
   if (!e->ops) return nullptr;
   e->scratch.resize(Scratch::words(L, e->P.N));
