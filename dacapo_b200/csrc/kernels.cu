@@ -1,12 +1,12 @@
 // sm_100a kernels of libB200_HEVM.so.
 //
 //  * NTT-based warp-job kernels: thin __global__ wrappers around ntt_bodies.cuh.  A CTA is
-//    8 independent warps (256 threads); each warp owns one job and a private padded
-//    shared-memory tile; there is no __syncthreads anywhere.
+//    4 independent warps (128 threads); each warp owns one job and a private padded
+//    shared-memory tile; only the key inner-product kernel has CTA barriers (its phase boundaries).
 //  * element-wise RNS kernels (256-bit vector loads/stores, one HBM pass)
 //  * samplers, key-generation / encryption helpers
-//  * fp64 CKKS encoder / decoder kernels (radix-2 special FFT, explicit *_rn intrinsics so that
-//    no FMA contraction changes bits w.r.t. the host restatement)
+//  * fp64 CKKS encoder / decoder kernels (radix-2 special FFT, four stages per launch, explicit *_rn
+//    intrinsics so that no FMA contraction changes bits w.r.t. the host restatement)
 #include "kernels.h"
 
 unsigned long long g_launch_count = 0;

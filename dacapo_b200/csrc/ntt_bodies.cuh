@@ -1,4 +1,4 @@
-// Warp-job bodies of the NTT-based kernels (N = 2^LOGA rows x 256 cols; LOGA = 6,7,8 <=> N = 2^14..2^16).
+// Warp-job bodies of the NTT-based kernels (N = 2^LOGA rows x 256 cols; LOGA = 6..9 <=> N = 2^14..2^17).
 // One warp executes one job (a (limb, tile) or (limb, row) pair); the key-switch inner-product
 // kernel uses one 4-warp CTA per (output prime, row) and splits the digit loop over its warps.
 // See ntt_core.cuh for the schedule, kernels.cu for the __global__ wrappers.
@@ -11,10 +11,10 @@
 //        CANON    canonical store (plain NTT)
 //        MODDOWN  (acc - u) * p^-1 + addend   with addend = permuted c0 | tensor product d0/d1
 //        RESCALE  (c - u) * q_last^-1
-//   body_mac_*   : forward pass B of every digit + key-switch inner product with the key
-//                  (128-bit lazy accumulators in registers, per-warp partial sums combined through
-//                  shared memory, one Barrett at the end): the l x (l+1) matrix of NTT'd digits
-//                  never exists in HBM.
+//   body_mac_*   : forward pass B of every digit into shared memory (radix-2^30 split), then the key-switch
+//                  inner product per coefficient over all digits (carry-free 64-bit column accumulators,
+//                  one Barrett at the end): the l x (l+1) matrix of NTT'd digits never exists in HBM.
+// Every body takes an optional target range (t0/nt/i_end) for the limb-sharded multi-GPU key switch.
 #pragma once
 #include "ntt_core.cuh"
 
