@@ -324,6 +324,8 @@ def main():
     ap.add_argument("--no-op-table", action="store_true")
     ap.add_argument("--no-resnet-mix", action="store_true", help="skip the ResNet-20 op-mix replay (N=1 only)")
     ap.add_argument("--no-sharded", action="store_true", help="skip the limb-sharded key-switch section (N>1 only)")
+    ap.add_argument("--ncu-range", action="store_true",
+                    help="bracket the timed region with cudaProfilerStart/Stop (ncu --profile-from-start off captures exactly the timed launches)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -393,10 +395,14 @@ def main():
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
+    if args.ncu_range:
+        lib.hevmx_profiler_range(vm, 1)
     lib.hevmx_timer(vm, 0)
     for _ in range(args.steps):
         lib.run(vm)
     ms = lib.hevmx_timer(vm, 1)
+    if args.ncu_range:
+        lib.hevmx_profiler_range(vm, 0)
     barrier()
     clocks = sampler.stop()
     launches = lib.hevmx_param(vm, 6) - launches0
