@@ -21,6 +21,18 @@ def test_example_script_runs_and_is_accurate(tmp_path):
     assert rms < 1e-3, rms  # the reference reports ~1e-3 on ResNet (README.md:187)
 
 
+def test_resnet_example_script(tmp_path):
+    """examples/resnet20.py = the reference's examples/tests/ResNet.py flow on the committed fixture."""
+    env = {**__import__("os").environ, "HOME": str(tmp_path)}
+    r = subprocess.run([sys.executable, str(REPO / "examples" / "resnet20.py"), "b200c", "40", "B200", "GPU"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "benchname: ResNet" in r.stdout and "waterline: 40" in r.stdout and "library: B200" in r.stdout
+    rms = float([l for l in r.stdout.splitlines() if l.startswith("rms:")][0].split()[1])
+    latency = float([l for l in r.stdout.splitlines() if l.startswith("latency:")][0].split()[1])
+    assert rms < 5e-3 and latency < 5.0, (rms, latency)
+
+
 def test_setlibnhw_argument_forms():
     sys.path.insert(0, str(REPO))
     from dacapo_b200 import runner
