@@ -9,23 +9,25 @@ import numpy as np
 FIXTURE = Path(__file__).resolve().parent.parent / "tests" / "golden" / "resnet20"
 
 
-def resnet20_files(tmpdir=None):
+def resnet20_files(tmpdir=None, variant=""):
     """Decompress the constants next to a copy of the program; returns (cst_path, hevm_path, input, expected, meta).
 
     The directory layout mimics the reference's `optimized/<compiler>/<bench>.<waterline>._hecate_<bench>.hevm`
     so that HEVM.printer (runner.py:256-271) can parse it."""
+    fixture = FIXTURE.parent / ("resnet20" + variant)  # variant "_nt16": nt = 2^16 slots, N = 2^17
     tmp = Path(tmpdir or tempfile.mkdtemp(prefix="resnet20_"))
     cst = tmp / "traced" / "_hecate_ResNet.cst"
     hv = tmp / "optimized" / "b200c" / "ResNet.40._hecate_ResNet.hevm"
     cst.parent.mkdir(parents=True, exist_ok=True)
     hv.parent.mkdir(parents=True, exist_ok=True)
     if not cst.is_file():
-        with lzma.open(FIXTURE / "resnet20.cst.xz") as f, open(cst, "wb") as o:
+        with lzma.open(fixture / "resnet20.cst.xz") as f, open(cst, "wb") as o:
             while True:
                 b = f.read(1 << 24)
                 if not b:
                     break
                 o.write(b)
-    hv.write_bytes((FIXTURE / "resnet20.hevm").read_bytes())
-    meta = json.loads((FIXTURE / "meta.json").read_text())
-    return str(cst), str(hv), np.load(FIXTURE / "input.npy"), np.load(FIXTURE / "expected.npy"), meta
+    hv.write_bytes((fixture / "resnet20.hevm").read_bytes())
+    meta = json.loads((fixture / "meta.json").read_text())
+    x = np.load(fixture / "input.npy") if (fixture / "input.npy").is_file() else np.load(fixture / "input.npz")["packed"]
+    return str(cst), str(hv), x, np.load(fixture / "expected.npy"), meta

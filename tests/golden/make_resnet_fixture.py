@@ -33,12 +33,13 @@ from dacapo_b200 import compiler, frontend  # noqa: E402
 sys.modules["hecate"] = frontend  # the reference scripts do `import hecate as hc`
 
 
-def main():
+def make(nt_bits, logN, out, cost, do_sweep):
     import torch
-    out = HERE / "resnet20"
     out.mkdir(exist_ok=True)
     bench = REF / "examples" / "benchmarks" / "ResNet.py"
-    src = bench.read_text().replace('"nt" : 2**16,', '"nt" : 2**14,')
+    src = bench.read_text()
+    assert '"nt" : 2**16,' in src
+    src = src.replace('"nt" : 2**16,', f'"nt" : 2**{nt_bits},')
     g = {"__name__": "__main__", "__file__": str(bench)}
     t0 = time.time()
     frontend.reset()
@@ -46,9 +47,8 @@ def main():
     graph = g["modName"]  # frontend.save() returns the recorded Graph
     print(f"traced {len(graph.nodes)} nodes, {len(graph.consts)} constants in {time.time() - t0:.1f}s")
 
-    # bootstrap levels are chosen against the measured B200 cost profile (profiled_B200_GPU.json at the repo root)
-    cost = json.loads((REPO / "profiled_B200_GPU.json").read_text())["latencyTableExact"]
-    prog, c = compiler.compile_graph(graph, compiler.Options(logN=15, num_primes=14, waterline=40, cost_table=cost))
+    # bootstrap levels are chosen against the measured B200 cost profile of this ring size
+    prog, c = compiler.compile_graph(graph, compiler.Options(logN=logN, num_primes=14, waterline=40, cost_table=cost))
     print("lowered ops:", c.stats, "ct regs", prog.num_ct, "pt regs", prog.num_pt, "pool", len(prog.constants))
     (out / "resnet20.hevm").write_bytes(prog.hevm_bytes())
     raw = prog.cst_bytes()
@@ -57,8 +57,8 @@ def main():
 
     # waterline sweep (BASELINE.json configs[3]): same graph, same constant pool, other scale-management waterlines
     sweep = {}
-    for W in (30, 35, 45, 50):
-        pw, cw = compiler.compile_graph(graph, compiler.Options(logN=15, num_primes=14, waterline=W, cost_table=cost))
+    for W in (30, 35, 45, 50) if do_sweep else ():
+        pw, cw = compiler.compile_graph(graph, compiler.Options(logN=logN, num_primes=14, waterline=W, cost_table=cost))
         if pw.cst_bytes() != raw:
             print(f"waterline {W}: constant pool differs, skipped")
             continue
@@ -72,19 +72,31 @@ def main():
     x = torch.randn(1, 3, 32, 32).clamp(-2.0, 2.0)
     with torch.no_grad():
         logits = model(x).cpu().numpy()[0].astype(np.float64)
-    shapes = {"nt": 2 ** 14, "bb": 32, "ko": 1, "ho": 32, "wo": 32}
+    shapes = {"nt": 2 ** nt_bits, "bb": 32, "ko": 1, "ho": 32, "wo": 32}
     conv1_shapes = g["CascadeConv"](shapes, model.module.conv1)
     close = g["shapeClosure"](**conv1_shapes)
     packed = np.asarray(close["MPP"](x)[0], dtype=np.float64).ravel()
-    np.save(out / "input.npy", packed)
+    if do_sweep:
+        np.save(out / "input.npy", packed)
+    else:
+        np.savez_compressed(out / "input.npz", packed=packed)
     np.save(out / "expected.npy", logits)
     meta = {"post_scale": 32.0, "n_out": 10, "lowered_ops": c.stats, "traced_nodes": len(graph.nodes),
             "ct_registers": prog.num_ct, "pt_registers": prog.num_pt, "hevm_ops": len(prog.ops), "waterline": 40,
             "waterline_sweep": sweep,
-            "source": "examples/benchmarks/ResNet.py (nt=2^14) traced with dacapo_b200.frontend, compiled with dacapo_b200.compiler",
+            "logN": logN, "slots": 2 ** nt_bits,
+            "source": f"examples/benchmarks/ResNet.py (nt=2^{nt_bits}) traced with dacapo_b200.frontend, compiled with dacapo_b200.compiler",
             "weights": "examples/data/resnet20.silu.model", "input": "torch.manual_seed(1); randn(1,3,32,32).clamp(-2,2)"}
     (out / "meta.json").write_text(json.dumps(meta, indent=1))
     print("logits", logits)
+
+
+def main():
+    cost15 = json.loads((REPO / "profiled_B200_GPU.json").read_text())["latencyTableExact"]
+    make(14, 15, HERE / "resnet20", cost15, True)
+    # BASELINE.json configs[2]: nt = 2^16 slots (the benchmark's own default) => N = 2^17; same 14 x 60-bit chain
+    cost17 = json.loads((REPO / "profiles" / "profiled_B200_GPU_N17_L30.json").read_text())["latencyTableExact"]
+    make(16, 17, HERE / "resnet20_nt16", {k: v[:13] for k, v in cost17.items()}, False)
 
 
 if __name__ == "__main__":
