@@ -214,17 +214,23 @@ def workload_config(batch, note=None):
     return c
 
 
-def resnet20_real(lib, vm, tmp, reps=3):
+def resnet20_real(lib, vm, tmp, reps=3, variant=""):
     """The real encrypted ResNet-20 (BASELINE.json configs[0]) from the committed fixture: program traced from the
     reference's examples/benchmarks/ResNet.py, compiled by dacapo_b200.compiler; rms against the plaintext torch
     logits exactly like examples/tests/ResNet.py:113-118 (hc-test times run() only)."""
     from dacapo_b200 import fixtures
-    cst, hv, x, expected, meta = fixtures.resnet20_files(tmp)
+    cst, hv, x, expected, meta = fixtures.resnet20_files(tmp, variant)
+    if variant:  # another ring size (nt = 2^16 slots => N = 2^17): its own VM, keys derived on the device
+        kd = tempfile.mkdtemp(prefix="hevm_bench_keys_big_")
+        os.environ.update(HEVM_LOGN=str(meta["logN"]), HEVM_NUM_PRIMES=str(NPRIMES), HEVM_SEED=str(SEED), HEVM_PRIME_BITS="60")
+        lib.create_context(kd.encode())
+        vm = lib.initFullVM(kd.encode(), True)
+        os.environ.update(HEVM_LOGN=str(LOGN))
     t0 = time.perf_counter()
     lib.load(vm, cst.encode(), hv.encode())
     lib.preprocess(vm)
     t_pre = time.perf_counter() - t0
-    out = np.zeros(SLOTS)
+    out = np.zeros(meta.get("slots", SLOTS))
     lat, e2e = [], []
     for i in range(reps + 1):
         t0 = time.perf_counter()
@@ -239,8 +245,9 @@ def resnet20_real(lib, vm, tmp, reps=3):
             e2e.append(t3 - t0)
     res = out[:meta["n_out"]] * meta["post_scale"]
     err = res - expected
-    return {"what": "encrypted ResNet-20 (SiLU, nt=2^14 slots, N=2^15, 14x60-bit primes, waterline 40), synthetic seeded input, "
-                    "weights examples/data/resnet20.silu.model; program compiled by dacapo_b200.compiler (not hecate-opt)",
+    return {"what": f"encrypted ResNet-20 (SiLU, nt=2^{int(np.log2(meta.get('slots', SLOTS)))} slots, N=2^{meta.get('logN', LOGN)}, 14x60-bit primes, waterline 40), "
+                    "synthetic seeded input, weights examples/data/resnet20.silu.model; program compiled by dacapo_b200.compiler "
+                    "(not hecate-opt), bootstrap levels from the measured cost profile",
             "run_latency_s": float(np.median(lat)), "first_run_s": None, "e2e_latency_s": float(np.median(e2e)), "load_preprocess_s": t_pre,
             "rms": float(np.sqrt(np.sum(err * err) / res.shape[-1])), "argmax_ok": bool(np.argmax(res) == np.argmax(expected)),
             "lowered_ops": meta["lowered_ops"], "hevm_ops": meta["hevm_ops"],
@@ -468,6 +475,7 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_resnet_mix:
         line["resnet20"] = resnet20_real(lib, vm, tmp)
+        line["resnet20_nt16"] = resnet20_real(lib, vm, tempfile.mkdtemp(prefix="hevm_bench_nt16_"), reps=2, variant="_nt16")
         line["resnet20_opmix"] = resnet_mix(lib, vm, tmp, cpu=not args.no_cpu_baseline)
 
     if (args.op_table or world == 1) and not args.no_op_table and rank == 0:
