@@ -530,10 +530,11 @@ struct VM {
   }
   static double op_cost(const HevmOp &op, int level) {
     switch (op.opcode) {
-    case 1: case 8: return 40.0 + 12.0 * level;
-    case 3: return 15.0 + 1.5 * level;
-    case 10: return 250.0;
-    default: return 4.0;
+    // microseconds measured on one B200 at N = 2^15 (profiled_B200_GPU.json): key switch 51 us at level 3 .. 148 us at 13
+    case 1: case 8: return 30.0 + 7.0 * level + 0.16 * level * level;
+    case 3: return 14.0 + 1.1 * level;
+    case 10: return 178.0 + 4.0 * level;
+    default: return 3.5 + 0.25 * level;
     }
   }
   void invalidate_graph() {
