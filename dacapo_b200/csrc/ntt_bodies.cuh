@@ -474,28 +474,37 @@ template <int LOGA> HD void body_mac_dot(const ArgsFwdB &a, int job, int tid, co
     for (int K = 0; K < 2; K++)
       _Pragma("unroll")
       for (int j = 0; j < 2; j++) c[K][j][0] = c[K][j][1] = c[K][j][2] = c[K][j][3] = 0;
-    for (int J0 = Jb; J0 < Je; J0 += MAC_KEY_BATCH) {
+    // running pointers: key rows of digit J (kq: poly 0, kq + kstride: poly 1) and its x row
+    const u64 *kq = kp + (size_t)Jb * dstride;
+    const u64 *xq = xbuf + (size_t)Jb * 256 + 2 * tid;
+    int J = Jb;
+    for (; J + MAC_KEY_BATCH <= Je; J += MAC_KEY_BATCH) { // full batches: the key rows of MAC_KEY_BATCH digits in flight
       U2 k[MAC_KEY_BATCH][2];
       _Pragma("unroll")
       for (int b = 0; b < MAC_KEY_BATCH; b++) {
-        const u64 *p = kp + (size_t)(J0 + b) * dstride;
-        if (J0 + b < Je) {
-          k[b][0] = ldg_key2(p);
-          k[b][1] = ldg_key2(p + kstride);
-        } else {
-          k[b][0] = k[b][1] = U2{0, 0};
-        }
+        k[b][0] = ldg_key2(kq);
+        k[b][1] = ldg_key2(kq + kstride);
+        kq += dstride;
       }
       _Pragma("unroll")
       for (int b = 0; b < MAC_KEY_BATCH; b++) {
-        const int J = J0 + b < Je ? J0 + b : Je - 1; // stay inside xbuf; the key is zero there
-        const u64 *xp = xbuf + (size_t)J * 256 + 2 * tid;
-        const u64 xa = xp[0], xb = xp[1];
+        const u64 xa = xq[b * 256], xb = xq[b * 256 + 1];
         mac30(c[0][0], xa, k[b][0].a);
         mac30(c[0][1], xb, k[b][0].b);
         mac30(c[1][0], xa, k[b][1].a);
         mac30(c[1][1], xb, k[b][1].b);
       }
+      xq += MAC_KEY_BATCH * 256;
+    }
+    for (; J < Je; J++) { // remaining digits one by one
+      const U2 k0 = ldg_key2(kq), k1 = ldg_key2(kq + kstride);
+      const u64 xa = xq[0], xb = xq[1];
+      mac30(c[0][0], xa, k0.a);
+      mac30(c[0][1], xb, k0.b);
+      mac30(c[1][0], xa, k1.a);
+      mac30(c[1][1], xb, k1.b);
+      kq += dstride;
+      xq += 256;
     }
     _Pragma("unroll")
     for (int K = 0; K < 2; K++)
@@ -503,11 +512,7 @@ template <int LOGA> HD void body_mac_dot(const ArgsFwdB &a, int job, int tid, co
       for (int j = 0; j < 2; j++) flush30(lo[K][j], hi[K][j], c[K][j]);
   };
   u64 lo[2][2] = {{0, 0}, {0, 0}}, hi[2][2] = {{0, 0}, {0, 0}};
-  if (a.l <= MAC_FLUSH_DIGITS) {
-    chunk(0, a.l, lo, hi);
-  } else {
-    for (int Jc = 0; Jc < a.l; Jc += MAC_FLUSH_DIGITS) chunk(Jc, a.l < Jc + MAC_FLUSH_DIGITS ? a.l : Jc + MAC_FLUSH_DIGITS, lo, hi);
-  }
+  for (int Jc = 0; Jc < a.l; Jc += MAC_FLUSH_DIGITS) chunk(Jc, a.l < Jc + MAC_FLUSH_DIGITS ? a.l : Jc + MAC_FLUSH_DIGITS, lo, hi);
   _Pragma("unroll")
   for (int K = 0; K < 2; K++) {
     u64 v[2];
