@@ -98,3 +98,50 @@ def test_constant_folding_and_residual_alignment(oracle_lib, tmp_path):
     assert np.max(np.abs(out - ref)) < 1e-4
     text = asm.disassemble(prog)
     assert "rotate" in text and "mulcc" in text
+
+
+def test_latency_driven_bootstrap_levels_and_graph_evaluator(oracle_lib, tmp_path):
+    """Options.cost_table (the measured profile's schema) picks the level every placed bootstrap returns to; the
+    program still computes frontend.evaluate(graph).  With a table in which bootstraps are cheap and key switches
+    steep in the level, the planner bootstraps more often and keeps rotations low."""
+    hc.reset()
+    n = 1 << (LOGN - 1)
+
+    @hc.func("c")
+    def f(x):
+        y = x
+        for i in range(6):
+            s = y + y.rotate(1 << i) * 0.5          # rotation-heavy layer ...
+            y = s * s * 0.45 + 0.05                 # ... followed by a ct x ct level
+        return y
+
+    g = hc.save()
+    top = NPR - 1
+    steep = {"earth.rotate_single": [10.0 * (l + 1) ** 2 for l in range(top)], "earth.mul_double": [10.0 * (l + 1) ** 2 for l in range(top)],
+             "earth.mul_single": [1.0] * top, "earth.add_double": [1.0] * top, "earth.add_single": [1.0] * top,
+             "earth.rescale_single": [2.0] * top, "earth.modswitch_single": [0.5] * top, "earth.negate_single": [1.0] * top,
+             "earth.bootstrap_single": [5.0] * top}
+    base, cb = compiler.compile_graph(g, compiler.Options(logN=LOGN, num_primes=NPR))
+    prog, c = compiler.compile_graph(g, compiler.Options(logN=LOGN, num_primes=NPR, cost_table=steep))
+    assert c.stats.get("bootstrap", 0) >= cb.stats.get("bootstrap", 0)
+    x = np.random.default_rng(5).uniform(-1, 1, n)
+    expected = hc.evaluate(g, [x], n)[0]
+    for p in (base, prog):
+        out = run_on(oracle_lib, p, [x], tmp_path)[0]
+        assert np.max(np.abs(out - expected)) < 1e-3
+
+
+def test_composite_rotation_is_split_into_naf_steps():
+    """rotate(k) without a key of its own is emitted as SEAL's NAF steps, least significant first (Evaluator::rotate_internal)."""
+    hc.reset()
+
+    @hc.func("c")
+    def f(x):
+        return x.rotate(7) + x.rotate(-3)
+
+    g = hc.save()
+    prog, c = compiler.compile_graph(g, compiler.Options(logN=LOGN, num_primes=NPR))
+    steps = [(r if r < 32768 else r - 65536) for oc, d, l, r in prog.ops if oc == asm.ROTATE]
+    assert sorted(steps) == sorted([-1, 8, 1, -4])  # 7 = -1 + 8, -3 = +1 - 4
+    cmp_ = compiler.Compiler(g, compiler.Options(logN=LOGN, num_primes=NPR))
+    assert cmp_.naf_terms(7) == [-1, 8] and cmp_.naf_terms(-3) == [1, -4] and cmp_.naf_terms(64) == [64]
