@@ -258,6 +258,37 @@ __global__ void __launch_bounds__(256) k_elementwise(const NttTables *T, int log
     stg4(out + off, r[0], r[1], r[2], r[3]);
   }
 }
+// acc + x0*p0 + x1*p1 + ...: the canonical value after every step equals the one the separate mulcp / addcc kernels
+// produce, so the final residues are bit-identical
+__global__ void __launch_bounds__(256) k_mulp_add_n(const NttTables *T, int logN, u64 *out, const u64 *acc, MulpTerms t, size_t pitch,
+                                                    int l, size_t nvec) {
+  const size_t polyw = (size_t)l << logN;
+  for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
+    const size_t w = v * 4;
+    const int K = w >= polyw;
+    const size_t rem = w - (K ? polyw : 0);
+    const int i = (int)(rem >> logN);
+    const size_t off = (size_t)K * pitch + rem;
+    const ModQ m = T->mod[i];
+    u64 r[4];
+    ldg_stream4(acc + off, r[0], r[1], r[2], r[3]);
+    for (int k = 0; k < t.n; k++) {
+      u64 x[4], y[4];
+      ldg_stream4(t.x[k] + off, x[0], x[1], x[2], x[3]);
+      ldg_stream4(t.p[k] + rem, y[0], y[1], y[2], y[3]);
+#pragma unroll
+      for (int e = 0; e < 4; e++) r[e] = csub(mulmod(x[e], y[e], m) + r[e], m.q);
+    }
+    stg4(out + off, r[0], r[1], r[2], r[3]);
+  }
+}
+static int ew_grid(size_t nthreads);
+void launch_mulp_add_n(cudaStream_t s, const NttTables *T, int logN, u64 *out, const u64 *acc, const MulpTerms &t, size_t pitch, int l) {
+  const size_t nvec = ((size_t)2 * l << logN) / 4;
+  PRE_LAUNCH(s, KC_ELEMENTWISE);
+  k_mulp_add_n<<<ew_grid(nvec), 256, 0, s>>>(T, logN, out, acc, t, pitch, l, nvec);
+  POST_LAUNCH_S(s);
+}
 static int ew_grid(size_t nthreads) {
   size_t g = (nthreads + 255) / 256;
   const size_t cap = 148 * 8; // 8 resident CTAs of 256 threads per SM, 148 SMs

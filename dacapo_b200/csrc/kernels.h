@@ -54,6 +54,13 @@ struct GpuLauncher {
 };
 
 // ---- element-wise ciphertext kernels (SEAL add/negate/add_plain/multiply_plain, limb drop) ----
+// out = acc + sum_k x[k] * p[k] (k < n <= 8): a chain of multiply_plain + add, one HBM pass
+struct MulpTerms {
+  const u64 *x[8];
+  const u64 *p[8];
+  int n;
+};
+void launch_mulp_add_n(cudaStream_t s, const NttTables *T, int logN, u64 *out, const u64 *acc, const MulpTerms &t, size_t pitch, int l);
 enum { EW_ADD = 0, EW_NEG = 1, EW_ADDP = 2, EW_MULP = 3, EW_COPY = 4, EW_MULP_ADD = 5 /* out = a * p + b */ };
 // out[K][i][n] = op(a[K][i][n], b...) for K<2, i<l ; ct poly pitch = `pitch` words; plaintext `p` is [l][N]
 void launch_elementwise(cudaStream_t s, int op, const NttTables *T, int logN, u64 *out, const u64 *a, const u64 *b,

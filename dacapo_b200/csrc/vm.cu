@@ -582,7 +582,7 @@ struct VM {
     // peephole: mulcp t <- x * p immediately followed by addcc d <- t + y (either operand order) where t is dead
     // afterwards becomes ONE kernel d <- x * p + y (same canonical residues; register metadata of both ops is
     // still applied in order).  Liveness is conservative: every register is live at the end of the program.
-    std::vector<char> fuse(prog.size(), 0);
+    std::vector<char> fuse(prog.size(), 0), acc_dead(prog.size(), 0);
     {
       static const bool on = !(std::getenv("HEVM_FUSE") && std::atoi(std::getenv("HEVM_FUSE")) == 0);
       std::vector<char> live(ct.size(), 1);
@@ -595,64 +595,132 @@ struct VM {
           const int t = m.dst;
           const bool t_once = (o.lhs == t) != (o.rhs == t);
           const bool t_dead = (o.dst == t) || !live[t]; // liveness after the addcc
-          if (t_once && t_dead && m.lhs < ct.size()) fuse[i - 1] = 1;
+          if (t_once && t_dead && m.lhs < ct.size()) {
+            fuse[i - 1] = 1;
+            const int y = (o.lhs == t) ? o.rhs : o.lhs; // the other addend: dead after this pair?
+            acc_dead[i - 1] = (o.dst == y) || !live[y];
+          }
         }
         live[o.dst] = 0;
         live[o.lhs < ct.size() ? o.lhs : o.dst] = 1;
         if (o.opcode == 6 || o.opcode == 8) live[o.rhs < ct.size() ? o.rhs : o.dst] = 1;
       }
     }
+    // chain_cont[pc] (pc = a fused pair with result register D): the next op that touches D is another fused pair that
+    // takes D as its addend, does not multiply D itself, and after which D is dead -- the running sum then never has
+    // to exist in D
+    std::vector<char> chain_cont(prog.size(), 0);
+    for (size_t pc = 0; pc + 1 < prog.size(); pc++) {
+      if (!fuse[pc]) continue;
+      const int D = prog[pc + 1].dst;
+      for (size_t j = pc + 2; j < prog.size() && j < pc + 2 + 96; j++) {
+        const HevmOp &o = prog[j];
+        const bool ct_op = (o.opcode >= 1 && o.opcode <= 4) || (o.opcode >= 6 && o.opcode <= 10);
+        if (!ct_op) continue;
+        const bool two = o.opcode == 6 || o.opcode == 8;
+        if (fuse[j]) {
+          const HevmOp &a2 = prog[j + 1];
+          const int t2 = o.dst, y2 = (a2.lhs == t2) ? a2.rhs : a2.lhs;
+          if (o.lhs == D || t2 == D) break;                       // reads / clobbers D
+          if (y2 == D) {
+            chain_cont[pc] = acc_dead[j];
+            break;
+          }
+          if (a2.dst == D) break;
+          j++; // skip the addcc of that pair
+          continue;
+        }
+        if (o.dst == D || o.lhs == D || (two && o.rhs == D)) break;
+      }
+    }
+    const bool chains_on = !spare.empty() && !(std::getenv("HEVM_CHAIN") && std::atoi(std::getenv("HEVM_CHAIN")) == 0);
+    struct Pending {
+      bool active = false;
+      int accreg = -1, lvl = 0;
+      u64 *acc_buf = nullptr;
+      std::vector<u64 *> xs;
+      std::vector<const u64 *> ps;
+    } pend;
+    auto pinned = [&](const u64 *b) {
+      if (!pend.active) return false;
+      if (b == pend.acc_buf) return true;
+      for (u64 *x : pend.xs)
+        if (x == b) return true;
+      return false;
+    };
+    auto flush_pending = [&]() {
+      if (!pend.active) return;
+      const int wr = pend.accreg, lvl = pend.lvl;
+      std::vector<u64 *> srcs(pend.xs);
+      srcs.push_back(pend.acc_buf);
+      double dep_ready = 0, min_start = 1e300;
+      for (u64 *b : srcs) dep_ready = std::max(dep_ready, bs[b].ready);
+      for (int i = 0; i < nl; i++) min_start = std::min(min_start, std::max(lanes[i].load, dep_ready));
+      int best = -1;
+      for (size_t k = 0; k < srcs.size() && best < 0; k++) {
+        const int pl = bs[srcs[k]].wr_lane;
+        if (pl >= 0 && std::max(lanes[pl].load, dep_ready) <= min_start + 2.0) best = pl;
+      }
+      if (best < 0)
+        for (int i = 0; i < nl; i++) {
+          if (std::max(lanes[i].load, dep_ready) > min_start + 1e-9) continue;
+          if (best < 0 || lanes[i].load > lanes[best].load) best = i;
+        }
+      const double best_start = std::max(lanes[best].load, dep_ready);
+      Lane &L0 = lanes[best];
+      auto wait_on = [&](int lane, cudaEvent_t e) {
+        if (e && lane != best) CUDA_CHECK(cudaStreamWaitEvent(L0.stream, e, 0));
+      };
+      u64 *old_buf = ct[wr].d, *dst_buf = old_buf;
+      if (pool_head < pool.size()) {
+        dst_buf = pool[pool_head++];
+        pool.push_back(old_buf);
+      }
+      for (u64 *b : srcs) wait_on(bs[b].wr_lane, bs[b].wr);
+      BufState &D = bs[dst_buf];
+      wait_on(D.wr_lane, D.wr);
+      for (auto &r : D.readers) wait_on(r.first, r.second);
+      ln = &L0;
+      if (pend.xs.size() == 1) {
+        launch_elementwise(L0.stream, EW_MULP_ADD, dT, logN, dst_buf, pend.xs[0], pend.acc_buf, pend.ps[0], pitch, lvl);
+      } else {
+        MulpTerms mt{};
+        mt.n = (int)pend.xs.size();
+        for (int k = 0; k < mt.n; k++) mt.x[k] = pend.xs[k], mt.p[k] = pend.ps[k];
+        launch_mulp_add_n(L0.stream, dT, logN, dst_buf, pend.acc_buf, mt, pitch, lvl);
+      }
+      ct[wr].d = dst_buf;
+      cudaEvent_t done = new_event();
+      CUDA_CHECK(cudaEventRecord(done, L0.stream));
+      for (u64 *b : srcs)
+        if (b != dst_buf) bs[b].readers.emplace_back(best, done);
+      BufState &D2 = bs[dst_buf];
+      D2.wr = done, D2.wr_lane = best, D2.readers.clear();
+      L0.load = best_start + 4.0 + 1.5 * (double)pend.xs.size();
+      D2.ready = L0.load;
+      pend.active = false, pend.xs.clear(), pend.ps.clear();
+    };
     for (size_t pc = 0; pc < prog.size(); pc++) {
       const HevmOp &op = prog[pc];
       if (fuse[pc]) {
         const HevmOp &m = op, &ad = prog[pc + 1];
         const int t = m.dst, y = (ad.lhs == t) ? ad.rhs : ad.lhs, wr = ad.dst;
-        u64 *xb = ct[m.lhs].d, *yb = ct[y].d;
-        const u64 *pb = ptr(m.rhs).d;
         const int lvl = ct[m.lhs].level;
         if (ct[y].level != lvl) die("addcc: level mismatch");
-        u64 *srcs[2] = {xb, yb};
-        double dep_ready = std::max(bs[xb].ready, bs[yb].ready), min_start = 1e300;
-        for (int i = 0; i < nl; i++) min_start = std::min(min_start, std::max(lanes[i].load, dep_ready));
-        int best = -1;
-        for (int k = 0; k < 2 && best < 0; k++) {
-          const int pl = bs[srcs[k]].wr_lane;
-          if (pl >= 0 && std::max(lanes[pl].load, dep_ready) <= min_start + 2.0) best = pl;
-        }
-        if (best < 0)
-          for (int i = 0; i < nl; i++) {
-            if (std::max(lanes[i].load, dep_ready) > min_start + 1e-9) continue;
-            if (best < 0 || lanes[i].load > lanes[best].load) best = i;
-          }
-        const double best_start = std::max(lanes[best].load, dep_ready);
-        Lane &L0 = lanes[best];
-        auto wait_on = [&](int lane, cudaEvent_t e) {
-          if (e && lane != best) CUDA_CHECK(cudaStreamWaitEvent(L0.stream, e, 0));
-        };
-        u64 *old_buf = ct[wr].d, *dst_buf = old_buf;
-        if (pool_head < pool.size()) {
-          dst_buf = pool[pool_head++];
-          pool.push_back(old_buf);
-        }
-        for (int k = 0; k < 2; k++) wait_on(bs[srcs[k]].wr_lane, bs[srcs[k]].wr);
-        BufState &D = bs[dst_buf];
-        wait_on(D.wr_lane, D.wr);
-        for (auto &r : D.readers) wait_on(r.first, r.second);
-        ln = &L0;
-        launch_elementwise(L0.stream, EW_MULP_ADD, dT, logN, dst_buf, xb, yb, pb, pitch, lvl);
+        // accumulation chains s1 = s0 + x1*p1; s2 = s1 + x2*p2; ... (convolution taps): the terms are collected and issued
+        // as ONE kernel when the chain ends -- nothing else reads the intermediate sums (chain_cont), the captured source
+        // buffers stay pinned until then
+        const bool extend = pend.active && pend.accreg == y && pend.lvl == lvl && pend.xs.size() < 8;
+        if (!extend) flush_pending();
+        if (!pend.active) pend.active = true, pend.acc_buf = ct[y].d, pend.lvl = lvl;
+        pend.accreg = wr; // the register that holds the running sum from here on
+        pend.xs.push_back(ct[m.lhs].d);
+        pend.ps.push_back(ptr(m.rhs).d);
         meta_only = true; // both ops' level / scale bookkeeping, in program order (SEAL_HEVM.cpp:297-323)
         exec(m);
         exec(ad);
         meta_only = false;
-        ct[wr].d = dst_buf;
-        cudaEvent_t done = new_event();
-        CUDA_CHECK(cudaEventRecord(done, L0.stream));
-        for (int k = 0; k < 2; k++)
-          if (srcs[k] != dst_buf) bs[srcs[k]].readers.emplace_back(best, done);
-        BufState &D2 = bs[dst_buf];
-        D2.wr = done, D2.wr_lane = best, D2.readers.clear();
-        L0.load = best_start + 5.0;
-        D2.ready = L0.load;
+        if (!(chain_cont[pc] && chains_on) || pend.xs.size() >= 8) flush_pending();
         pc++;
         continue;
       }
@@ -671,6 +739,11 @@ struct VM {
       for (int k = 0; k < nrd; k++)
         if ((size_t)rd[k] >= ct.size()) die("ciphertext register index out of range");
       if ((size_t)wr >= ct.size()) die("ciphertext register index out of range");
+      if (pend.active) {
+        bool touch = wr == pend.accreg || (pool_head < pool.size() && pinned(pool[pool_head]));
+        for (int k = 0; k < nrd; k++) touch |= rd[k] == pend.accreg;
+        if (touch) flush_pending();
+      }
       if (op.opcode == 4 && op.lhs == op.dst) { // in-place limb drop: metadata only, no kernel, no dependency
         exec(op);
         continue;
@@ -740,6 +813,7 @@ struct VM {
       L0.load = best_start + op_cost(op, lvl);
       D2.ready = L0.load;
     }
+    flush_pending();
     final_map.resize(home.size());
     for (size_t r = 0; r < home.size(); r++) final_map[r] = ct[r].d;
     if (std::getenv("HEVM_SCHED_DEBUG")) {

@@ -314,6 +314,67 @@ def test_fused_mulcp_addcc_bit_exact(pair, tmp_path):
         vm.lib.hevmx_resize(vm.vm, 8, 4)
 
 
+def test_accumulation_chain_bit_exact(pair, tmp_path):
+    """acc += rot_k(x) * p_k chains (convolution taps): the scheduler defers the terms and issues one multi-term kernel
+    per chain (at most 8 terms); the rotation register is recycled between the taps, a chain is longer than 8, another
+    is cut by a read of the accumulator -- all bit-identical to the oracle's sequential interpreter."""
+    g, o = pair
+    lv = 4
+    p = asm.Program(init_level=13)
+    x = p.arg(40, lv)
+    acc, r, t, z, acc2 = (p.new_ct() for _ in range(5))
+    pts = []
+    for k in range(11):
+        pt = p.new_pt()
+        p.encode(pt, p.const(np.linspace(-1 + 0.1 * k, 0.7, 29 + k)), lv, 40)
+        pts.append(pt)
+    p.emit(asm.MULCP, acc, x, pts[0])                      # acc = x * p0
+    for k in range(1, 11):                                  # ten taps: longer than one kernel's 8 terms
+        p.rotate(r, x, 1 << (k % 5))                       # the same register r is overwritten for every tap
+        p.emit(asm.MULCP, t, r, pts[k])
+        p.emit(asm.ADDCC, acc, acc, t)
+    p.emit(asm.MULCP, acc2, x, pts[1])
+    for k in range(2, 6):
+        p.rotate(r, x, -(1 << k))
+        p.emit(asm.MULCP, t, r, pts[k])
+        p.emit(asm.ADDCC, acc2, t, acc2)                   # accumulator as the right operand
+        if k == 3:
+            p.emit(asm.ADDCC, z, acc2, acc)                # a read of acc2 in the middle of its chain
+    p.emit(asm.MULCP, t, acc2, pts[6])                     # multiplicand is the accumulator itself: no chain
+    p.emit(asm.ADDCC, acc2, acc2, t)
+    ping, pong = p.new_ct(), p.new_ct()                     # running sum alternates between two registers (SSA-style allocation)
+    p.emit(asm.MULCP, ping, x, pts[7])
+    cur, nxt = ping, pong
+    for k in range(5):
+        p.rotate(r, x, 3 + k)                               # composite steps: several key switches each
+        p.emit(asm.MULCP, t, r, pts[k])
+        p.emit(asm.ADDCC, nxt, cur, t)
+        cur, nxt = nxt, cur
+    p.emit(asm.ADDCC, z, z, cur)                            # final consumer; `nxt` holds a dead intermediate sum
+    p.emit(asm.NEGATE, nxt, x)                              # ... and is overwritten before the program ends
+    for reg in (acc, acc2, z, r, cur, nxt):
+        p.result(reg, 80, lv)
+    cst, hv = tmp_path / "a.cst", tmp_path / "a.hevm"
+    p.save(cst, hv)
+    n = o.N // 2
+    xs = np.random.default_rng(78).uniform(-1, 1, n)
+    outs = []
+    for vm in pair:
+        lib = vm.lib
+        lib.load(vm.vm, str(cst).encode(), str(hv).encode())
+        lib.preprocess(vm.vm)
+        lib.hevmx_set_enc_counter(vm.vm, 11)
+        lib.encrypt(vm.vm, 0, xs.ctypes.data_as(C.POINTER(C.c_double)), n)
+        lib.run(vm.vm)
+        lib.run(vm.vm)
+        outs.append([(vm.ct_read(reg), vm.ct_info(reg)) for reg in (acc, acc2, z, r, cur, nxt)])
+    for (a, ia), (b, ib) in zip(*outs):
+        assert ia == ib
+        assert np.array_equal(a, b)
+    for vm in pair:
+        vm.lib.hevmx_resize(vm.vm, 8, 4)
+
+
 def test_full_size_properties(pair):
     """Size-independent properties on the device alone (no oracle): add/negate cancel exactly,
     rotate(k) o rotate(-k) = id up to noise, rotate and multiply commute with decryption."""
