@@ -498,12 +498,59 @@ template <int K, bool GS> __global__ void k_fft_multi(int logN, double2 *v, cons
     for (int t = 0; t < P; t++) v[base + (size_t)t * gap_lo] = x[t];
   }
 }
-// all logN stages: groups of four (the remainder group first for GS -- smallest gaps --, last for CT)
+// The FFT_LC stages whose butterflies stay inside 2^FFT_LC-point contiguous chunks (gaps 1 .. 2^(FFT_LC-1)) in ONE
+// launch: a 1024-thread CTA owns a chunk in shared memory, one butterfly per thread and stage, __syncthreads between
+// stages.  Same butterflies on the same operands as the per-stage loops => bit-identical.
+#define FFT_LC 11
+template <bool GS> __global__ void __launch_bounds__(1024) k_fft_chunk(int logN, double2 *v, const double2 *roots, double fix, int has_last) {
+  __shared__ double2 sh[1 << FFT_LC];
+  const size_t n = (size_t)1 << logN, base = (size_t)blockIdx.x << FFT_LC;
+  const int tid = threadIdx.x;
+  sh[tid] = v[base + tid];
+  sh[tid + 1024] = v[base + tid + 1024];
+  __syncthreads();
+  for (int st = 0; st < FFT_LC; st++) {
+    const int gap = GS ? (1 << st) : (1 << (FFT_LC - 1 - st));
+    const size_t m = n / (2 * (size_t)gap);
+    const int gl = tid / gap, j = tid - gl * gap, off = 2 * gl * gap + j;
+    const size_t g = (base + off) / (2 * (size_t)gap);
+    const double2 u = sh[off], w = sh[off + gap];
+    if (GS) {
+      const double2 r = roots[(n - 2 * m) + 1 + g];
+      if (has_last && m == 1) {
+        const double2 sr = make_double2(__dmul_rn(r.x, fix), __dmul_rn(r.y, fix));
+        const double2 sm_ = cadd(u, w);
+        sh[off] = make_double2(__dmul_rn(sm_.x, fix), __dmul_rn(sm_.y, fix));
+        sh[off + gap] = cmul(csubc(u, w), sr);
+      } else {
+        sh[off] = cadd(u, w);
+        sh[off + gap] = cmul(csubc(u, w), r);
+      }
+    } else {
+      const double2 r = roots[m + g];
+      const double2 wr = cmul(w, r);
+      sh[off] = cadd(u, wr);
+      sh[off + gap] = csubc(u, wr);
+    }
+    __syncthreads();
+  }
+  v[base + tid] = sh[tid];
+  v[base + tid + 1024] = sh[tid + 1024];
+}
+// all logN stages: the FFT_LC contiguous stages in one chunk kernel, the strided ones in register groups of four
+// (GS walks the gaps upward: chunk kernel first; CT walks them downward: chunk kernel last)
 template <bool GS> static void launch_fft_all(cudaStream_t s, int logN, double2 *work, const double2 *roots, double fix) {
   const size_t n = (size_t)1 << logN;
+  const bool chunked = logN >= FFT_LC;
   int done = 0;
-  while (done < logN) {
-    const int k = (logN - done >= 4) ? 4 : logN - done;
+  if (chunked && GS) {
+    k_fft_chunk<true><<<(unsigned)(n >> FFT_LC), 1024, 0, s>>>(logN, work, roots, fix, logN == FFT_LC);
+    POST_LAUNCH_S(s);
+    done = FFT_LC;
+  }
+  const int strided_end = (chunked && !GS) ? logN - FFT_LC : logN;
+  while (done < strided_end) {
+    const int k = (strided_end - done >= 4) ? 4 : strided_end - done;
     // GS walks gaps 1, 2, 4, ... upward; CT walks gaps n/2, n/4, ... downward
     const int gap_lo = GS ? (1 << done) : (int)(n >> (done + k));
     const size_t sets = n >> k;
@@ -516,6 +563,10 @@ template <bool GS> static void launch_fft_all(cudaStream_t s, int logN, double2 
     }
     POST_LAUNCH_S(s);
     done += k;
+  }
+  if (chunked && !GS) {
+    k_fft_chunk<false><<<(unsigned)(n >> FFT_LC), 1024, 0, s>>>(logN, work, roots, fix, 0);
+    POST_LAUNCH_S(s);
   }
 }
 __global__ void k_enc_max(int logN, const double2 *work, unsigned long long *maxbits) {
