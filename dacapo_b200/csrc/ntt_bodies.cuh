@@ -169,6 +169,7 @@ struct ArgsFwdA {
   int plast; // ROUND: prime index of the divided-out modulus
   // limb-sharded key switching: only the targets [t0, t0 + nt) are produced (nt = 0: all of them)
   int t0, nt;
+  int pmod; // PRE_NONE: limb d uses prime prime0 + (d % pmod) * pstep (several polynomials in one launch); 0 = no wrap
 };
 template <int LOGA, int PRE> HD void body_fwd_A(const ArgsFwdA &a, int job, LaneA *st, u64 *sm) {
   const NttTables &T = *a.T;
@@ -177,7 +178,7 @@ template <int LOGA, int PRE> HD void body_fwd_A(const ArgsFwdA &a, int job, Lane
   int ps, pd, sl; // source prime, destination prime, source limb
   if (PRE == PRE_NONE) {
     sl = d;
-    ps = pd = a.prime0 + d * a.pstep;
+    ps = pd = a.prime0 + (a.pmod ? d % a.pmod : d) * a.pstep;
   } else if (PRE == PRE_MODUP) {
     const int Iidx = d / a.l + a.t0; // job rows enumerate the owned targets only
     sl = d - (Iidx - a.t0) * a.l;
@@ -329,6 +330,7 @@ struct ArgsFwdB {
   // limb-sharded key switching: MAC jobs cover the targets Iidx = i_end-1, i_end-2, ... (i_end = 0: l+1, i.e. all);
   // MODDOWN_GALOIS jobs cover the limbs [t0, t0 + nt) (nt = 0: all l)
   int i_end, t0, nt;
+  int pmod; // CANON: limb d uses prime prime0 + (d % pmod) * pstep; 0 = no wrap
 };
 
 // ---- key-switch inner product: one CTA of MAC_WARPS warps per (Iidx, row) ----------------------
@@ -551,7 +553,7 @@ template <int LOGA, int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, Lane
   Tw *tw = warp_tw(sm);
   LANE_DECL;
   if (EPI == EPI_CANON) {
-    const int p = a.prime0 + d * a.pstep;
+    const int p = a.prime0 + (a.pmod ? d % a.pmod : d) * a.pstep;
     const ModQ m = T.mod[p];
     const u64 *src = a.src + (size_t)d * N + r * 256;
     FOR_LANES(S, st, {

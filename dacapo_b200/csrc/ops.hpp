@@ -33,7 +33,8 @@ struct Scratch {      // device (or emulator-host) buffers, sized for the top le
 struct OpsIface {
   Scratch sc;
   virtual ~OpsIface() {}
-  virtual void ntt_fwd(const u64 *src, u64 *dst, int nl, int prime0, int pstep) = 0;
+  // limb k is transformed under prime prime0 + (pmod ? k % pmod : k) * pstep (pmod: several polynomials of pmod limbs each)
+  virtual void ntt_fwd(const u64 *src, u64 *dst, int nl, int prime0, int pstep, int pmod = 0) = 0;
   virtual void ntt_inv(const u64 *src, u64 *dst, int nl, int prime0, int pstep, int round = 0) = 0;
   virtual void keyswitch(int mode, const u64 *a, const u64 *b, u64 *dst, size_t pitch, int l, const u64 *key, u32 elt) = 0;
   virtual void rescale(const u64 *src, size_t src_pitch, u64 *dst, size_t dst_pitch, int l) = 0;
@@ -53,16 +54,17 @@ template <class LA, int LOGA> struct HeOps : OpsIface {
   int sp() const { return L - 1; }
 
   // forward NTT of nl limbs (limb k under prime prime0 + k*pstep); src may equal dst; canonical output
-  void ntt_fwd(const u64 *src, u64 *dst, int nl, int prime0, int pstep) override {
+  void ntt_fwd(const u64 *src, u64 *dst, int nl, int prime0, int pstep, int pmod = 0) override {
     for (int done = 0; done < nl;) { // staged through s2 in chunks
       int chunk = nl - done;
       int cap = L * (L - 1);
       if (chunk > cap) chunk = cap;
       ArgsFwdA a{};
-      a.T = T, a.src = src + (size_t)done * N, a.dst = sc.s2, a.nd = chunk, a.prime0 = prime0 + done * pstep, a.pstep = pstep;
+      a.T = T, a.src = src + (size_t)done * N, a.dst = sc.s2, a.nd = chunk, a.prime0 = prime0 + (pmod ? 0 : done * pstep), a.pstep = pstep;
+      a.pmod = pmod; // (with pmod the whole batch must fit one chunk: checked below)
       la.template fwd_A<LOGA, PRE_NONE>(a, chunk * TILES_A);
       ArgsFwdB b{};
-      b.T = T, b.src = sc.s2, b.dst = dst + (size_t)done * N, b.nd = chunk, b.prime0 = a.prime0, b.pstep = pstep;
+      b.T = T, b.src = sc.s2, b.dst = dst + (size_t)done * N, b.nd = chunk, b.prime0 = a.prime0, b.pstep = pstep, b.pmod = pmod;
       la.template fwd_B<LOGA, EPI_CANON>(b, chunk * ROWS);
       done += chunk;
     }

@@ -87,7 +87,7 @@ struct Lane {
   double2 *d_work = nullptr;
   unsigned long long *d_maxbits = nullptr;
   double *d_vals = nullptr, *d_vals_in = nullptr;
-  u64 *d_u = nullptr, *d_e = nullptr, *d_tmpct = nullptr, *d_coef = nullptr;
+  u64 *d_u = nullptr, *d_e = nullptr, *d_ue = nullptr, *d_tmpct = nullptr, *d_coef = nullptr;
   PtReg boot_pt;
   double load = 0; // scheduling estimate
 };
@@ -161,6 +161,7 @@ struct VM {
       l.d_vals_in = dalloc<double>(slots);
       l.d_u = dalloc<u64>((size_t)L * N);
       l.d_e = dalloc<u64>((size_t)2 * L * N);
+      l.d_ue = dalloc<u64>((size_t)3 * L * N); // encryption randomness u | e0 | e1, contiguous
       l.d_tmpct = dalloc<u64>((size_t)2 * L * N);
       l.d_coef = dalloc<u64>((size_t)L * N);
       l.boot_pt.d = dalloc<u64>((size_t)(L - 1) * N); // never reallocated (graph capture forbids cudaMalloc)
@@ -351,14 +352,17 @@ struct VM {
   void encrypt_pt(const PtReg &p, CtReg &out, u64 k) {
     const int l = p.level, nl = l + 1;
     const u64 counter = k;
-    launch_sample_ternary(ln->stream, dT, logN, ln->d_u, nl, seed, enc_stream(counter, 0), d_ctr_base);
-    ln->ops->ntt_fwd(ln->d_u, ln->d_u, nl, 0, 1);
-    for (int j = 0; j < 2; j++) {
-      u64 *e = ln->d_e + (size_t)j * nl * N;
-      launch_sample_cbd(ln->stream, dT, logN, e, nl, seed, enc_stream(counter, 1 + j), d_ctr_base);
-      ln->ops->ntt_fwd(e, e, nl, 0, 1);
+    // u, e0, e1 live back to back in d_ue ([3][nl][N]) so that one launch pair transforms all three
+    u64 *u = ln->d_ue, *e01 = ln->d_ue + (size_t)nl * N;
+    launch_sample_ternary(ln->stream, dT, logN, u, nl, seed, enc_stream(counter, 0), d_ctr_base);
+    for (int j = 0; j < 2; j++)
+      launch_sample_cbd(ln->stream, dT, logN, e01 + (size_t)j * nl * N, nl, seed, enc_stream(counter, 1 + j), d_ctr_base);
+    if (3 * nl <= L * (L - 1)) {
+      ln->ops->ntt_fwd(u, u, 3 * nl, 0, 1, nl);
+    } else {
+      for (int j = 0; j < 3; j++) ln->ops->ntt_fwd(u + (size_t)j * nl * N, u + (size_t)j * nl * N, nl, 0, 1);
     }
-    launch_enc_combine(ln->stream, dT, logN, nl, ln->d_tmpct, ln->d_u, d_pk, (size_t)L * N, ln->d_e);
+    launch_enc_combine(ln->stream, dT, logN, nl, ln->d_tmpct, u, d_pk, (size_t)L * N, e01);
     ln->ops->rescale(ln->d_tmpct, (size_t)nl * N, out.d, pitch, nl);
     launch_elementwise(ln->stream, EW_ADDP, dT, logN, out.d, out.d, nullptr, p.d, pitch, l);
     out.level = l;
