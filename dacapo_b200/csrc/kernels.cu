@@ -336,6 +336,26 @@ __global__ void k_sample_small(const NttTables *T, int logN, u64 *out, int limbs
     for (int i = 0; i < limbs; i++) out[(size_t)i * N + k] = t < 0 ? T->mod[i].q - (u64)(-t) : (u64)t;
   }
 }
+// the three small polynomials of one public-key encryption in one launch: blockIdx.y = 0 ternary u (stream0),
+// 1 and 2 the centred-binomial errors e0, e1 (stream0 + 1, + 2); out = [3][limbs][N]; same values as three
+// k_sample_small launches
+__global__ void k_sample_enc(const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream0, const u64 *ctr) {
+  const size_t N = (size_t)1 << logN;
+  const int which = blockIdx.y;
+  u64 stream = stream0 + which;
+  if (ctr) stream += *ctr * 4;
+  u64 *o = out + (size_t)which * limbs * N;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < N; k += (size_t)gridDim.x * blockDim.x) {
+    const u64 w = rnd64(seed, stream, k);
+    const int t = which ? __popcll(w & 0x1FFFFF) - __popcll((w >> 21) & 0x1FFFFF) : (int)(w % 3) - 1;
+    for (int i = 0; i < limbs; i++) o[(size_t)i * N + k] = t < 0 ? T->mod[i].q - (u64)(-t) : (u64)t;
+  }
+}
+static int ew_grid(size_t nthreads);
+void launch_sample_enc(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream0, const u64 *ctr) {
+  k_sample_enc<<<dim3(ew_grid((size_t)1 << logN), 3), 256, 0, s>>>(T, logN, out, limbs, seed, stream0, ctr);
+  POST_LAUNCH_S(s);
+}
 __global__ void k_sample_uniform(const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream_base) {
   const size_t N = (size_t)1 << logN, total = N * limbs;
   for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < total; v += (size_t)gridDim.x * blockDim.x) {

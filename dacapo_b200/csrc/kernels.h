@@ -73,6 +73,7 @@ void launch_sample_uniform(cudaStream_t s, const NttTables *T, int logN, u64 *ou
 
 // ---- key generation / encryption helpers ----
 // c0[i] = -(c1[i]*sk[i] + e[i]); if (digit >= 0 && i == digit) c0[i] += (p mod q_i) * newkey[i]
+void launch_sample_enc(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream0, const u64 *ctr);
 void launch_key_split(cudaStream_t s, u64 *key, size_t words);
 void launch_ksk_finish(cudaStream_t s, const NttTables *T, int logN, int L, u64 *c0, const u64 *c1, const u64 *sk,
                        const u64 *e, const u64 *newkey, int digit);

@@ -354,9 +354,7 @@ struct VM {
     const u64 counter = k;
     // u, e0, e1 live back to back in d_ue ([3][nl][N]) so that one launch pair transforms all three
     u64 *u = ln->d_ue, *e01 = ln->d_ue + (size_t)nl * N;
-    launch_sample_ternary(ln->stream, dT, logN, u, nl, seed, enc_stream(counter, 0), d_ctr_base);
-    for (int j = 0; j < 2; j++)
-      launch_sample_cbd(ln->stream, dT, logN, e01 + (size_t)j * nl * N, nl, seed, enc_stream(counter, 1 + j), d_ctr_base);
+    launch_sample_enc(ln->stream, dT, logN, u, nl, seed, enc_stream(counter, 0), d_ctr_base); // streams +0 (u), +1, +2 (e0, e1)
     if (3 * nl <= L * (L - 1)) {
       ln->ops->ntt_fwd(u, u, 3 * nl, 0, 1, nl);
     } else {
