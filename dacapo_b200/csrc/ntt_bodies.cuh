@@ -662,6 +662,12 @@ template <int LOGA, int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, Lane
         _Pragma("unroll")
         for (int e = 0; e < 8; e++) v[e] = csub(v[e] + w[e], q);
       }
+      if (EPI == EPI_RESCALE && K == 0 && a.add1) { // public-key encryption: c0 += plaintext (Encryptor::encrypt, last step)
+        u64 w[8];
+        load8_stream(a.add1 + off + b, w);
+        _Pragma("unroll")
+        for (int e = 0; e < 8; e++) v[e] = csub(v[e] + w[e], q);
+      }
       store8(o + b, v);
     });
   }

@@ -37,7 +37,8 @@ struct OpsIface {
   virtual void ntt_fwd(const u64 *src, u64 *dst, int nl, int prime0, int pstep, int pmod = 0) = 0;
   virtual void ntt_inv(const u64 *src, u64 *dst, int nl, int prime0, int pstep, int round = 0) = 0;
   virtual void keyswitch(int mode, const u64 *a, const u64 *b, u64 *dst, size_t pitch, int l, const u64 *key, u32 elt) = 0;
-  virtual void rescale(const u64 *src, size_t src_pitch, u64 *dst, size_t dst_pitch, int l) = 0;
+  // add_pt (optional, [l-1][N]): added to polynomial 0 of the result (the plaintext of a public-key encryption)
+  virtual void rescale(const u64 *src, size_t src_pitch, u64 *dst, size_t dst_pitch, int l, const u64 *add_pt = nullptr) = 0;
   // limb-sharded key switch: this rank owns the key-switch targets [tlo, thi) of [0, l]
   // (target l = the special prime); between the stages the caller exchanges sc.t (all-gather) and sc.rnd (broadcast)
   // mode LD_GALOIS: rotation of ciphertext `a` (b unused); mode LD_PRODUCT: multiply a*b + relinearise
@@ -212,7 +213,7 @@ template <class LA, int LOGA> struct HeOps : OpsIface {
 
   // ---- rescale: 2 polys with l limbs -> l-1 limbs (divide by q_{l-1} and round); three launches -------
   // src/dst poly pitches may differ (encrypt uses a compact (l)-limb temporary).
-  void rescale(const u64 *src, size_t src_pitch, u64 *dst, size_t dst_pitch, int l) override {
+  void rescale(const u64 *src, size_t src_pitch, u64 *dst, size_t dst_pitch, int l, const u64 *add_pt = nullptr) override {
     {
       ArgsInttB x{};
       x.T = T, x.src = src + (size_t)(l - 1) * N, x.sstride = src_pitch, x.dst = sc.s1, x.nl = 2, x.prime0 = l - 1, x.pstep = 0;
@@ -228,12 +229,12 @@ template <class LA, int LOGA> struct HeOps : OpsIface {
       for (int K = 0; K < 2; K++) {
         ArgsFwdB w{};
         w.T = T, w.src = sc.s4 + (size_t)K * (l - 1) * N, w.dst = dst + (size_t)K * dst_pitch, w.l = l - 1, w.add0 = src + (size_t)K * src_pitch;
-        w.pitch = 0, w.plast = l - 1;
+        w.pitch = 0, w.plast = l - 1, w.add1 = K == 0 ? add_pt : nullptr; // (the job index K is 0 in both launches)
         la.template fwd_B<LOGA, EPI_RESCALE>(w, (l - 1) * ROWS);
       }
     } else {
       ArgsFwdB w{};
-      w.T = T, w.src = sc.s4, w.dst = dst, w.l = l - 1, w.add0 = src, w.pitch = dst_pitch, w.plast = l - 1;
+      w.T = T, w.src = sc.s4, w.dst = dst, w.l = l - 1, w.add0 = src, w.pitch = dst_pitch, w.plast = l - 1, w.add1 = add_pt;
       la.template fwd_B<LOGA, EPI_RESCALE>(w, 2 * (l - 1) * ROWS);
     }
   }

@@ -361,8 +361,7 @@ struct VM {
       for (int j = 0; j < 3; j++) ln->ops->ntt_fwd(u + (size_t)j * nl * N, u + (size_t)j * nl * N, nl, 0, 1);
     }
     launch_enc_combine(ln->stream, dT, logN, nl, ln->d_tmpct, u, d_pk, (size_t)L * N, e01);
-    ln->ops->rescale(ln->d_tmpct, (size_t)nl * N, out.d, pitch, nl);
-    launch_elementwise(ln->stream, EW_ADDP, dT, logN, out.d, out.d, nullptr, p.d, pitch, l);
+    ln->ops->rescale(ln->d_tmpct, (size_t)nl * N, out.d, pitch, nl, p.d); // ... + plaintext, in the same epilogue
     out.level = l;
     out.scale = p.scale;
   }
