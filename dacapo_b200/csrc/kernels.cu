@@ -470,6 +470,17 @@ __global__ void k_enc_scatter(int logN, const double *vals, int len, const u32 *
     work[slot_index[slots + i]] = make_double2(v, -0.0);
   }
 }
+// decode's gather followed by encode's scatter of the same N/2 values, in place (the wrapper bootstrap re-encodes what it
+// just decoded): position slot_index[i] is read and rewritten by thread i alone, slot_index[slots + i] is only written
+__global__ void k_recode(int logN, const u32 *slot_index, double2 *work, unsigned long long *maxbits) {
+  const size_t slots = (size_t)1 << (logN - 1);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *maxbits = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < slots; i += (size_t)gridDim.x * blockDim.x) {
+    const double v = work[slot_index[i]].x;
+    work[slot_index[i]] = make_double2(v, 0.0);
+    work[slot_index[slots + i]] = make_double2(v, -0.0);
+  }
+}
 // Up to four consecutive radix-2 stages per launch: a thread owns the 2^K points  base + t * gap_lo  (t < 2^K) that
 // are closed under the stages with gaps gap_lo .. gap_lo * 2^(K-1), keeps them in registers and performs exactly the
 // butterflies of SEAL's stage-by-stage loops on them (Gentleman-Sande with m groups of gap n/(2m), roots consumed at
@@ -634,8 +645,10 @@ __global__ void k_enc_round(const NttTables *T, int logN, int level, const doubl
 void launch_encode(cudaStream_t s, const NttTables *T, const EncoderTables &E, int logN, const double *vals, int len,
                    int level, double scale, double2 *work, unsigned long long *maxbits, u64 *out) {
   const size_t n = (size_t)1 << logN;
-  k_enc_scatter<<<ew_grid(n / 2), 256, 0, s>>>(logN, vals, len, E.slot_index, work, maxbits);
-  POST_LAUNCH_S(s);
+  if (vals) { // nullptr: the slots are already in `work` (launch_decode with out == nullptr re-scattered them)
+    k_enc_scatter<<<ew_grid(n / 2), 256, 0, s>>>(logN, vals, len, E.slot_index, work, maxbits);
+    POST_LAUNCH_S(s);
+  }
   const double fix = scale / (double)n;
   launch_fft_all<true>(s, logN, work, E.inv_root, fix);
   k_enc_max<<<ew_grid(n), 256, 0, s>>>(logN, work, maxbits);
@@ -731,7 +744,7 @@ __global__ void k_dec_gather(int logN, const double2 *work, const u32 *slot_inde
     out[i] = work[slot_index[i]].x;
 }
 void launch_decode(cudaStream_t s, const NttTables *T, const EncoderTables &E, const DecodeTables &D, int logN, int l,
-                   const u64 *coeff, double scale, double2 *work, double *out) {
+                   const u64 *coeff, double scale, double2 *work, double *out, unsigned long long *maxbits) {
   const size_t n = (size_t)1 << logN;
   if (l + 1 > DEC_MAXW) {
     std::fprintf(stderr, "[b200-hevm] fatal: decode supports at most %d limbs\n", DEC_MAXW - 1);
@@ -740,6 +753,10 @@ void launch_decode(cudaStream_t s, const NttTables *T, const EncoderTables &E, c
   k_dec_compose<<<ew_grid(n), 256, 0, s>>>(T, logN, l, coeff, D, 1.0 / scale, work);
   POST_LAUNCH_S(s);
   launch_fft_all<false>(s, logN, work, E.fwd_root, 0.0);
-  k_dec_gather<<<ew_grid(n / 2), 256, 0, s>>>(logN, work, E.slot_index, out);
+  if (out) {
+    k_dec_gather<<<ew_grid(n / 2), 256, 0, s>>>(logN, work, E.slot_index, out);
+  } else { // decode -> encode round trip: leave the values in `work`, scattered for the encoder
+    k_recode<<<ew_grid(n / 2), 256, 0, s>>>(logN, E.slot_index, work, maxbits);
+  }
   POST_LAUNCH_S(s);
 }

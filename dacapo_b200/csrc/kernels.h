@@ -102,4 +102,4 @@ struct DecodeTables { // per level, device
 };
 // coeff: [l][N] coefficient-form canonical limbs -> out: N/2 doubles (device)
 void launch_decode(cudaStream_t s, const NttTables *T, const EncoderTables &E, const DecodeTables &D, int logN, int l,
-                   const u64 *coeff, double scale, double2 *work, double *out);
+                   const u64 *coeff, double scale, double2 *work, double *out, unsigned long long *maxbits = nullptr);

@@ -381,7 +381,7 @@ struct VM {
     ln->ops->ntt_inv(p.d, ln->d_coef, p.level, 0, 1);
     const DecTabs &t = dec_tabs(p.level);
     DecodeTables D{t.punct, t.invp, t.Q, t.half};
-    launch_decode(ln->stream, dT, E, D, logN, p.level, ln->d_coef, p.scale, ln->d_work, d_out);
+    launch_decode(ln->stream, dT, E, D, logN, p.level, ln->d_coef, p.scale, ln->d_work, d_out, ln->d_maxbits);
   }
 
   // ---------------------------------------------------------------- the opcodes (SEAL_HEVM.cpp:269-334)
@@ -504,9 +504,9 @@ struct VM {
     case 10: { // "bootstrap" = decrypt + re-encrypt at the target level, entirely on device
       CtReg &s = ctr(op.lhs), &d = ctr(op.dst);
       decrypt_to_pt(s, ln->boot_pt);
-      decode_pt(ln->boot_pt, ln->d_vals);
+      decode_pt(ln->boot_pt, nullptr); // the N/2 values stay in the lane's FFT buffer, already scattered for the encoder
       const int64_t sb = (int64_t)std::log2(s.scale); // SEAL_HEVM.cpp:332 truncation
-      encode_internal(ln->boot_pt, ln->d_vals, (int)(N / 2), op.rhs, sb);
+      encode_internal(ln->boot_pt, nullptr, (int)(N / 2), op.rhs, sb);
       encrypt_pt(ln->boot_pt, d, boot_index++);
       break;
     }
