@@ -325,6 +325,7 @@ struct ArgsFwdB {
   const u64 *add0;   // GALOIS: pc0 [l][N];  RELIN: a (ct, poly pitch) ; RESCALE: input ct
   const u64 *add1;   // RELIN: b (ct)
   size_t pitch;      // poly pitch (words) of ct operands / output
+  size_t spitch;     // RESCALE: poly pitch of the INPUT ciphertext when it differs from `pitch` (0 = same)
   int plast;         // prime divided out (sp for MODDOWN, l_in-1 for RESCALE)
   u64 *sp_rows;      // MAC: [2][N] inverse pass-B output of the special-prime accumulators (mod-down input)
   // limb-sharded key switching: MAC jobs cover the targets Iidx = i_end-1, i_end-2, ... (i_end = 0: l+1, i.e. all);
@@ -648,7 +649,7 @@ template <int LOGA, int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, Lane
     FOR_LANES(S, st, {
       const int b = lane * 8;
       u64 c[8], v[8];
-      const u64 *cin = (EPI == EPI_RESCALE) ? a.add0 + (size_t)K * a.pitch + off + b
+      const u64 *cin = (EPI == EPI_RESCALE) ? a.add0 + (size_t)K * (a.spitch ? a.spitch : a.pitch) + off + b
                                             : a.acc + ((size_t)K * (a.l + 1) + i) * N + r * 256 + b;
       load8_stream(cin, c);
       _Pragma("unroll")

@@ -224,17 +224,9 @@ template <class LA, int LOGA> struct HeOps : OpsIface {
       x.T = T, x.src = sc.s1, x.dst = sc.s4, x.nsrc = 2, x.l = l - 1, x.plast = l - 1, x.ngroups = pick_groups(2, l - 1);
       la.template invA_fwdA<LOGA, PRE_ROUND>(x, 2 * x.ngroups * TILES_A);
     }
-    if (src_pitch != dst_pitch) {
-      // epilogue addresses input and output with one pitch: run per poly
-      for (int K = 0; K < 2; K++) {
-        ArgsFwdB w{};
-        w.T = T, w.src = sc.s4 + (size_t)K * (l - 1) * N, w.dst = dst + (size_t)K * dst_pitch, w.l = l - 1, w.add0 = src + (size_t)K * src_pitch;
-        w.pitch = 0, w.plast = l - 1, w.add1 = K == 0 ? add_pt : nullptr; // (the job index K is 0 in both launches)
-        la.template fwd_B<LOGA, EPI_RESCALE>(w, (l - 1) * ROWS);
-      }
-    } else {
+    {
       ArgsFwdB w{};
-      w.T = T, w.src = sc.s4, w.dst = dst, w.l = l - 1, w.add0 = src, w.pitch = dst_pitch, w.plast = l - 1, w.add1 = add_pt;
+      w.T = T, w.src = sc.s4, w.dst = dst, w.l = l - 1, w.add0 = src, w.pitch = dst_pitch, w.spitch = src_pitch, w.plast = l - 1, w.add1 = add_pt;
       la.template fwd_B<LOGA, EPI_RESCALE>(w, 2 * (l - 1) * ROWS);
     }
   }
