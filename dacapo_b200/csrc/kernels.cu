@@ -568,6 +568,46 @@ template <bool GS> __global__ void __launch_bounds__(1024) k_fft_chunk(int logN,
   v[base + tid] = sh[tid];
   v[base + tid + 1024] = sh[tid + 1024];
 }
+// The K = logN - FFT_LC strided stages (gaps 2^FFT_LC * 2^s) in ONE launch: a CTA owns 2^(FFT_LC-K) neighbouring columns
+// (index mod 2^FFT_LC) with their 2^K points each, 2^FFT_LC points in shared memory, one butterfly per thread and stage.
+// Loads / stores are contiguous runs of 2^(FFT_LC-K) points.  Same butterflies, same operands => bit-identical.
+template <bool GS> __global__ void __launch_bounds__(1024) k_fft_cols(int logN, double2 *v, const double2 *roots, double fix) {
+  __shared__ double2 sh[1 << FFT_LC];
+  const int K = logN - FFT_LC, logC = FFT_LC - K, C = 1 << logC;
+  const size_t n = (size_t)1 << logN;
+  const int tid = threadIdx.x;
+  const size_t col0 = (size_t)blockIdx.x << logC;
+  for (int i = tid; i < (1 << FFT_LC); i += 1024) sh[i] = v[col0 + (i & (C - 1)) + ((size_t)(i >> logC) << FFT_LC)];
+  __syncthreads();
+  const int c = tid & (C - 1), bidx = tid >> logC;
+  for (int st = 0; st < K; st++) {
+    const int sft = GS ? st : K - 1 - st;
+    const int t = ((bidx >> sft) << (sft + 1)) | (bidx & ((1 << sft) - 1));
+    const size_t gap = (size_t)1 << (FFT_LC + sft), m = n / (2 * gap);
+    const size_t off = col0 + c + ((size_t)t << FFT_LC), g = off / (2 * gap);
+    const int i0 = (t << logC) + c, i1 = ((t + (1 << sft)) << logC) + c;
+    const double2 u = sh[i0], w = sh[i1];
+    if (GS) {
+      const double2 r = roots[(n - 2 * m) + 1 + g];
+      if (m == 1) {
+        const double2 sr = make_double2(__dmul_rn(r.x, fix), __dmul_rn(r.y, fix));
+        const double2 sm_ = cadd(u, w);
+        sh[i0] = make_double2(__dmul_rn(sm_.x, fix), __dmul_rn(sm_.y, fix));
+        sh[i1] = cmul(csubc(u, w), sr);
+      } else {
+        sh[i0] = cadd(u, w);
+        sh[i1] = cmul(csubc(u, w), r);
+      }
+    } else {
+      const double2 r = roots[m + g];
+      const double2 wr = cmul(w, r);
+      sh[i0] = cadd(u, wr);
+      sh[i1] = csubc(u, wr);
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < (1 << FFT_LC); i += 1024) v[col0 + (i & (C - 1)) + ((size_t)(i >> logC) << FFT_LC)] = sh[i];
+}
 // all logN stages: the FFT_LC contiguous stages in one chunk kernel, the strided ones in register groups of four
 // (GS walks the gaps upward: chunk kernel first; CT walks them downward: chunk kernel last)
 template <bool GS> static void launch_fft_all(cudaStream_t s, int logN, double2 *work, const double2 *roots, double fix) {
@@ -580,6 +620,12 @@ template <bool GS> static void launch_fft_all(cudaStream_t s, int logN, double2 
     done = FFT_LC;
   }
   const int strided_end = (chunked && !GS) ? logN - FFT_LC : logN;
+  const int Kc = logN - FFT_LC;
+  if (chunked && Kc >= 1 && Kc <= 6) { // all strided stages in one shared-memory launch
+    k_fft_cols<GS><<<1u << Kc, 1024, 0, s>>>(logN, work, roots, fix);
+    POST_LAUNCH_S(s);
+    done = strided_end;
+  }
   while (done < strided_end) {
     const int k = (strided_end - done >= 4) ? 4 : strided_end - done;
     // GS walks gaps 1, 2, 4, ... upward; CT walks gaps n/2, n/4, ... downward
