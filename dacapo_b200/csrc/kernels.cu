@@ -148,7 +148,7 @@ template <int LOGA, class K> static size_t warp_smem(K kern) {
 
 template <int LOGA, int LD> void GpuLauncher::intt_B(const ArgsInttB &a, int njobs) {
   if (njobs <= 0) return;
-  PRE_LAUNCH(stream, KC_INTT_B_PLAIN + LD);
+  PRE_LAUNCH(stream, LD == LD_DECRYPT ? KC_INTT_B_PLAIN : KC_INTT_B_PLAIN + LD);
   launch_pdl(k_intt_B<LOGA, LD>, ctas_for(njobs), CTA_THREADS, warp_smem<LOGA>(k_intt_B<LOGA, LD>), stream, a, njobs);
   POST_LAUNCH_S(stream);
 }
@@ -191,6 +191,7 @@ template <int LOGA, int PRE> void GpuLauncher::invA_fwdA(const ArgsInvFwdA &a, i
   template void GpuLauncher::intt_B<LOGA, LD_PLAIN>(const ArgsInttB &, int);                                           \
   template void GpuLauncher::intt_B<LOGA, LD_GALOIS>(const ArgsInttB &, int);                                          \
   template void GpuLauncher::intt_B<LOGA, LD_PRODUCT>(const ArgsInttB &, int);                                         \
+  template void GpuLauncher::intt_B<LOGA, LD_DECRYPT>(const ArgsInttB &, int);                                         \
   template void GpuLauncher::intt_A<LOGA>(const ArgsInttA &, int);                                                     \
   template void GpuLauncher::fwd_A<LOGA, PRE_NONE>(const ArgsFwdA &, int);                                             \
   template void GpuLauncher::fwd_A<LOGA, PRE_MODUP>(const ArgsFwdA &, int);                                            \

@@ -18,7 +18,7 @@
 #pragma once
 #include "ntt_core.cuh"
 
-enum { LD_PLAIN = 0, LD_GALOIS = 1, LD_PRODUCT = 2 };
+enum { LD_PLAIN = 0, LD_GALOIS = 1, LD_PRODUCT = 2, LD_DECRYPT = 3 /* c0 + c1 * s: src = c1, src2 = s, c0 = c0 */ };
 enum { PRE_NONE = 0, PRE_MODUP = 1, PRE_ROUND = 2 };
 enum { EPI_CANON = 0, EPI_MAC = 1, EPI_MODDOWN_GALOIS = 2, EPI_MODDOWN_RELIN = 3, EPI_RESCALE = 4 };
 
@@ -102,6 +102,11 @@ template <int LOGA, int LD> HD void body_intt_B(const ArgsInttB &a, int job, Lan
       load8_stream(a.src2 + (size_t)limb * N + base, v);
       _Pragma("unroll")
       for (int e = 0; e < 8; e++) S.x[e] = mulmod(u[e], v[e], m);
+      if (LD == LD_DECRYPT) { // Decryptor: c0 + c1 * s (SEAL_HEVM.cpp:330, 449)
+        load8_stream(a.c0 + (size_t)limb * N + base, u);
+        _Pragma("unroll")
+        for (int e = 0; e < 8; e++) S.x[e] = csub(S.x[e] + u[e], m.q);
+      }
     }
     cp_async_wait();
   });

@@ -36,6 +36,8 @@ struct OpsIface {
   // limb k is transformed under prime prime0 + (pmod ? k % pmod : k) * pstep (pmod: several polynomials of pmod limbs each)
   virtual void ntt_fwd(const u64 *src, u64 *dst, int nl, int prime0, int pstep, int pmod = 0) = 0;
   virtual void ntt_inv(const u64 *src, u64 *dst, int nl, int prime0, int pstep, int round = 0) = 0;
+  // coefficient form of the decrypted plaintext c0 + c1 * s of a level-l ciphertext (both polys at `pitch`), canonical
+  virtual void decrypt_inv(const u64 *ct, size_t pitch, const u64 *sk, u64 *dst, int l) = 0;
   virtual void keyswitch(int mode, const u64 *a, const u64 *b, u64 *dst, size_t pitch, int l, const u64 *key, u32 elt) = 0;
   // add_pt (optional, [l-1][N]): added to polynomial 0 of the result (the plaintext of a public-key encryption)
   virtual void rescale(const u64 *src, size_t src_pitch, u64 *dst, size_t dst_pitch, int l, const u64 *add_pt = nullptr) = 0;
@@ -86,6 +88,14 @@ template <class LA, int LOGA> struct HeOps : OpsIface {
     }
   }
 
+  void decrypt_inv(const u64 *ct, size_t pitch, const u64 *sk, u64 *dst, int l) override {
+    ArgsInttB a{};
+    a.T = T, a.src = ct + pitch, a.src2 = sk, a.c0 = ct, a.dst = sc.s2, a.nl = l, a.prime0 = 0, a.pstep = 1;
+    la.template intt_B<LOGA, LD_DECRYPT>(a, l * ROWS);
+    ArgsInttA b{};
+    b.T = T, b.src = sc.s2, b.dst = dst, b.nl = l, b.prime0 = 0, b.pstep = 1, b.round = 0;
+    la.template intt_A<LOGA>(b, l * TILES_A);
+  }
   // how many target groups the fused inverse+forward pass-A kernel is split into: enough warp jobs to
   // cover the machine (148 SMs x 8 warps) without recomputing the inverse pass more than needed
   static int pick_groups(int nsrc, int ntargets) {

@@ -503,8 +503,14 @@ struct VM {
     }
     case 10: { // "bootstrap" = decrypt + re-encrypt at the target level, entirely on device
       CtReg &s = ctr(op.lhs), &d = ctr(op.dst);
-      decrypt_to_pt(s, ln->boot_pt);
-      decode_pt(ln->boot_pt, nullptr); // the N/2 values stay in the lane's FFT buffer, already scattered for the encoder
+      // decrypt (c0 + c1 s) fused into the inverse NTT's load; the N/2 decoded values stay in the lane's FFT buffer,
+      // already scattered for the encoder
+      ln->ops->decrypt_inv(s.d, pitch, d_sk, ln->d_coef, s.level);
+      {
+        const DecTabs &t = dec_tabs(s.level);
+        DecodeTables D{t.punct, t.invp, t.Q, t.half};
+        launch_decode(ln->stream, dT, E, D, logN, s.level, ln->d_coef, s.scale, ln->d_work, nullptr, ln->d_maxbits);
+      }
       const int64_t sb = (int64_t)std::log2(s.scale); // SEAL_HEVM.cpp:332 truncation
       encode_internal(ln->boot_pt, nullptr, (int)(N / 2), op.rhs, sb);
       encrypt_pt(ln->boot_pt, d, boot_index++);
