@@ -214,7 +214,7 @@ def workload_config(batch, note=None):
     return c
 
 
-def resnet20_real(lib, vm, tmp, reps=3, variant=""):
+def resnet20_real(lib, vm, tmp, reps=3, variant="", cpu=False):
     """The real encrypted ResNet-20 (BASELINE.json configs[0]) from the committed fixture: program traced from the
     reference's examples/benchmarks/ResNet.py, compiled by dacapo_b200.compiler; rms against the plaintext torch
     logits exactly like examples/tests/ResNet.py:113-118 (hc-test times run() only)."""
@@ -245,7 +245,13 @@ def resnet20_real(lib, vm, tmp, reps=3, variant=""):
             e2e.append(t3 - t0)
     res = out[:meta["n_out"]] * meta["post_scale"]
     err = res - expected
-    return {"what": f"encrypted ResNet-20 (SiLU, nt=2^{int(np.log2(meta.get('slots', SLOTS)))} slots, N=2^{meta.get('logN', LOGN)}, 14x60-bit primes, waterline 40), "
+    extra = {}
+    if cpu and not variant:
+        est, _ = cpu_port_estimate(program_histogram(hv))
+        extra = {"cpu_port_estimate_s": est, "speedup_vs_cpu_port_estimate": est / float(np.median(lat)),
+                 "cpu_port_estimate_note": "this very program on the CPU port (oracle, one thread): sum over (op, level) of count x measured "
+                                           "oracle time for key-switch steps, mulcc, rescale, mulcp, addcc and bootstrap"}
+    return {**extra, "what": f"encrypted ResNet-20 (SiLU, nt=2^{int(np.log2(meta.get('slots', SLOTS)))} slots, N=2^{meta.get('logN', LOGN)}, 14x60-bit primes, waterline 40), "
                     "synthetic seeded input, weights examples/data/resnet20.silu.model; program compiled by dacapo_b200.compiler "
                     "(not hecate-opt), bootstrap levels from the measured cost profile",
             "run_latency_s": float(np.median(lat)), "first_run_s": None, "e2e_latency_s": float(np.median(e2e)), "load_preprocess_s": t_pre,
@@ -253,6 +259,65 @@ def resnet20_real(lib, vm, tmp, reps=3, variant=""):
             "lowered_ops": meta["lowered_ops"], "hevm_ops": meta["hevm_ops"],
             "reference_README": {"latency_s": 53.726, "rms": 9.515e-4, "hardware": "unspecified CPU, SEAL single thread (README.md:186-187)"},
             "speedup_vs_README_latency": 53.726 / float(np.median(lat))}
+
+
+_CPU_OP_CACHE = {}
+
+
+def cpu_port_estimate(per_level):
+    """Latency of an op mix on the CPU port (oracle, one thread): every (op, level) pair is timed once on the oracle and
+    multiplied by its count.  per_level: {(name, level): count}, names ks_steps / mulcc / rescale / mulcp / addcc / bootstrap
+    (for bootstrap the level is the target level)."""
+    olib = _binding.bind(_binding.ORACLE_LIB)
+    if "vm" not in _CPU_OP_CACHE:
+        kd = tempfile.mkdtemp(prefix="hevm_cpu_mix_")
+        ovm = make_vm(olib, kd)
+        olib.hevmx_resize(ovm, 4, 2)
+        _CPU_OP_CACHE["vm"] = ovm
+    ovm = _CPU_OP_CACHE["vm"]
+    u64p = C.POINTER(C.c_uint64)
+    primes = np.zeros(NPRIMES, dtype=np.uint64)
+    olib.hevmx_primes(ovm, primes.ctypes.data_as(u64p))
+    est, table = 0.0, {}
+    rng = np.random.default_rng(3)
+    ops = (("ks_steps", asm.ROTATE, 1), ("mulcc", asm.MULCC, 0), ("rescale", asm.RESCALE, 0), ("mulcp", asm.MULCP, 0),
+           ("addcc", asm.ADDCC, 0), ("bootstrap", asm.BOOTSTRAP, None))
+    for lvl in sorted({l for (_, l) in per_level}):
+        for name, opc, rhs in ops:
+            n = per_level.get((name, lvl), 0)
+            if not n:
+                continue
+            key = (name, lvl)
+            if key not in _CPU_OP_CACHE:
+                src_l = 2 if name == "bootstrap" else lvl
+                a = np.zeros((2, src_l, N), dtype=np.uint64)
+                for i in range(src_l):
+                    a[:, i, :] = rng.integers(0, int(primes[i]), size=(2, N), dtype=np.uint64)
+                olib.hevmx_ct_write(ovm, 0, a.ctypes.data_as(u64p), src_l, 2.0 ** 40)
+                olib.hevmx_pt_write(ovm, 0, a[0].ctypes.data_as(u64p), src_l, 2.0 ** 40)
+                t0 = time.perf_counter()
+                olib.hevmx_exec(ovm, opc, 1, 0, lvl if rhs is None else rhs)
+                _CPU_OP_CACHE[key] = time.perf_counter() - t0
+            table[f"{name}@{lvl}"] = _CPU_OP_CACHE[key]
+            est += n * _CPU_OP_CACHE[key]
+    return est, table
+
+
+def program_histogram(hevm_path):
+    """(op, level) counts of a compiled program (rotations are single key-switch steps in our compiler's output)."""
+    p = asm.parse_hevm(open(hevm_path, "rb").read())
+    names = {asm.ROTATE: "ks_steps", asm.MULCC: "mulcc", asm.RESCALE: "rescale", asm.MULCP: "mulcp", asm.ADDCC: "addcc", asm.BOOTSTRAP: "bootstrap"}
+    lv, hist = {i: lvl for i, lvl in enumerate(p.arg_level)}, {}
+    for oc, d, l, r in p.ops:
+        if oc in (asm.ENCODE, asm.PLACEHOLDER):
+            continue
+        L = lv.get(l, p.init_level)
+        res = L - 1 if oc == asm.RESCALE else L - r if oc == asm.MODSWITCH else r if oc == asm.BOOTSTRAP else L
+        if oc in names:
+            key = (names[oc], res if oc == asm.BOOTSTRAP else L)
+            hist[key] = hist.get(key, 0) + 1
+        lv[d] = res
+    return hist
 
 
 def resnet_mix(lib, vm, tmp, cpu=True, reps=3):
@@ -286,34 +351,10 @@ def resnet_mix(lib, vm, tmp, cpu=True, reps=3):
            "e2e_latency_s": float(np.median(e2e)), "preprocess_s": t_pre, "finite_output": bool(np.all(np.isfinite(out))),
            "reference_README_latency_s": 53.726}
     if cpu:
-        olib = _binding.bind(_binding.ORACLE_LIB)
-        kd = tempfile.mkdtemp(prefix="hevm_cpu_mix_")
-        ovm = make_vm(olib, kd)
-        olib.hevmx_resize(ovm, 4, 2)
-        u64p = C.POINTER(C.c_uint64)
-        primes = np.zeros(NPRIMES, dtype=np.uint64)
-        olib.hevmx_primes(ovm, primes.ctypes.data_as(u64p))
-        est, table = 0.0, {}
-        rng = np.random.default_rng(3)
-        for lvl in sorted({l for (_, l) in per_level}):
-            a = np.zeros((2, lvl, N), dtype=np.uint64)
-            for i in range(lvl):
-                a[:, i, :] = rng.integers(0, int(primes[i]), size=(2, N), dtype=np.uint64)
-            olib.hevmx_ct_write(ovm, 0, a.ctypes.data_as(u64p), lvl, 2.0 ** 40)
-            olib.hevmx_pt_write(ovm, 0, a[0].ctypes.data_as(u64p), lvl, 2.0 ** 40)
-            for name, opc, rhs in (("ks_steps", asm.ROTATE, 1), ("mulcc", asm.MULCC, 0), ("rescale", asm.RESCALE, 0),
-                                   ("mulcp", asm.MULCP, 0), ("addcc", asm.ADDCC, 0)):
-                n = per_level.get((name, lvl), 0)
-                if not n:
-                    continue
-                t0 = time.perf_counter()
-                olib.hevmx_exec(ovm, opc, 1, 0, rhs)
-                dt = time.perf_counter() - t0
-                table[f"{name}@{lvl}"] = dt
-                est += n * dt
+        est, _ = cpu_port_estimate(per_level)
         res["cpu_port_estimate_s"] = est
         res["cpu_port_estimate_note"] = ("sum over (op, level) of count x single-thread oracle time for rotate-step, mulcc, rescale, "
-                                         "mulcp, addcc (bootstrap / negate / addcp not counted)")
+                                         "mulcp, addcc, bootstrap (negate / addcp / modswitch not counted)")
         res["speedup_vs_cpu_port_estimate"] = est / res["run_latency_s"]
     return res
 
@@ -474,7 +515,7 @@ def main():
     }
 
     if rank == 0 and world == 1 and not args.no_resnet_mix:
-        line["resnet20"] = resnet20_real(lib, vm, tmp)
+        line["resnet20"] = resnet20_real(lib, vm, tmp, cpu=not args.no_cpu_baseline)
         line["resnet20_nt16"] = resnet20_real(lib, vm, tempfile.mkdtemp(prefix="hevm_bench_nt16_"), reps=2, variant="_nt16")
         line["resnet20_opmix"] = resnet_mix(lib, vm, tmp, cpu=not args.no_cpu_baseline)
 
