@@ -34,6 +34,13 @@ REPO = Path(__file__).resolve().parent
 sys.path.insert(0, str(REPO))
 from dacapo_b200 import _binding, hevm_asm as asm  # noqa: E402
 
+
+def _fixtures():
+    """tests/fixtures.py: the committed ResNet-20 fixture and the path of the CPU oracle (checker / cpu_baseline leg only)."""
+    sys.path.insert(0, str(REPO / "tests"))
+    import fixtures
+    return fixtures
+
 LOGN, NPRIMES, TOP = 15, 14, 13
 N = 1 << LOGN
 SLOTS = N // 2
@@ -148,7 +155,7 @@ def measured_peak():
 # ------------------------------------------------------------------------------------------------
 def cpu_chain_rate(nthreads, reps, keydirs):
     """Oracle (CPU port of the reference path): `nthreads` independent VMs, each runs one full chain per rep."""
-    olib = _binding.bind(_binding.ORACLE_LIB)
+    olib = _binding.bind(_fixtures().ORACLE_LIB)
     prog, steps, _ = build_program(1)
     nops = len(prog.ops)
     tmp = tempfile.mkdtemp(prefix="hevm_cpu_")
@@ -218,7 +225,7 @@ def resnet20_real(lib, vm, tmp, reps=3, variant="", cpu=False):
     """The real encrypted ResNet-20 (BASELINE.json configs[0]) from the committed fixture: program traced from the
     reference's examples/benchmarks/ResNet.py, compiled by dacapo_b200.compiler; rms against the plaintext torch
     logits exactly like examples/tests/ResNet.py:113-118 (hc-test times run() only)."""
-    from dacapo_b200 import fixtures
+    fixtures = _fixtures()
     cst, hv, x, expected, meta = fixtures.resnet20_files(tmp, variant)
     if variant:  # another ring size (nt = 2^16 slots => N = 2^17): its own VM, keys derived on the device
         kd = tempfile.mkdtemp(prefix="hevm_bench_keys_big_")
@@ -268,7 +275,7 @@ def cpu_port_estimate(per_level):
     """Latency of an op mix on the CPU port (oracle, one thread): every (op, level) pair is timed once on the oracle and
     multiplied by its count.  per_level: {(name, level): count}, names ks_steps / mulcc / rescale / mulcp / addcc / bootstrap
     (for bootstrap the level is the target level)."""
-    olib = _binding.bind(_binding.ORACLE_LIB)
+    olib = _binding.bind(_fixtures().ORACLE_LIB)
     if "vm" not in _CPU_OP_CACHE:
         kd = tempfile.mkdtemp(prefix="hevm_cpu_mix_")
         ovm = make_vm(olib, kd)

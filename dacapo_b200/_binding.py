@@ -1,4 +1,4 @@
-"""ctypes prototypes shared by every lib*_HEVM.so (product and CPU oracle).
+"""ctypes prototypes of lib*_HEVM.so (the same block binds any library exporting the reference ABI).
 
 Mirrors the prototype block of the reference driver
 (reference: python/hecate/hecate/runner.py:34-71) and adds the hevmx_* hooks of
@@ -9,7 +9,6 @@ from pathlib import Path
 
 REPO = Path(__file__).resolve().parent.parent
 B200_LIB = Path(__file__).resolve().parent / "libB200_HEVM.so"
-ORACLE_LIB = REPO / "oracle" / "libORACLE_HEVM.so"
 
 ABI_SYMBOLS = [
     "create_context", "initFullVM", "initClientVM", "initServerVM", "load", "loadClient",
@@ -24,7 +23,7 @@ EXT_SYMBOLS = [
 ]
 
 B200_ONLY_SYMBOLS = ["hevmx_ntt_bench", "hevmx_timer", "hevmx_profile", "hevmx_profile_read", "hevmx_profiler_range",
-                     "hevmx_ks_shard_stage", "hevmx_mulcc_shard_stage", "hevmx_dev_ptr", "hevmx_stream"]
+                     "hevmx_ks_shard_stage", "hevmx_mulcc_shard_stage", "hevmx_dev_ptr", "hevmx_stream", "hevmx_exec_batch"]
 
 _u64p = C.POINTER(C.c_uint64)
 _f64p = C.POINTER(C.c_double)
@@ -102,6 +101,7 @@ def bind(path):
         lw.hevmx_mulcc_shard_stage.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64]
         lw.hevmx_dev_ptr.argtypes = [C.c_void_p, C.c_int64]
         lw.hevmx_dev_ptr.restype = C.c_void_p
+        lw.hevmx_exec_batch.argtypes = [C.c_void_p, C.c_int64, C.c_int64, _i64p, _i64p, _i64p]
         lw.hevmx_stream.argtypes = [C.c_void_p]
         lw.hevmx_stream.restype = C.c_void_p
     return lw

@@ -8,6 +8,7 @@
 //  * fp64 CKKS encoder / decoder kernels (radix-2 special FFT, four stages per launch, explicit *_rn
 //    intrinsics so that no FMA contraction changes bits w.r.t. the host restatement)
 #include "kernels.h"
+#include <algorithm>
 
 unsigned long long g_launch_count = 0;
 bool g_pdl_suspended = false;
@@ -15,7 +16,7 @@ KProfiler g_prof;
 const char *const g_kernel_class_names[KC_COUNT] = {
     "intt_B_plain", "intt_B_galois", "intt_B_product", "intt_A", "fwd_A_plain", "fwd_A_modup", "fwd_A_round",
     "fwd_B_canon", "fwd_B_mac", "fwd_B_moddown_galois", "fwd_B_moddown_relin", "fwd_B_rescale", "invA_fwdA_modup",
-    "invA_fwdA_round", "elementwise", "other"};
+    "invA_fwdA_round", "elementwise", "ks_fused_galois", "ks_fused_relin", "rescale_fused", "other"};
 cudaEvent_t KProfiler::ev() {
   if (used == pool.size()) {
     cudaEvent_t e;
@@ -111,6 +112,131 @@ template <int LOGA> __global__ void __launch_bounds__(MAC_WARPS * 32, MAC_MIN_CT
   }
 }
 
+
+// ---- single-launch key switch / rescale (ks_fused.cuh): persistent CTAs, ticket-ordered work units, per-limb
+// completion counters instead of kernel boundaries -----------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+#ifndef FUSED_POLL_ALL
+#define FUSED_POLL_ALL 0
+#endif
+#ifndef FUSED_POLL_NS
+#define FUSED_POLL_NS 64
+#endif
+template <int LOGA, int MODE> __global__ void __launch_bounds__(CTA_THREADS, 4) k_ks_fused(KsFusedArgs A) {
+  __shared__ int s_ticket, s_last;
+  const int L = A.Ltot;
+  const size_t N = (size_t)1 << (LOGA + 8);
+  grid_dep_wait(); // the previous kernel on this stream has zeroed the counters / produced the operands
+  grid_dep_launch();
+  const KsUnits K = ks_units<LOGA, MODE>(A);
+  unsigned *const ctl0 = reinterpret_cast<unsigned *>(A.ct[0].scratch + Scratch::words(L, N) - KS_CTL_WORDS); // launch-wide ticket / exit counters
+  if (threadIdx.x == 0) s_ticket = (int)atomicAdd(ctl0 + ctl_ticket(L), 1u);
+  for (;;) {
+    __syncthreads();
+    const int ticket = s_ticket;
+    if (ticket >= K.total) break;
+    const int warp = threadIdx.x >> 5;
+    {
+      const KsUnit un = ks_decode(K, A.nct, ticket);
+      const KsDeps d = ks_deps<LOGA, MODE>(A, un);
+#if FUSED_POLL_ALL
+      if (d.nwait) { // every thread polls with an acquire load
+        const unsigned *ctl = reinterpret_cast<const unsigned *>(A.ct[un.c].scratch + Scratch::words(L, N) - KS_CTL_WORDS);
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+          if (k < d.nwait)
+            while (ld_acquire_u32(ctl + d.widx[k]) < d.wtarget[k]) __nanosleep(FUSED_POLL_NS);
+      }
+#else
+      if ((threadIdx.x & 31) == 0 && d.nwait) { // lane 0 of every warp polls (relaxed), then one acquire fence
+        const unsigned *ctl = reinterpret_cast<const unsigned *>(A.ct[un.c].scratch + Scratch::words(L, N) - KS_CTL_WORDS);
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+          if (k < d.nwait)
+            while (ld_relaxed_u32(ctl + d.widx[k]) < d.wtarget[k]) __nanosleep(FUSED_POLL_NS);
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      }
+#endif
+      __syncwarp();
+    }
+    {
+      const KsUnit un = ks_decode(K, A.nct, ticket);
+      const KsCt &c = A.ct[un.c];
+      Scratch sc;
+      sc.carve(c.scratch, L, N);
+      u64 *sm = dyn_smem + (size_t)warp * Geo<LOGA>::WARP_WORDS;
+      const int job = un.u * WARPS_PER_CTA + warp;
+      switch (un.phase) {
+      case 0: {
+        LaneB8 st[1];
+        body_intt_B<LOGA, MODE == FUSED_RESCALE ? LD_PLAIN : MODE>(ks_args_p1<MODE>(A, c, sc), job, st, sm);
+        break;
+      }
+      case 1: {
+        LaneA st[1];
+        body_invA_fwdA<LOGA, PRE_MODUP>(ks_args_p2(A, sc), job, st, sm);
+        break;
+      }
+      case 2: {
+        const ArgsFwdB a = ks_args_p3<MODE>(A, c, sc);
+        Tw *tw_s = reinterpret_cast<Tw *>(dyn_smem);
+        u64 *tiles = dyn_smem + MAC_TW_WORDS, *rowbufs = tiles + MAC_WARPS * TILE_B_WORDS, *xbuf = rowbufs + MAC_WARPS * MAC_ROW_WORDS;
+        body_mac_stage<LOGA>(a, un.u, threadIdx.x, tw_s);
+        __syncthreads();
+        LaneB8 st[1];
+        body_mac_warp<LOGA>(a, un.u, warp, st, tiles + warp * TILE_B_WORDS, tw_s, rowbufs + warp * MAC_ROW_WORDS, xbuf);
+        __syncthreads();
+        body_mac_dot<LOGA>(a, un.u, threadIdx.x, xbuf, tiles);
+        if (mac_Iidx<LOGA>(a, un.u) == a.l) {
+          __syncthreads();
+          if (warp < 2) body_mac_tail<LOGA>(a, un.u, warp, st, rowbufs + warp * 2 * MAC_ROW_WORDS, tw_s, tiles);
+        }
+        break;
+      }
+      case 3: {
+        LaneA st[1];
+        body_invA_fwdA<LOGA, PRE_ROUND>(ks_args_p4<MODE>(A, sc), job, st, sm);
+        break;
+      }
+      default: {
+        LaneB8 st[1];
+        body_fwd_B<LOGA, MODE == LD_GALOIS ? EPI_MODDOWN_GALOIS : MODE == LD_PRODUCT ? EPI_MODDOWN_RELIN : EPI_RESCALE>(ks_args_p5<MODE>(A, c, sc), job, st, sm);
+        break;
+      }
+      }
+    }
+    __syncthreads(); // every warp of the unit has issued its stores (and read s_ticket)
+    // (the next ticket is NOT requested ahead of time: a held ticket would delay a unit that idle CTAs could start now)
+    if (threadIdx.x == 0) s_ticket = (int)atomicAdd(ctl0 + ctl_ticket(L), 1u);
+    if (threadIdx.x < 32) { // signals (recomputed rather than kept live across the unit body)
+      const KsUnit un = ks_decode(K, A.nct, ticket);
+      const KsDeps d = ks_deps<LOGA, MODE>(A, un);
+      if ((int)threadIdx.x < d.sig_count && (int)threadIdx.x != d.sig_skip) {
+        unsigned *ctl = reinterpret_cast<unsigned *>(A.ct[un.c].scratch + Scratch::words(L, N) - KS_CTL_WORDS);
+        __threadfence();
+        atomicAdd(ctl + d.sig_first + threadIdx.x, d.sig_inc);
+      }
+    }
+  }
+  // the last CTA to leave zeroes every counter block for the next launch on these scratch areas
+  if (threadIdx.x == 0) s_last = atomicAdd(ctl0 + ctl_nexit(L), 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last)
+    for (int cc = 0; cc < A.nct; cc++) {
+      unsigned *ctl = reinterpret_cast<unsigned *>(A.ct[cc].scratch + Scratch::words(L, N) - KS_CTL_WORDS);
+      for (int i = threadIdx.x; i < ctl_count(L); i += CTA_THREADS) ctl[i] = 0;
+    }
+}
+
 static inline int ctas_for(int njobs) { return (njobs + WARPS_PER_CTA - 1) / WARPS_PER_CTA; }
 // launch with programmatic stream serialization: the kernel may begin (twiddle staging) while its
 // predecessor drains; every such kernel executes griddepcontrol.wait before touching global data
@@ -187,6 +313,34 @@ template <int LOGA, int PRE> void GpuLauncher::invA_fwdA(const ArgsInvFwdA &a, i
   launch_pdl(k_invA_fwdA<LOGA, PRE>, ctas_for(njobs), CTA_THREADS, warp_smem<LOGA>(k_invA_fwdA<LOGA, PRE>), stream, a, njobs);
   POST_LAUNCH_S(stream);
 }
+
+static int fused_grid_cap() {
+  static const int cap = std::getenv("HEVM_FUSED_GRID") ? std::max(1, std::atoi(std::getenv("HEVM_FUSED_GRID"))) : 148 * 4;
+  return cap;
+}
+// Single ops keep the five (three) PDL-chained launches: measured on B200 (profiles/r02_fused_vs_launches.md) the
+// persistent single-launch form is SLOWER for one ciphertext (rotate l = 13: 177 us vs 147 us; l = 1: 44 vs 44 us) --
+// a phase costs 8-10 us because of the serial instruction stream of its warp jobs, not because of the launch --
+// and only pays off when one launch carries a batch of independent ciphertexts.  HEVM_FUSED=1 forces it everywhere.
+bool GpuLauncher::fused() const {
+  static const bool on = std::getenv("HEVM_FUSED") && std::atoi(std::getenv("HEVM_FUSED")) != 0;
+  return on;
+}
+template <int LOGA, int MODE> void GpuLauncher::ks_fused(const KsFusedArgs &a) {
+  const KsUnits K = ks_units<LOGA, MODE>(a);
+  if (K.total <= 0) return;
+  const size_t warp_bytes = (size_t)WARPS_PER_CTA * Geo<LOGA>::WARP_WORDS * sizeof(u64);
+  const size_t mac_bytes = MODE == FUSED_RESCALE ? 0 : mac_smem_words(a.l) * sizeof(u64);
+  static bool optin = false; // per (LOGA, MODE) instantiation
+  if (!optin) {
+    const size_t mx = std::max(warp_bytes, mac_smem_words(HEVM_MAXL) * sizeof(u64));
+    CUDA_CHECK(cudaFuncSetAttribute((const void *)k_ks_fused<LOGA, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+    optin = true;
+  }
+  PRE_LAUNCH(stream, MODE == LD_GALOIS ? KC_KS_FUSED_GALOIS : MODE == LD_PRODUCT ? KC_KS_FUSED_RELIN : KC_RESCALE_FUSED);
+  launch_pdl(k_ks_fused<LOGA, MODE>, std::min(K.total, fused_grid_cap()), CTA_THREADS, std::max(warp_bytes, mac_bytes), stream, a);
+  POST_LAUNCH_S(stream);
+}
 #define INSTANTIATE(LOGA)                                                                                              \
   template void GpuLauncher::intt_B<LOGA, LD_PLAIN>(const ArgsInttB &, int);                                           \
   template void GpuLauncher::intt_B<LOGA, LD_GALOIS>(const ArgsInttB &, int);                                          \
@@ -202,7 +356,10 @@ template <int LOGA, int PRE> void GpuLauncher::invA_fwdA(const ArgsInvFwdA &a, i
   template void GpuLauncher::fwd_B<LOGA, EPI_RESCALE>(const ArgsFwdB &, int);                                          \
   template void GpuLauncher::mac<LOGA>(const ArgsFwdB &, int);                                                         \
   template void GpuLauncher::invA_fwdA<LOGA, PRE_MODUP>(const ArgsInvFwdA &, int);                                     \
-  template void GpuLauncher::invA_fwdA<LOGA, PRE_ROUND>(const ArgsInvFwdA &, int);
+  template void GpuLauncher::invA_fwdA<LOGA, PRE_ROUND>(const ArgsInvFwdA &, int);                                     \
+  template void GpuLauncher::ks_fused<LOGA, LD_GALOIS>(const KsFusedArgs &);                                           \
+  template void GpuLauncher::ks_fused<LOGA, LD_PRODUCT>(const KsFusedArgs &);                                          \
+  template void GpuLauncher::ks_fused<LOGA, FUSED_RESCALE>(const KsFusedArgs &);
 INSTANTIATE(6)
 INSTANTIATE(7)
 INSTANTIATE(8)
@@ -312,70 +469,91 @@ void launch_elementwise(cudaStream_t s, int op, const NttTables *T, int logN, u6
 }
 
 // =====================================================================================
-// samplers: rnd(seed, stream, idx) = mix(mix(seed + G*(stream+1)) + G*(idx+1))
+// samplers (specification shared with the oracle, oracle/ckks_oracle.hpp "sampler"):
+//   rnd(key, stream, idx) = 64-bit word (idx & 7) of the ChaCha20 block with the 256-bit key, nonce = stream,
+//   block counter = idx >> 3.  One thread computes one block = the values of 8 (small) or 4 (uniform) coefficients.
 // =====================================================================================
-__device__ __forceinline__ u64 mix64(u64 z) {
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
+__device__ __forceinline__ u32 rotl32(u32 v, int c) { return __funnelshift_l(v, v, c); }
+__device__ __forceinline__ void chacha20_block(const Seed256 &key, u64 nonce, u64 counter, u64 (&out)[8]) {
+  u32 x[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key.k[0], key.k[1], key.k[2], key.k[3], key.k[4], key.k[5], key.k[6],
+               key.k[7], (u32)counter, (u32)(counter >> 32), (u32)nonce, (u32)(nonce >> 32)};
+  u32 in[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) in[i] = x[i];
+#define QR(a, b, c, d)                                                                                                 \
+  x[a] += x[b], x[d] = rotl32(x[d] ^ x[a], 16), x[c] += x[d], x[b] = rotl32(x[b] ^ x[c], 12), x[a] += x[b],            \
+      x[d] = rotl32(x[d] ^ x[a], 8), x[c] += x[d], x[b] = rotl32(x[b] ^ x[c], 7)
+#pragma unroll 1
+  for (int r = 0; r < 10; r++) {
+    QR(0, 4, 8, 12), QR(1, 5, 9, 13), QR(2, 6, 10, 14), QR(3, 7, 11, 15);
+    QR(0, 5, 10, 15), QR(1, 6, 11, 12), QR(2, 7, 8, 13), QR(3, 4, 9, 14);
+  }
+#undef QR
+#pragma unroll
+  for (int j = 0; j < 8; j++) out[j] = (u64)(x[2 * j] + in[2 * j]) | ((u64)(x[2 * j + 1] + in[2 * j + 1]) << 32);
 }
-__device__ __forceinline__ u64 rnd64(u64 seed, u64 stream, u64 idx) {
-  const u64 G = 0x9E3779B97F4A7C15ull;
-  return mix64(mix64(seed + G * (stream + 1)) + G * (idx + 1));
+__device__ __forceinline__ int small_from_word(u64 w, int cbd) {
+  return cbd ? __popcll(w & 0x1FFFFF) - __popcll((w >> 21) & 0x1FFFFF) : (int)(w % 3) - 1;
 }
 template <int CBD>
-__global__ void k_sample_small(const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream, const u64 *ctr) {
+__global__ void k_sample_small(const NttTables *T, int logN, u64 *out, int limbs, Seed256 key, u64 stream, const u64 *ctr) {
   const size_t N = (size_t)1 << logN;
   if (ctr) stream += *ctr * 4; // encryption counter base kept on the device (graph replays advance it)
-  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < N; k += (size_t)gridDim.x * blockDim.x) {
-    const u64 w = rnd64(seed, stream, k);
-    int t;
-    if (CBD)
-      t = __popcll(w & 0x1FFFFF) - __popcll((w >> 21) & 0x1FFFFF);
-    else
-      t = (int)(w % 3) - 1;
-    for (int i = 0; i < limbs; i++) out[(size_t)i * N + k] = t < 0 ? T->mod[i].q - (u64)(-t) : (u64)t;
+  for (size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x; b < N / 8; b += (size_t)gridDim.x * blockDim.x) {
+    u64 w[8];
+    chacha20_block(key, stream, b, w);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int t = small_from_word(w[j], CBD);
+      for (int i = 0; i < limbs; i++) out[(size_t)i * N + 8 * b + j] = t < 0 ? T->mod[i].q - (u64)(-t) : (u64)t;
+    }
   }
 }
 // the three small polynomials of one public-key encryption in one launch: blockIdx.y = 0 ternary u (stream0),
 // 1 and 2 the centred-binomial errors e0, e1 (stream0 + 1, + 2); out = [3][limbs][N]; same values as three
 // k_sample_small launches
-__global__ void k_sample_enc(const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream0, const u64 *ctr) {
+__global__ void k_sample_enc(const NttTables *T, int logN, u64 *out, int limbs, Seed256 key, u64 stream0, const u64 *ctr) {
   const size_t N = (size_t)1 << logN;
   const int which = blockIdx.y;
   u64 stream = stream0 + which;
   if (ctr) stream += *ctr * 4;
   u64 *o = out + (size_t)which * limbs * N;
-  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < N; k += (size_t)gridDim.x * blockDim.x) {
-    const u64 w = rnd64(seed, stream, k);
-    const int t = which ? __popcll(w & 0x1FFFFF) - __popcll((w >> 21) & 0x1FFFFF) : (int)(w % 3) - 1;
-    for (int i = 0; i < limbs; i++) o[(size_t)i * N + k] = t < 0 ? T->mod[i].q - (u64)(-t) : (u64)t;
+  for (size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x; b < N / 8; b += (size_t)gridDim.x * blockDim.x) {
+    u64 w[8];
+    chacha20_block(key, stream, b, w);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int t = small_from_word(w[j], which != 0);
+      for (int i = 0; i < limbs; i++) o[(size_t)i * N + 8 * b + j] = t < 0 ? T->mod[i].q - (u64)(-t) : (u64)t;
+    }
   }
 }
 static int ew_grid(size_t nthreads);
-void launch_sample_enc(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream0, const u64 *ctr) {
-  k_sample_enc<<<dim3(ew_grid((size_t)1 << logN), 3), 256, 0, s>>>(T, logN, out, limbs, seed, stream0, ctr);
+void launch_sample_enc(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, const Seed256 &key, u64 stream0, const u64 *ctr) {
+  k_sample_enc<<<dim3(ew_grid(((size_t)1 << logN) / 8), 3), 256, 0, s>>>(T, logN, out, limbs, key, stream0, ctr);
   POST_LAUNCH_S(s);
 }
-__global__ void k_sample_uniform(const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream_base) {
-  const size_t N = (size_t)1 << logN, total = N * limbs;
+__global__ void k_sample_uniform(const NttTables *T, int logN, u64 *out, int limbs, Seed256 key, u64 stream_base) {
+  const size_t N = (size_t)1 << logN, total = (N / 4) * limbs; // one ChaCha block = the (hi, lo) pairs of 4 coefficients
   for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < total; v += (size_t)gridDim.x * blockDim.x) {
-    const int i = (int)(v >> logN);
-    const size_t k = v & (N - 1);
-    const u64 hi = rnd64(seed, stream_base + i, 2 * k), lo = rnd64(seed, stream_base + i, 2 * k + 1);
-    out[v] = reduce128(lo, hi, T->mod[i]);
+    const int i = (int)(v / (N / 4));
+    const size_t b = v - (size_t)i * (N / 4);
+    u64 w[8];
+    chacha20_block(key, stream_base + i, b, w);
+#pragma unroll
+    for (int j = 0; j < 4; j++) out[(size_t)i * N + 4 * b + j] = reduce128(w[2 * j + 1], w[2 * j], T->mod[i]);
   }
 }
-void launch_sample_ternary(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream, const u64 *ctr) {
-  k_sample_small<0><<<ew_grid((size_t)1 << logN), 256, 0, s>>>(T, logN, out, limbs, seed, stream, ctr);
+void launch_sample_ternary(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, const Seed256 &key, u64 stream, const u64 *ctr) {
+  k_sample_small<0><<<ew_grid(((size_t)1 << logN) / 8), 256, 0, s>>>(T, logN, out, limbs, key, stream, ctr);
   POST_LAUNCH_S(s);
 }
-void launch_sample_cbd(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream, const u64 *ctr) {
-  k_sample_small<1><<<ew_grid((size_t)1 << logN), 256, 0, s>>>(T, logN, out, limbs, seed, stream, ctr);
+void launch_sample_cbd(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, const Seed256 &key, u64 stream, const u64 *ctr) {
+  k_sample_small<1><<<ew_grid(((size_t)1 << logN) / 8), 256, 0, s>>>(T, logN, out, limbs, key, stream, ctr);
   POST_LAUNCH_S(s);
 }
-void launch_sample_uniform(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream_base) {
-  k_sample_uniform<<<ew_grid((size_t)limbs << logN), 256, 0, s>>>(T, logN, out, limbs, seed, stream_base);
+void launch_sample_uniform(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, const Seed256 &key, u64 stream_base) {
+  k_sample_uniform<<<ew_grid(((size_t)limbs << logN) / 4), 256, 0, s>>>(T, logN, out, limbs, key, stream_base);
   POST_LAUNCH_S(s);
 }
 

@@ -24,7 +24,7 @@ extern bool g_pdl_suspended; // set while run() is being captured into a CUDA gr
 enum {
   KC_INTT_B_PLAIN = 0, KC_INTT_B_GALOIS, KC_INTT_B_PRODUCT, KC_INTT_A, KC_FWD_A_NONE, KC_FWD_A_MODUP, KC_FWD_A_ROUND,
   KC_FWD_B_CANON, KC_FWD_B_MAC, KC_FWD_B_MODDOWN_GALOIS, KC_FWD_B_MODDOWN_RELIN, KC_FWD_B_RESCALE, KC_INVA_FWDA_MODUP, KC_INVA_FWDA_ROUND, KC_ELEMENTWISE,
-  KC_OTHER, KC_COUNT
+  KC_KS_FUSED_GALOIS, KC_KS_FUSED_RELIN, KC_RESCALE_FUSED, KC_OTHER, KC_COUNT
 };
 extern const char *const g_kernel_class_names[KC_COUNT];
 struct KProfiler {
@@ -51,6 +51,9 @@ struct GpuLauncher {
   template <int LOGA, int EPI> void fwd_B(const ArgsFwdB &a, int njobs);
   template <int LOGA, int PRE> void invA_fwdA(const ArgsInvFwdA &a, int njobs);
   template <int LOGA> void mac(const ArgsFwdB &a, int njobs); // one 4-warp CTA per job
+  // single-launch key switch / rescale (ks_fused.cuh); HEVM_FUSED=0 falls back to the separate launches
+  bool fused() const;
+  template <int LOGA, int MODE> void ks_fused(const KsFusedArgs &a);
 };
 
 // ---- element-wise ciphertext kernels (SEAL add/negate/add_plain/multiply_plain, limb drop) ----
@@ -66,14 +69,17 @@ enum { EW_ADD = 0, EW_NEG = 1, EW_ADDP = 2, EW_MULP = 3, EW_COPY = 4, EW_MULP_AD
 void launch_elementwise(cudaStream_t s, int op, const NttTables *T, int logN, u64 *out, const u64 *a, const u64 *b,
                         const u64 *p, size_t pitch, int l);
 
-// ---- samplers (specification shared with the oracle: oracle/ckks_oracle.hpp "sampler") ----
-void launch_sample_ternary(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream, const u64 *ctr = nullptr);
-void launch_sample_cbd(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream, const u64 *ctr = nullptr);
-void launch_sample_uniform(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream_base);
+// ---- samplers (specification shared with the oracle: oracle/ckks_oracle.hpp "sampler"): ChaCha20 keyed by 256 bits ----
+struct Seed256 {
+  u32 k[8];
+};
+void launch_sample_ternary(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, const Seed256 &key, u64 stream, const u64 *ctr = nullptr);
+void launch_sample_cbd(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, const Seed256 &key, u64 stream, const u64 *ctr = nullptr);
+void launch_sample_uniform(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, const Seed256 &key, u64 stream_base);
 
 // ---- key generation / encryption helpers ----
 // c0[i] = -(c1[i]*sk[i] + e[i]); if (digit >= 0 && i == digit) c0[i] += (p mod q_i) * newkey[i]
-void launch_sample_enc(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, u64 seed, u64 stream0, const u64 *ctr);
+void launch_sample_enc(cudaStream_t s, const NttTables *T, int logN, u64 *out, int limbs, const Seed256 &key, u64 stream0, const u64 *ctr);
 void launch_key_split(cudaStream_t s, u64 *key, size_t words);
 void launch_ksk_finish(cudaStream_t s, const NttTables *T, int logN, int L, u64 *c0, const u64 *c1, const u64 *sk,
                        const u64 *e, const u64 *newkey, int digit);

@@ -7,27 +7,7 @@
 //   keyswitch : Evaluator::switch_key_inplace   (rotate: SEAL_HEVM.cpp:273, mulcc+relin: 315-316)
 //   rescale   : RNSTool::divide_and_round_q_last_ntt_inplace (SEAL_HEVM.cpp:283, also inside encrypt)
 #pragma once
-#include "ntt_bodies.cuh"
-
-struct Scratch {      // device (or emulator-host) buffers, sized for the top level
-  u64 *s1 = nullptr;  // [L][N]      inverse pass-B output
-  u64 *t = nullptr;   // [L][N]      coefficient-form digits / rounding term
-  u64 *s2 = nullptr;  // [L][L-1][N] forward pass-A output of every (I,J) digit  (also NTT staging)
-  u64 *acc = nullptr; // [2][L][N]   key-switch accumulators
-  u64 *s4 = nullptr;  // [2][L][N]   forward pass-A output of the rounding terms
-  u64 *pc0 = nullptr; // [L][N]      permuted c0 (rotate)
-  u64 *rnd = nullptr; // [2][N]      limb-sharded key switch: rounded special-limb coefficients (broadcast by their owner)
-  static size_t words(int L, size_t N) { return ((size_t)L + L + (size_t)L * (L - 1) + 2 * L + 2 * L + L + 2) * N; }
-  void carve(u64 *base, int L, size_t N) {
-    s1 = base;
-    t = s1 + (size_t)L * N;
-    s2 = t + (size_t)L * N;
-    acc = s2 + (size_t)L * (L - 1) * N;
-    s4 = acc + (size_t)2 * L * N;
-    pc0 = s4 + (size_t)2 * L * N;
-    rnd = pc0 + (size_t)L * N;
-  }
-};
+#include "ks_fused.cuh"
 
 // ring-size independent interface (the VM holds one of these per lane)
 struct OpsIface {
@@ -45,6 +25,10 @@ struct OpsIface {
   // (target l = the special prime); between the stages the caller exchanges sc.t (all-gather) and sc.rnd (broadcast)
   // mode LD_GALOIS: rotation of ciphertext `a` (b unused); mode LD_PRODUCT: multiply a*b + relinearise
   virtual void ks_shard_stage(int stage, int mode, const u64 *a, const u64 *b, u64 *dst, size_t pitch, int l, const u64 *key, u32 elt, int tlo, int thi) = 0;
+  // batched single-launch forms (independent ciphertexts of one level in ONE kernel; every item brings its own scratch
+  // area, see KsCt): key switch of `n` ciphertexts / rescale of `n` ciphertexts (item.a = source, item.b = optional plaintext)
+  virtual void keyswitch_batch(int mode, int n, const KsCt *items, size_t pitch, int l) = 0;
+  virtual void rescale_batch(int n, const KsCt *items, size_t src_pitch, size_t dst_pitch, int l) = 0;
 };
 
 template <class LA, int LOGA> struct HeOps : OpsIface {
@@ -115,6 +99,11 @@ template <class LA, int LOGA> struct HeOps : OpsIface {
   // `pitch` = words between the two polys of every ciphertext operand.  dst may alias a or b.
   // Five launches: B' | A'+mod-up+A | B+MAC(+B' of the special limb) | A'+round+A | B+mod-down epilogue
   void keyswitch(int mode, const u64 *a, const u64 *b, u64 *dst, size_t pitch, int l, const u64 *key, u32 elt) override {
+    if (la.fused()) { // one persistent launch (ks_fused.cuh)
+      KsCt it{a, b, dst, key, sc.s1, elt, 0};
+      keyswitch_batch(mode, 1, &it, pitch, l);
+      return;
+    }
     // 1. inverse pass B of the target, fused with the Galois gather / the tensor product d2
     {
       ArgsInttB x{};
@@ -159,6 +148,30 @@ template <class LA, int LOGA> struct HeOps : OpsIface {
         w.add0 = a, w.add1 = b;
         la.template fwd_B<LOGA, EPI_MODDOWN_RELIN>(w, l * ROWS);
       }
+    }
+  }
+
+  void keyswitch_batch(int mode, int n, const KsCt *items, size_t pitch, int l) override {
+    for (int done = 0; done < n; done += KS_MAX_BATCH) {
+      KsFusedArgs x{};
+      x.T = T, x.l = l, x.sp = sp(), x.Ltot = L, x.pitch = pitch;
+      x.nct = n - done < KS_MAX_BATCH ? n - done : KS_MAX_BATCH;
+      x.ng2 = pick_groups(l, l + 1), x.ng4 = pick_groups(2, l);
+      for (int k = 0; k < x.nct; k++) x.ct[k] = items[done + k];
+      if (mode == LD_GALOIS)
+        la.template ks_fused<LOGA, LD_GALOIS>(x);
+      else
+        la.template ks_fused<LOGA, LD_PRODUCT>(x);
+    }
+  }
+  void rescale_batch(int n, const KsCt *items, size_t src_pitch, size_t dst_pitch, int l) override {
+    for (int done = 0; done < n; done += KS_MAX_BATCH) {
+      KsFusedArgs x{};
+      x.T = T, x.l = l, x.sp = sp(), x.Ltot = L, x.pitch = dst_pitch, x.spitch = src_pitch;
+      x.nct = n - done < KS_MAX_BATCH ? n - done : KS_MAX_BATCH;
+      x.ng2 = 1, x.ng4 = pick_groups(2, l - 1);
+      for (int k = 0; k < x.nct; k++) x.ct[k] = items[done + k];
+      la.template ks_fused<LOGA, FUSED_RESCALE>(x);
     }
   }
 
@@ -224,6 +237,11 @@ template <class LA, int LOGA> struct HeOps : OpsIface {
   // ---- rescale: 2 polys with l limbs -> l-1 limbs (divide by q_{l-1} and round); three launches -------
   // src/dst poly pitches may differ (encrypt uses a compact (l)-limb temporary).
   void rescale(const u64 *src, size_t src_pitch, u64 *dst, size_t dst_pitch, int l, const u64 *add_pt = nullptr) override {
+    if (la.fused()) {
+      KsCt it{src, add_pt, dst, nullptr, sc.s1, 0, 0};
+      rescale_batch(1, &it, src_pitch, dst_pitch, l);
+      return;
+    }
     {
       ArgsInttB x{};
       x.T = T, x.src = src + (size_t)(l - 1) * N, x.sstride = src_pitch, x.dst = sc.s1, x.nl = 2, x.prime0 = l - 1, x.pstep = 0;

@@ -12,6 +12,7 @@
 #include "kernels.h"
 #include <cmath>
 #include <cuda_profiler_api.h>
+#include <nvtx3/nvToolsExt.h> // header-only NVTX v3: one range per HEVM opcode class
 #include <complex>
 #include <cstring>
 #include <fstream>
@@ -19,6 +20,7 @@
 #include <algorithm>
 #include <map>
 #include <random>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -43,10 +45,11 @@ struct HevmOp {
   uint16_t opcode, dst, lhs, rhs;
 };
 #pragma pack(pop)
-struct ParamFile { // <dir>/hevm_params.bin : ring geometry + key seed (own format; SURVEY 8b "Files consumed")
-  uint64_t magic, logN, L, bits, seed;
+struct ParamFile { // <dir>/hevm_params.bin : ring geometry + 256-bit key seed (own format, version 2; SURVEY 8b "Files consumed")
+  uint64_t magic, logN, L, bits;
+  uint32_t seed[8];
 };
-const uint64_t PARAM_MAGIC = 0x3030324D56454842ull;
+const uint64_t PARAM_MAGIC = 0x3230324D56454842ull;
 
 // sampler stream ids (specification shared with the oracle)
 inline u64 ksk_stream(u64 key_id, u64 digit, u64 kind, u64 limb) { return (((key_id * 64 + digit) * 2 + kind) * 64 + limb) + (16ull << 20); }
@@ -96,7 +99,12 @@ struct VM {
   hp::HostParams P;
   int logN = 0, L = 0;
   size_t N = 0, pitch = 0;
-  u64 seed = 0, enc_counter = 0;
+  // Key material comes from the 256-bit seed of the parameter file through a keyed ChaCha20 PRF; the encryption
+  // randomness (u, e0, e1 of every encrypt / bootstrap) uses a separate key that is FRESH PER VM (std::random_device)
+  // -- two processes sharing a key directory never encrypt with the same randomness -- unless a parity test pins it
+  // to the key seed with hevmx_set_enc_counter.
+  Seed256 seed{}, enc_seed{};
+  u64 enc_counter = 0;
   u64 *d_ctr_base = nullptr; // device copy of the encryption counter base (read by the samplers)
   std::vector<Lane> lanes;
   Lane *ln = nullptr; // lane the host code is currently issuing on
@@ -114,6 +122,11 @@ struct VM {
   // register renaming: logical ciphertext register -> physical buffer.  `home[r]` is the identity buffer of
   // register r (where encrypt / ct_write put data and where every run() starts); `spare` are extra buffers.
   std::vector<u64 *> home, spare, final_map;
+  // register metadata (level, scale) of every ciphertext register when the graph was captured: `entry_meta` is what the
+  // captured kernels were specialised for (a replay is only valid from the same entry state of the registers the
+  // program reads before writing), `final_meta` is what a run leaves behind (restored after every replay)
+  std::vector<std::pair<int, double>> entry_meta, final_meta;
+  std::vector<char> live_in;
   bool use_graph = true;
   // program
   std::vector<std::vector<double>> consts;
@@ -127,13 +140,23 @@ struct VM {
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
 
   // ---------------------------------------------------------------- setup
+  u64 *new_scratch() { // one NTT scratch area; the fused kernels' completion counters at its end start out (and stay) zero
+    u64 *p = dalloc<u64>(Scratch::words(L, N));
+    CUDA_CHECK(cudaMemset(p + Scratch::words(L, N) - KS_CTL_WORDS, 0, KS_CTL_WORDS * sizeof(u64)));
+    return p;
+  }
   void init(const ParamFile &pf) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) die("no CUDA device visible: libB200_HEVM.so has no CPU path");
     if (const char *e = std::getenv("HEVM_DEVICE")) CUDA_CHECK(cudaSetDevice(std::atoi(e)));
     if (pf.logN < 14 || pf.logN > 17) die("supported ring sizes: N = 2^14 .. 2^17 (HEVM_LOGN = 14..17)");
     if (pf.L < 2 || pf.L > HEVM_MAXL) die("number of primes out of range");
-    logN = (int)pf.logN, L = (int)pf.L, N = (size_t)1 << logN, seed = pf.seed;
+    logN = (int)pf.logN, L = (int)pf.L, N = (size_t)1 << logN;
+    std::memcpy(seed.k, pf.seed, sizeof seed.k);
+    {
+      std::random_device rd;
+      for (auto &w : enc_seed.k) w = rd();
+    }
     pitch = (size_t)(L - 1) * N;
     P.build(logN, L, (int)pf.bits);
     Tw *d_tw = upload(P.tw), *d_itw = upload(P.itw);
@@ -154,7 +177,7 @@ struct VM {
       CUDA_CHECK(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
       l.la.stream = l.stream;
       l.ops = make_ops(l.la, dT, logN, L);
-      l.ops->sc.carve(dalloc<u64>(Scratch::words(L, N)), L, N);
+      l.ops->sc.carve(new_scratch(), L, N);
       l.d_work = dalloc<double2>(N);
       l.d_maxbits = dalloc<unsigned long long>(1);
       l.d_vals = dalloc<double>(slots);
@@ -289,6 +312,18 @@ struct VM {
       elts.push_back(posp), posp = (posp * posp) & (m - 1);
       elts.push_back(negp), negp = (negp * negp) & (m - 1);
     }
+    // HEVM_GALOIS_STEPS="1,-2,64": only these rotation steps get a key (SEAL KeyGenerator::create_galois_keys(steps));
+    // unset = the default set of create_galois_keys() that the reference uses (SEAL_HEVM.cpp:82-83)
+    if (const char *e = std::getenv("HEVM_GALOIS_STEPS")) {
+      elts.clear();
+      for (const char *p = e; *p;) {
+        char *end = nullptr;
+        const long st = std::strtol(p, &end, 10);
+        if (end == p) break;
+        elts.push_back(galois_elt_from_step((int)st));
+        p = (*end == ',') ? end + 1 : end;
+      }
+    }
     for (u64 elt : elts) {
       if (d_gal.count(elt)) continue;
       launch_galois_gather(ln->stream, logN, L, nk, d_sk, (u32)elt);
@@ -354,7 +389,7 @@ struct VM {
     const u64 counter = k;
     // u, e0, e1 live back to back in d_ue ([3][nl][N]) so that one launch pair transforms all three
     u64 *u = ln->d_ue, *e01 = ln->d_ue + (size_t)nl * N;
-    launch_sample_enc(ln->stream, dT, logN, u, nl, seed, enc_stream(counter, 0), d_ctr_base); // streams +0 (u), +1, +2 (e0, e1)
+    launch_sample_enc(ln->stream, dT, logN, u, nl, enc_seed, enc_stream(counter, 0), d_ctr_base); // streams +0 (u), +1, +2 (e0, e1)
     if (3 * nl <= L * (L - 1)) {
       ln->ops->ntt_fwd(u, u, 3 * nl, 0, 1, nl);
     } else {
@@ -414,7 +449,17 @@ struct VM {
   u64 boot_index = 0; // encryptions issued so far inside the current run()
   double shard_scale = 0; // hevmx_mulcc_shard_stage: result scale computed at stage 1
   bool meta_only = false; // exec() of addcc / mulcp updates register metadata only (their kernels were fused by the scheduler)
+  struct NvtxRange { // host-side range around the issue of one op (visible in Nsight Systems; free when no tool is attached)
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+  };
+  static const char *op_class_name(unsigned opcode) {
+    static const char *const names[11] = {"hevm.encode", "hevm.rotate", "hevm.negate", "hevm.rescale", "hevm.modswitch", "hevm.upscale",
+                                          "hevm.addcc", "hevm.addcp", "hevm.mulcc", "hevm.mulcp", "hevm.bootstrap"};
+    return opcode < 11 ? names[opcode] : "hevm.placeholder";
+  }
   void exec(const HevmOp &op) {
+    NvtxRange nvtx(op_class_name(op.opcode));
     switch (op.opcode) {
     case 1: { // rotate
       CtReg &s = ctr(op.lhs), &d = ctr(op.dst);
@@ -520,6 +565,59 @@ struct VM {
     }
   }
 
+  // ---------------------------------------------------------------- batched ops (independent ciphertexts, one launch)
+  // n independent ops of one opcode whose sources sit at the same level: rotate (single key-switch steps), mulcc and
+  // rescale go out as ONE persistent kernel over all n ciphertexts (ks_fused.cuh; BASELINE configs[1] "batched
+  // ciphertexts"); everything else, and any batch that does not qualify, is issued op by op.
+  std::vector<u64 *> batch_scratch;
+  u64 *scratch_for(size_t k) {
+    while (batch_scratch.size() <= k) batch_scratch.push_back(new_scratch());
+    return batch_scratch[k];
+  }
+  void exec_batch(int opcode, int n, const int64_t *dst, const int64_t *lhs, const int64_t *rhs) {
+    bool ok = (opcode == 1 || opcode == 3 || opcode == 8) && n > 1;
+    int lvl = 0;
+    std::vector<KsCt> items;
+    for (int k = 0; ok && k < n; k++) {
+      CtReg &a = ctr((size_t)lhs[k]), &d = ctr((size_t)dst[k]);
+      if (k == 0) lvl = a.level;
+      if (a.level != lvl || lvl < (opcode == 3 ? 2 : 1)) ok = false;
+      for (int j = 0; ok && j < k; j++) // not independent: an item writes what another item reads or writes
+        if (dst[j] == dst[k] || dst[j] == lhs[k] || dst[k] == lhs[j] || (opcode == 8 && (dst[j] == rhs[k] || dst[k] == rhs[j]))) ok = false;
+      if (!ok) break;
+      KsCt it{a.d, nullptr, d.d, nullptr, scratch_for((size_t)k), 0, 0};
+      if (opcode == 1) {
+        std::vector<int> steps;
+        rotate_steps((int16_t)rhs[k], steps);
+        if (steps.size() != 1) {
+          ok = false;
+          break;
+        }
+        const u64 elt = galois_elt_from_step(steps[0]);
+        it.key = d_gal.at(elt), it.elt = (u32)elt;
+      } else if (opcode == 8) {
+        CtReg &b = ctr((size_t)rhs[k]);
+        if (b.level != lvl) ok = false;
+        it.b = b.d, it.key = d_relin;
+      }
+      items.push_back(it);
+    }
+    if (!ok) {
+      for (int k = 0; k < n; k++) exec(HevmOp{(uint16_t)opcode, (uint16_t)dst[k], (uint16_t)lhs[k], (uint16_t)rhs[k]});
+      return;
+    }
+    if (opcode == 3)
+      ln->ops->rescale_batch(n, items.data(), pitch, pitch, lvl);
+    else
+      ln->ops->keyswitch_batch(opcode == 1 ? LD_GALOIS : LD_PRODUCT, n, items.data(), pitch, lvl);
+    for (int k = 0; k < n; k++) { // register metadata, as exec() would have left it
+      CtReg &a = ctr((size_t)lhs[k]), &d = ctr((size_t)dst[k]);
+      if (opcode == 1) d.level = lvl, d.scale = a.scale;
+      if (opcode == 3) d.scale = a.scale / (double)P.q[lvl - 1], d.level = lvl - 1;
+      if (opcode == 8) d.scale = a.scale * ctr((size_t)rhs[k]).scale, d.level = lvl;
+    }
+  }
+
   // ---------------------------------------------------------------- run(): multi-lane schedule + CUDA graph
   // The program is static, so run() is issued once as a dependency-respecting schedule over the lanes
   // (independent ciphertext ops overlap on the GPU) while being captured into a CUDA graph; later
@@ -542,6 +640,21 @@ struct VM {
     case 3: return 14.0 + 1.1 * level;
     case 10: return 178.0 + 4.0 * level;
     default: return 3.5 + 0.25 * level;
+    }
+  }
+  // registers the program reads before (or without) writing them: their level / scale at entry shapes the schedule
+  void compute_live_in() {
+    live_in.assign(ct.size(), 0);
+    std::vector<char> written(ct.size(), 0);
+    auto rd = [&](unsigned r) {
+      if (r < ct.size() && !written[r]) live_in[r] = 1;
+    };
+    for (const HevmOp &o : prog) {
+      const bool ct_op = ((o.opcode >= 1 && o.opcode <= 4) || (o.opcode >= 6 && o.opcode <= 10)) && !(o.opcode == 4 && (int16_t)o.rhs <= 0);
+      if (!ct_op) continue;
+      rd(o.lhs);
+      if (o.opcode == 6 || o.opcode == 8) rd(o.rhs);
+      if (o.dst < ct.size()) written[o.dst] = 1;
     }
   }
   void invalidate_graph() {
@@ -576,7 +689,11 @@ struct VM {
       std::vector<std::pair<int, cudaEvent_t>> readers;
     };
     std::map<u64 *, BufState> bs;
-    std::vector<u64 *> pool(spare.begin(), spare.end()); // FIFO of free physical buffers (oldest first)
+    // FIFO of free physical buffers (oldest first).  Only SPARE buffers circulate: a register's home buffer is where
+    // encrypt() / hevmx_ct_write put data between runs, so it must never end up backing another register.
+    std::vector<u64 *> pool(spare.begin(), spare.end());
+    const std::set<u64 *> home_set(home.begin(), home.end());
+    auto is_home = [&](u64 *b) { return home_set.count(b) != 0; };
     size_t pool_head = 0;
     reset_mapping();
     for (Lane &l : lanes) l.load = 0;
@@ -595,7 +712,8 @@ struct VM {
       std::vector<char> live(ct.size(), 1);
       for (size_t i = prog.size(); on && i-- > 0;) {
         const HevmOp &o = prog[i];
-        const bool writes = (o.opcode >= 1 && o.opcode <= 4) || (o.opcode >= 6 && o.opcode <= 10);
+        // (modswitch with downFactor <= 0 leaves dst untouched, SEAL_HEVM.cpp:288-292: not a write, not a read)
+        const bool writes = ((o.opcode >= 1 && o.opcode <= 4) || (o.opcode >= 6 && o.opcode <= 10)) && !(o.opcode == 4 && (int16_t)o.rhs <= 0);
         if (!writes || o.dst >= ct.size()) continue;
         if (i > 0 && o.opcode == 6 && prog[i - 1].opcode == 9 && o.lhs < ct.size() && o.rhs < ct.size()) {
           const HevmOp &m = prog[i - 1];
@@ -622,7 +740,7 @@ struct VM {
       const int D = prog[pc + 1].dst;
       for (size_t j = pc + 2; j < prog.size() && j < pc + 2 + 96; j++) {
         const HevmOp &o = prog[j];
-        const bool ct_op = (o.opcode >= 1 && o.opcode <= 4) || (o.opcode >= 6 && o.opcode <= 10);
+        const bool ct_op = ((o.opcode >= 1 && o.opcode <= 4) || (o.opcode >= 6 && o.opcode <= 10)) && !(o.opcode == 4 && (int16_t)o.rhs <= 0);
         if (!ct_op) continue;
         const bool two = o.opcode == 6 || o.opcode == 8;
         if (fuse[j]) {
@@ -681,7 +799,7 @@ struct VM {
       u64 *old_buf = ct[wr].d, *dst_buf = old_buf;
       if (pool_head < pool.size()) {
         dst_buf = pool[pool_head++];
-        pool.push_back(old_buf);
+        if (!is_home(old_buf)) pool.push_back(old_buf);
       }
       for (u64 *b : srcs) wait_on(bs[b].wr_lane, bs[b].wr);
       BufState &D = bs[dst_buf];
@@ -784,7 +902,7 @@ struct VM {
       u64 *old_buf = ct[wr].d, *dst_buf = old_buf;
       if (pool_head < pool.size()) {
         dst_buf = pool[pool_head++];
-        pool.push_back(old_buf);
+        if (!is_home(old_buf)) pool.push_back(old_buf);
       }
       for (int k = 0; k < nrd; k++) wait_on(bs[src_buf[k]].wr_lane, bs[src_buf[k]].wr); // RAW
       BufState &D = bs[dst_buf];
@@ -840,7 +958,19 @@ struct VM {
     ln = &lanes[0];
     preallocate_registers();
     CUDA_CHECK(cudaMemcpyAsync(d_ctr_base, &enc_counter, 8, cudaMemcpyHostToDevice, lanes[0].stream));
-    if (g_prof.on || lanes.size() == 1 && !use_graph) { // kernel-class profiling / plain mode: in order on lane 0
+    if (debug) { // setDebug(true): the reference's per-op trace (SEAL_HEVM.cpp:340-350, 270-271), ops in program order
+      boot_index = 0;
+      reset_mapping();
+      long i = (long)((head.head_size + cfg.body_len) / 8), j = 0;
+      for (auto &op : prog) {
+        std::printf("\n%lo %ld\nopcode [%u], dst [%u], lhs [%u], rhs [%u]\n", i++, j++, (unsigned)op.opcode, (unsigned)op.dst, (unsigned)op.lhs,
+                    (unsigned)op.rhs);
+        if (op.opcode == 1 && op.lhs < ct.size()) std::printf("%g\n", std::log2(ct[op.lhs].scale));
+        exec(op);
+      }
+      std::fflush(stdout);
+      enc_counter += boot_index;
+    } else if (g_prof.on || lanes.size() == 1 && !use_graph) { // kernel-class profiling / plain mode: in order on lane 0
       boot_index = 0;
       reset_mapping();
       for (auto &op : prog) exec(op);
@@ -849,7 +979,14 @@ struct VM {
       issue_scheduled();
       enc_counter += boot_index;
     } else {
+      if (graph_exec) { // the captured kernels are specialised for the entry levels of the live-in registers
+        for (size_t r = 0; r < ct.size() && graph_exec; r++)
+          if (live_in[r] && (ct[r].level != entry_meta[r].first || ct[r].scale != entry_meta[r].second)) invalidate_graph();
+      }
       if (!graph_exec) {
+        compute_live_in();
+        entry_meta.resize(ct.size());
+        for (size_t r = 0; r < ct.size(); r++) entry_meta[r] = {ct[r].level, ct[r].scale};
         cudaGraph_t g = nullptr;
         g_pdl_suspended = true;
         const unsigned long long c0 = g_launch_count;
@@ -862,9 +999,14 @@ struct VM {
         CUDA_CHECK(cudaGraphInstantiate(&graph_exec, g, 0));
         CUDA_CHECK(cudaGraphDestroy(g));
         graph_nboot = (int)boot_index;
+        final_meta.resize(ct.size());
+        for (size_t r = 0; r < ct.size(); r++) final_meta[r] = {ct[r].level, ct[r].scale};
       }
       CUDA_CHECK(cudaGraphLaunch(graph_exec, lanes[0].stream));
-      for (size_t r = 0; r < final_map.size(); r++) ct[r].d = final_map[r]; // where the replay leaves each register
+      for (size_t r = 0; r < final_map.size(); r++) { // where (and in which state) the replay leaves each register
+        ct[r].d = final_map[r];
+        ct[r].level = final_meta[r].first, ct[r].scale = final_meta[r].second;
+      }
       g_launch_count += graph_launches; // every replay executes all recorded kernels
       enc_counter += graph_nboot;
     }
@@ -893,11 +1035,12 @@ void create_context(char *dir) {
   pf.logN = (e = std::getenv("HEVM_LOGN")) ? std::strtoull(e, nullptr, 10) : 15;
   pf.L = (e = std::getenv("HEVM_NUM_PRIMES")) ? std::strtoull(e, nullptr, 10) : 14;
   pf.bits = (e = std::getenv("HEVM_PRIME_BITS")) ? std::strtoull(e, nullptr, 10) : 60;
-  if ((e = std::getenv("HEVM_SEED")))
-    pf.seed = std::strtoull(e, nullptr, 0);
-  else {
+  if ((e = std::getenv("HEVM_SEED"))) { // tests: a fixed, public seed
+    const uint64_t v = std::strtoull(e, nullptr, 0);
+    pf.seed[0] = (uint32_t)v, pf.seed[1] = (uint32_t)(v >> 32);
+  } else {
     std::random_device rd;
-    pf.seed = ((uint64_t)rd() << 32) ^ rd();
+    for (auto &w : pf.seed) w = rd();
   }
   std::ofstream f(std::string(dir) + "/hevm_params.bin", std::ios::binary);
   if (!f) die("create_context: cannot write hevm_params.bin");
@@ -1003,7 +1146,7 @@ int64_t hevmx_param(void *h, int what) {
   switch (what) {
   case 0: return vm->logN;
   case 1: return vm->L;
-  case 2: return (int64_t)vm->seed;
+  case 2: return (int64_t)(vm->seed.k[0] | ((uint64_t)vm->seed.k[1] << 32));
   case 3: return (int64_t)vm->ct.size();
   case 4: return (int64_t)vm->pt.size();
   case 5: return (int64_t)vm->d_gal.size();
@@ -1069,6 +1212,11 @@ void hevmx_exec(void *h, int64_t opcode, int64_t dst, int64_t lhs, int64_t rhs) 
   vm->exec(op);
   if (opcode == 10) vm->enc_counter++;
 }
+void hevmx_exec_batch(void *h, int64_t opcode, int64_t n, const int64_t *dst, const int64_t *lhs, const int64_t *rhs) {
+  VM *vm = V(h);
+  vm->ln = &vm->lanes[0];
+  vm->exec_batch((int)opcode, (int)n, dst, lhs, rhs);
+}
 void hevmx_sync(void *h) { CUDA_CHECK(cudaStreamSynchronize(V(h)->ln->stream)); }
 void hevmx_ntt(void *h, uint64_t *data, int64_t prime_idx, int64_t count, int inverse) {
   VM *vm = V(h);
@@ -1130,7 +1278,14 @@ void hevmx_decode(void *h, int64_t ptreg, double *out) {
 }
 void hevmx_decrypt_to_pt(void *h, int64_t ctreg, int64_t ptreg) { V(h)->decrypt_to_pt(V(h)->ctr((size_t)ctreg), V(h)->ptr((size_t)ptreg)); }
 void hevmx_encrypt_pt(void *h, int64_t ptreg, int64_t ctreg) { V(h)->encrypt_pt_now(V(h)->ptr((size_t)ptreg), V(h)->ctr((size_t)ctreg)); }
-void hevmx_set_enc_counter(void *h, uint64_t c) { V(h)->enc_counter = c; }
+// TEST SWITCH: pins the encryption randomness to (key seed, counter) so that this library and the oracle, started from
+// the same hevm_params.bin, produce identical ciphertexts.  A captured run() graph carries the key it was built with.
+void hevmx_set_enc_counter(void *h, uint64_t c) {
+  VM *vm = V(h);
+  if (std::memcmp(vm->enc_seed.k, vm->seed.k, sizeof vm->seed.k) != 0) vm->invalidate_graph();
+  vm->enc_seed = vm->seed;
+  vm->enc_counter = c;
+}
 int64_t hevmx_key_read(void *h, int which, uint64_t elt, uint64_t *out) {
   VM *vm = V(h);
   const u64 *src = nullptr;

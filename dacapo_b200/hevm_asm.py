@@ -64,14 +64,29 @@ class Program:
         return len(self.constants) - 1
 
     def emit(self, opcode, dst, lhs=0, rhs=0):
+        """Append one 8-byte op {u16 opcode, dst, lhs, rhs} (HEVMHeader.h:27-32).  Operands that do not fit 16 bits are
+        an error, not wrapped: index 0xFFFF is the placeholder / all-ones marker, so a 65 536th register or constant
+        would silently alias another one."""
+        if opcode != PLACEHOLDER:
+            for name, v in (("dst", dst), ("lhs", lhs), ("rhs", rhs)):
+                if not 0 <= int(v) <= 0xFFFF:
+                    raise ValueError(f"HEVM operand {name}={v} does not fit the 16-bit field of opcode {opcode}")
+            if opcode != ENCODE and (int(dst) == 0xFFFF or int(lhs) == 0xFFFF):
+                raise ValueError("register index 0xFFFF is reserved (tensor.empty placeholder, EmitHEVM.cpp:54-58)")
         self.ops.append((opcode & 0xFFFF, dst & 0xFFFF, lhs & 0xFFFF, rhs & 0xFFFF))
         return dst
 
     def encode(self, pt, const_idx, level, scale_bits):
         """opcode 0: rhs packs (level<<10)+scale (CKKSOps.td:75); lhs=-1 encodes all-ones."""
+        if not 0 <= int(level) < 64 or not 0 <= int(scale_bits) < 1024:
+            raise ValueError(f"encode: level {level} / scale {scale_bits} do not fit the 6 + 10 bit packing (CKKSOps.td:75)")
+        if int(const_idx) >= 0xFFFF or int(pt) >= 0xFFFF:
+            raise ValueError("encode: more than 65 534 constants / plaintext registers cannot be addressed by a 16-bit operand")
         return self.emit(ENCODE, pt, PLACEHOLDER if const_idx < 0 else const_idx, (level << 10) + scale_bits)
 
     def rotate(self, dst, src, offset):
+        if not -32768 <= int(offset) <= 0xFFFF:
+            raise ValueError(f"rotate offset {offset} does not fit 16 bits (SEAL_HEVM.cpp:269 reads an int16)")
         return self.emit(ROTATE, dst, src, offset & 0xFFFF)  # low 16 bits, runtime reads int16
 
     # ---- serialisation --------------------------------------------------------------

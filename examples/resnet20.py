@@ -16,7 +16,8 @@ import numpy as np
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import dacapo_b200 as hc  # noqa: E402
-from dacapo_b200 import fixtures  # noqa: E402
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tests"))
+import fixtures  # noqa: E402  (committed test fixture: tests/fixtures.py)
 
 if __name__ == "__main__":
     hc.setLibnHW(sys.argv)

@@ -42,6 +42,9 @@ const char *hevmx_backend(void);
 /* --- libB200_HEVM.so only (measurement; not part of the oracle) --- */
 /* device-resident NTT throughput: batch limbs under each of the first nprimes primes, in place; returns ms per pass */
 double hevmx_ntt_bench(void *vm, int64_t batch, int64_t nprimes, int inverse, int64_t reps);
+/* n independent ops of ONE opcode (rotate with a single-key step / mulcc / rescale, sources at one level) as one
+ * batched kernel launch (BASELINE configs[1] "batched ciphertexts"); anything else is issued op by op */
+void hevmx_exec_batch(void *vm, int64_t opcode, int64_t n, const int64_t *dst, const int64_t *lhs, const int64_t *rhs);
 double hevmx_timer(void *vm, int which);        /* CUDA events on the VM stream: 0 start, 1 stop -> ms */
 void hevmx_profiler_range(void *vm, int on);  /* cudaProfilerStart/Stop (ncu --profile-from-start off) */
 void hevmx_profile(void *vm, int on);           /* per-kernel-class CUDA-event timing */

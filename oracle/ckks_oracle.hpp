@@ -275,27 +275,51 @@ struct NttTable {
 // Deterministic counter-based sampler (our own spec, shared BY SPECIFICATION with
 // the product so that keys / encryptions are reproducible on both sides; SEAL's
 // Blake2xb PRNG is seeded from random_device and cannot be matched).
-//   rnd(seed, stream, idx) = mix(mix(seed + G*(stream+1)) + G*(idx+1))
+//   rnd(key, stream, idx) = 64-bit word (idx & 7) of the ChaCha20 block with the 256-bit `key`, nonce = stream and
+//                           block counter = idx >> 3 (original 64-bit counter / 64-bit nonce layout; word j of a
+//                           block = state[2j] | state[2j+1] << 32)  -- a keyed cryptographic PRF, so the public `a`
+//                           polynomials reveal nothing about the streams that produced the secret key and the errors
 //   uniform mod q : (rnd(2k) * 2^64 + rnd(2k+1)) mod q
 //   ternary       : rnd(k) % 3 - 1                  (SEAL sample_poly_ternary)
 //   cbd           : popc(w & 0x1FFFFF) - popc((w>>21) & 0x1FFFFF)  (SEAL sample_poly_cbd, 21+21 bits)
+// Key material is derived from the 256-bit seed of hevm_params.bin; the encryption randomness (u, e0, e1) uses a
+// SEPARATE 256-bit key that is fresh per VM unless a test pins it (hevmx_set_enc_counter), see oracle_hevm.cpp.
 // ----------------------------------------------------------------------------
-inline u64 mix64(u64 z) {
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
+struct Seed256 {
+  uint32_t k[8];
+};
+inline uint32_t rotl32(uint32_t v, int c) { return (v << c) | (v >> (32 - c)); }
+inline void chacha20_block(const Seed256 &key, u64 nonce, u64 counter, u64 out[8]) {
+  uint32_t x[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key.k[0], key.k[1], key.k[2], key.k[3], key.k[4], key.k[5], key.k[6],
+                    key.k[7], (uint32_t)counter, (uint32_t)(counter >> 32), (uint32_t)nonce, (uint32_t)(nonce >> 32)};
+  uint32_t in[16];
+  for (int i = 0; i < 16; i++) in[i] = x[i];
+#define ORC_QR(a, b, c, d)                                                                                             \
+  x[a] += x[b], x[d] = rotl32(x[d] ^ x[a], 16), x[c] += x[d], x[b] = rotl32(x[b] ^ x[c], 12), x[a] += x[b],            \
+      x[d] = rotl32(x[d] ^ x[a], 8), x[c] += x[d], x[b] = rotl32(x[b] ^ x[c], 7)
+  for (int r = 0; r < 10; r++) {
+    ORC_QR(0, 4, 8, 12), ORC_QR(1, 5, 9, 13), ORC_QR(2, 6, 10, 14), ORC_QR(3, 7, 11, 15);
+    ORC_QR(0, 5, 10, 15), ORC_QR(1, 6, 11, 12), ORC_QR(2, 7, 8, 13), ORC_QR(3, 4, 9, 14);
+  }
+#undef ORC_QR
+  for (int j = 0; j < 8; j++) out[j] = (u64)(x[2 * j] + in[2 * j]) | ((u64)(x[2 * j + 1] + in[2 * j + 1]) << 32);
 }
-inline u64 rnd(u64 seed, u64 stream, u64 idx) {
-  const u64 G = 0x9E3779B97F4A7C15ull;
-  return mix64(mix64(seed + G * (stream + 1)) + G * (idx + 1));
-}
-inline u64 uniform_mod(u64 seed, u64 stream, u64 k, const Modulus &m) {
-  u64 hi = rnd(seed, stream, 2 * k), lo = rnd(seed, stream, 2 * k + 1);
+struct Prf { // one stream of the sampler; consecutive indices reuse the cached block
+  const Seed256 &key;
+  u64 stream, cur = ~0ull, w[8];
+  Prf(const Seed256 &k, u64 st) : key(k), stream(st) {}
+  u64 operator()(u64 idx) {
+    if ((idx >> 3) != cur) cur = idx >> 3, chacha20_block(key, stream, cur, w);
+    return w[idx & 7];
+  }
+};
+inline u64 uniform_mod(Prf &r, u64 k, const Modulus &m) {
+  u64 hi = r(2 * k), lo = r(2 * k + 1);
   return (u64)((((u128)hi << 64) | lo) % m.q);
 }
-inline int ternary(u64 seed, u64 stream, u64 k) { return (int)(rnd(seed, stream, k) % 3) - 1; }
-inline int cbd(u64 seed, u64 stream, u64 k) {
-  u64 w = rnd(seed, stream, k);
+inline int ternary(Prf &r, u64 k) { return (int)(r(k) % 3) - 1; }
+inline int cbd(Prf &r, u64 k) {
+  u64 w = r(k);
   return __builtin_popcountll(w & 0x1FFFFF) - __builtin_popcountll((w >> 21) & 0x1FFFFF);
 }
 // stream ids
@@ -333,7 +357,8 @@ struct KswKey {
 struct Context {
   int logN = 0, L = 0; // L = number of primes incl. the special (last) one
   size_t N = 0;
-  u64 seed = 0;
+  Seed256 seed{};     // key material
+  Seed256 enc_seed{}; // encryption randomness (fresh per VM unless pinned by a test)
   std::vector<Modulus> q;
   std::vector<NttTable> ntt;
   // encoder tables (SEAL ckks.cpp CKKSEncoder ctor)
@@ -349,11 +374,12 @@ struct Context {
 
   size_t max_level() const { return (size_t)L - 1; }
 
-  void init_params(int logn, int nprimes, int bits, u64 sd) {
+  void init_params(int logn, int nprimes, int bits, const Seed256 &sd) {
     logN = logn;
     L = nprimes;
     N = (size_t)1 << logn;
     seed = sd;
+    enc_seed = sd;
     auto ps = seal_primes(N, bits, nprimes);
     q.clear();
     ntt.resize(nprimes);
@@ -443,15 +469,17 @@ struct Context {
   }
 
   // -------- sampling helpers ----------------------------------------------------
-  void sample_ternary_rns(u64 stream, int limbs, u64 *out) const { // coefficient form
+  void sample_ternary_rns(const Seed256 &key, u64 stream, int limbs, u64 *out) const { // coefficient form
+    Prf r(key, stream);
     for (size_t k = 0; k < N; k++) {
-      int t = ternary(seed, stream, k);
+      int t = ternary(r, k);
       for (int i = 0; i < limbs; i++) out[(size_t)i * N + k] = t < 0 ? q[i].q - 1 : (u64)t;
     }
   }
-  void sample_cbd_rns(u64 stream, int limbs, u64 *out) const {
+  void sample_cbd_rns(const Seed256 &key, u64 stream, int limbs, u64 *out) const {
+    Prf r(key, stream);
     for (size_t k = 0; k < N; k++) {
-      int t = cbd(seed, stream, k);
+      int t = cbd(r, k);
       for (int i = 0; i < limbs; i++) out[(size_t)i * N + k] = t < 0 ? q[i].q - (u64)(-t) : (u64)t;
     }
   }
@@ -460,10 +488,11 @@ struct Context {
   // symmetric zero encryption at key level in NTT form: (c0, c1) = (-(a s + e), a)
   void encrypt_zero_symmetric(u64 a_stream_base, u64 e_stream, u64 *c0, u64 *c1) const {
     std::vector<u64> e((size_t)L * N);
-    sample_cbd_rns(e_stream, L, e.data());
+    sample_cbd_rns(seed, e_stream, L, e.data());
     for (int i = 0; i < L; i++) {
       u64 *a = c1 + (size_t)i * N;
-      for (size_t k = 0; k < N; k++) a[k] = uniform_mod(seed, a_stream_base + i, k, q[i]); // sampled in NTT form
+      Prf ra(seed, a_stream_base + i);
+      for (size_t k = 0; k < N; k++) a[k] = uniform_mod(ra, k, q[i]); // sampled in NTT form
       u64 *ei = e.data() + (size_t)i * N;
       ntt[i].forward(ei);
       const u64 *s = sk.data() + (size_t)i * N;
@@ -489,7 +518,7 @@ struct Context {
   static u64 galois_key_id(u64 elt) { return 1 + ((elt - 1) >> 1); } // GaloisKeys::get_index(elt)+1
   void keygen() {
     sk.assign((size_t)L * N, 0);
-    sample_ternary_rns(ST_SK << 20, L, sk.data());
+    sample_ternary_rns(seed, ST_SK << 20, L, sk.data());
     for (int i = 0; i < L; i++) ntt[i].forward(sk.data() + (size_t)i * N);
     pk.assign((size_t)2 * L * N, 0);
     encrypt_zero_symmetric(pk_a_stream(0), ST_PK_E << 20, pk.data(), pk.data() + (size_t)L * N);
@@ -499,7 +528,19 @@ struct Context {
       for (size_t k = 0; k < N; k++) s2[(size_t)i * N + k] = mulmod(sk[(size_t)i * N + k], sk[(size_t)i * N + k], q[i]);
     make_ksk(0, s2.data(), relin);
     // galois keys (create_galois_keys default set): new key = apply_galois_ntt(sk, elt)
-    for (u64 elt : galois_elts_all()) make_galois_key(elt);
+    // HEVM_GALOIS_STEPS="1,-2,64": only these rotation steps get a key (SEAL KeyGenerator::create_galois_keys(steps));
+    // unset = the default set of create_galois_keys() used by the reference (SEAL_HEVM.cpp:82-83)
+    if (const char *e = std::getenv("HEVM_GALOIS_STEPS")) {
+      for (const char *p = e; *p;) {
+        char *end = nullptr;
+        long st = std::strtol(p, &end, 10);
+        if (end == p) break;
+        make_galois_key(galois_elt_from_step((int)st));
+        p = (*end == ',') ? end + 1 : end;
+      }
+    } else {
+      for (u64 elt : galois_elts_all()) make_galois_key(elt);
+    }
   }
   void make_galois_key(u64 elt) {
     if (gal.count(elt)) return;
@@ -751,7 +792,7 @@ struct Context {
   void encrypt_zero_asym(int limbs /*use q_0..q_{limbs-1}*/, u64 counter, std::vector<u64> &c /*[2][limbs][N]*/) const {
     c.assign((size_t)2 * limbs * N, 0);
     std::vector<u64> u((size_t)limbs * N);
-    sample_ternary_rns(enc_stream(counter, 0), limbs, u.data());
+    sample_ternary_rns(enc_seed, enc_stream(counter, 0), limbs, u.data());
     for (int i = 0; i < limbs; i++) {
       ntt[i].forward(u.data() + (size_t)i * N);
       for (int j = 0; j < 2; j++) {
@@ -761,7 +802,7 @@ struct Context {
       }
     }
     for (int j = 0; j < 2; j++) {
-      sample_cbd_rns(enc_stream(counter, 1 + j), limbs, u.data());
+      sample_cbd_rns(enc_seed, enc_stream(counter, 1 + j), limbs, u.data());
       for (int i = 0; i < limbs; i++) {
         ntt[i].forward(u.data() + (size_t)i * N);
         u64 *o = c.data() + ((size_t)j * limbs + i) * N;

@@ -33,10 +33,11 @@ struct FileOp {
 #pragma pack(pop)
 
 struct ParamFile {
-  uint64_t magic; // "HEVMB200"
-  uint64_t logN, L, bits, seed;
+  uint64_t magic;
+  uint64_t logN, L, bits;
+  uint32_t seed[8]; // 256-bit key seed (format version 2)
 };
-const uint64_t PARAM_MAGIC = 0x3030324D56454842ull; // "BHEVM200" little-endian tag
+const uint64_t PARAM_MAGIC = 0x3230324D56454842ull; // "BHEVM202" little-endian tag: version 2 = 256-bit seed
 
 struct VM {
   Context ctx;
@@ -124,11 +125,12 @@ void create_context(char *dir) {
   pf.logN = (e = std::getenv("HEVM_LOGN")) ? std::strtoull(e, nullptr, 10) : 15;   // SEAL_HEVM.cpp:39
   pf.L = (e = std::getenv("HEVM_NUM_PRIMES")) ? std::strtoull(e, nullptr, 10) : 14; // SEAL_HEVM.cpp:40
   pf.bits = (e = std::getenv("HEVM_PRIME_BITS")) ? std::strtoull(e, nullptr, 10) : 60;
-  if ((e = std::getenv("HEVM_SEED")))
-    pf.seed = std::strtoull(e, nullptr, 0);
-  else {
+  if ((e = std::getenv("HEVM_SEED"))) { // tests: a fixed, public seed
+    const uint64_t v = std::strtoull(e, nullptr, 0);
+    pf.seed[0] = (uint32_t)v, pf.seed[1] = (uint32_t)(v >> 32);
+  } else {
     std::random_device rd;
-    pf.seed = ((uint64_t)rd() << 32) ^ rd();
+    for (auto &w : pf.seed) w = rd();
   }
   std::ofstream f(std::string(dir) + "/hevm_params.bin", std::ios::binary);
   f.write((const char *)&pf, sizeof pf);
@@ -137,7 +139,13 @@ void *initFullVM(char *dir, bool /*device*/) {
   auto vm = new VM();
   ParamFile pf;
   read_params(dir, pf);
-  vm->ctx.init_params((int)pf.logN, (int)pf.L, (int)pf.bits, pf.seed);
+  Seed256 sd;
+  std::memcpy(sd.k, pf.seed, sizeof sd.k);
+  vm->ctx.init_params((int)pf.logN, (int)pf.L, (int)pf.bits, sd);
+  { // encryption randomness: fresh per VM (hevmx_set_enc_counter pins it to the key seed for the parity tests)
+    std::random_device rd;
+    for (auto &w : vm->ctx.enc_seed.k) w = rd();
+  }
   vm->ctx.keygen();
   return vm;
 }
@@ -220,7 +228,7 @@ int64_t hevmx_param(void *h, int what) {
   switch (what) {
   case 0: return vm->ctx.logN;
   case 1: return vm->ctx.L;
-  case 2: return (int64_t)vm->ctx.seed;
+  case 2: return (int64_t)(vm->ctx.seed.k[0] | ((uint64_t)vm->ctx.seed.k[1] << 32));
   case 3: return (int64_t)vm->ct.size();
   case 4: return (int64_t)vm->pt.size();
   case 5: return (int64_t)vm->ctx.gal.size();
@@ -306,7 +314,13 @@ void hevmx_encrypt_pt(void *h, int64_t ptreg, int64_t ctreg) {
   auto vm = (VM *)h;
   vm->ctx.encrypt(vm->pt.at(ptreg), vm->ct.at(ctreg));
 }
-void hevmx_set_enc_counter(void *h, uint64_t c) { ((VM *)h)->ctx.enc_counter = c; }
+// TEST SWITCH: pins the encryption randomness to (key seed, counter) so that two libraries started from the same
+// hevm_params.bin produce identical ciphertexts; without it every VM encrypts with fresh entropy
+void hevmx_set_enc_counter(void *h, uint64_t c) {
+  auto vm = (VM *)h;
+  vm->ctx.enc_seed = vm->ctx.seed;
+  vm->ctx.enc_counter = c;
+}
 // key material read-out: which = 0 sk [L][N], 1 pk [2][L][N], 2 relin, 3 galois(elt)
 int64_t hevmx_key_read(void *h, int which, uint64_t elt, uint64_t *out) {
   auto vm = (VM *)h;

@@ -18,7 +18,8 @@ def oracle_lib():
     import subprocess
     from dacapo_b200 import _binding
     subprocess.run(["make", "-s", "-C", str(REPO / "oracle")], check=True)
-    return _binding.bind(_binding.ORACLE_LIB)
+    import fixtures
+    return _binding.bind(fixtures.ORACLE_LIB)
 
 
 @pytest.fixture(scope="session")

@@ -8,9 +8,62 @@
 // linked into libB200_HEVM.so and is not a fallback: the product has no host execution path.
 #include "../../dacapo_b200/csrc/host_params.hpp"
 #include "../../dacapo_b200/csrc/ops.hpp"
+#include <cstdio>
 #include <cstring>
 
 struct EmuLauncher {
+  bool use_fused = false;
+  long waits_checked = 0;
+  bool fused() const { return use_fused; }
+  // single-launch key switch / rescale: the tickets are replayed IN ORDER by one "CTA"; every wait of a unit must
+  // already be satisfied by the signals of lower tickets (that is the deadlock-freedom argument of ks_fused.cuh), and
+  // at the end every counter must sit exactly at the value its consumers wait for.
+  template <int LOGA, int MODE> void ks_fused(const KsFusedArgs &A) {
+    const KsUnits K = ks_units<LOGA, MODE>(A);
+    const size_t N = (size_t)1 << (LOGA + 8);
+    const int L = A.Ltot;
+    for (int ticket = 0; ticket < K.total; ticket++) {
+      const KsUnit un = ks_decode(K, A.nct, ticket);
+      const KsCt &c = A.ct[un.c];
+      Scratch sc;
+      sc.carve(c.scratch, L, N);
+      const KsDeps d = ks_deps<LOGA, MODE>(A, un);
+      for (int k = 0; k < d.nwait; k++, waits_checked++)
+        if (sc.ctl[d.widx[k]] < d.wtarget[k]) {
+          std::fprintf(stderr, "emul: ticket %d (phase %d unit %d) waits on counter %d = %u < %u: dependency order broken\n", ticket, un.phase, un.u,
+                       d.widx[k], sc.ctl[d.widx[k]], d.wtarget[k]);
+          std::abort();
+        }
+      if (un.phase == 2) {
+        mac<LOGA>(ks_args_p3<MODE>(A, c, sc), 1, un.u);
+      } else {
+        for (int w = 0; w < 4; w++) {
+          const int job = un.u * 4 + w;
+          alignas(16) u64 sm[Geo<LOGA>::WARP_WORDS];
+          if (un.phase == 0) {
+            LaneB8 st[32];
+            body_intt_B<LOGA, MODE == FUSED_RESCALE ? LD_PLAIN : MODE>(ks_args_p1<MODE>(A, c, sc), job, st, sm);
+          } else if (un.phase == 1) {
+            LaneA st[32];
+            body_invA_fwdA<LOGA, PRE_MODUP>(ks_args_p2(A, sc), job, st, sm);
+          } else if (un.phase == 3) {
+            LaneA st[32];
+            body_invA_fwdA<LOGA, PRE_ROUND>(ks_args_p4<MODE>(A, sc), job, st, sm);
+          } else {
+            LaneB8 st[32];
+            body_fwd_B<LOGA, MODE == LD_GALOIS ? EPI_MODDOWN_GALOIS : MODE == LD_PRODUCT ? EPI_MODDOWN_RELIN : EPI_RESCALE>(ks_args_p5<MODE>(A, c, sc), job, st, sm);
+          }
+        }
+      }
+      for (int k = 0; k < d.sig_count; k++)
+        if (k != d.sig_skip) sc.ctl[d.sig_first + k] += d.sig_inc;
+    }
+    for (int cc = 0; cc < A.nct; cc++) { // the last CTA's reset
+      Scratch sc;
+      sc.carve(A.ct[cc].scratch, L, N);
+      for (int i = 0; i < ctl_count(L); i++) sc.ctl[i] = 0;
+    }
+  }
   template <int LOGA, int LD> void intt_B(const ArgsInttB &a, int njobs) {
     for (int j = 0; j < njobs; j++) {
       LaneB8 st[32];
@@ -46,10 +99,10 @@ struct EmuLauncher {
       body_invA_fwdA<LOGA, PRE>(a, j, st, sm);
     }
   }
-  template <int LOGA> void mac(const ArgsFwdB &a, int njobs) { // one CTA of MAC_WARPS warps per job; CTA barriers = phase boundaries
+  template <int LOGA> void mac(const ArgsFwdB &a, int njobs, int job0 = 0) { // one CTA of MAC_WARPS warps per job; CTA barriers = phase boundaries
     std::vector<u64> smv(mac_smem_words(a.l) + 2);
     u64 *sm = smv.data() + ((reinterpret_cast<uintptr_t>(smv.data()) & 8) ? 1 : 0); // 16-byte aligned
-    for (int j = 0; j < njobs; j++) {
+    for (int j = job0; j < job0 + njobs; j++) {
       Tw *tw_s = reinterpret_cast<Tw *>(sm);
       u64 *tiles = sm + MAC_TW_WORDS, *rowbufs = tiles + MAC_WARPS * TILE_B_WORDS, *xbuf = rowbufs + MAC_WARPS * MAC_ROW_WORDS;
       for (int tid = 0; tid < MAC_WARPS * 32; tid++) body_mac_stage<LOGA>(a, j, tid, tw_s);
@@ -121,6 +174,21 @@ void emul_keyswitch_sharded(void *h, int mode, const u64 *a, const u64 *b, u64 *
       const int tlo = (int)((long)(l + 1) * g / ranks), thi = (int)((long)(l + 1) * (g + 1) / ranks);
       e->ops->ks_shard_stage(stage, mode, a, b, dst, (size_t)l * e->P.N, l, ks.data(), elt, tlo, thi);
     }
+}
+void emul_set_fused(void *h, int on) { ((Emu *)h)->la.use_fused = on != 0; }
+long emul_waits_checked(void *h) { return ((Emu *)h)->la.waits_checked; }
+// batched single-launch key switch: n ciphertexts (compact [2][l][N] each, contiguous), one scratch area per ciphertext
+void emul_keyswitch_batch(void *h, int mode, int n, const u64 *a, const u64 *b, u64 *dst, int l, const u64 *key, const u32 *elts) {
+  auto e = (Emu *)h;
+  const size_t kw = (size_t)(e->P.L - 1) * 2 * e->P.L * e->P.N, ctw = (size_t)2 * l * e->P.N, sw = Scratch::words(e->P.L, e->P.N);
+  std::vector<u64> ks(kw), scr(sw * n, 0);
+  for (size_t i = 0; i < kw; i++) ks[i] = split30(key[i]);
+  std::vector<KsCt> items(n);
+  for (int k = 0; k < n; k++) items[k] = KsCt{a + k * ctw, b ? b + k * ctw : nullptr, dst + k * ctw, ks.data(), scr.data() + k * sw, elts ? elts[k] : 0, 0};
+  const bool was = e->la.use_fused;
+  e->la.use_fused = true;
+  e->ops->keyswitch_batch(mode, n, items.data(), (size_t)l * e->P.N, l);
+  e->la.use_fused = was;
 }
 void emul_rescale(void *h, const u64 *src, u64 *dst, int l) {
   auto e = (Emu *)h;

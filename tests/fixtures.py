@@ -1,4 +1,5 @@
-"""Access to the committed ResNet-20 fixture (tests/golden/resnet20, made by tests/golden/make_resnet_fixture.py)."""
+"""TEST / BENCH INFRASTRUCTURE: access to the committed ResNet-20 fixture (tests/golden/resnet20, made by
+tests/golden/make_resnet_fixture.py) and the location of the CPU oracle library.  Not part of the product package."""
 import json
 import lzma
 import tempfile
@@ -6,7 +7,8 @@ from pathlib import Path
 
 import numpy as np
 
-FIXTURE = Path(__file__).resolve().parent.parent / "tests" / "golden" / "resnet20"
+FIXTURE = Path(__file__).resolve().parent / "golden" / "resnet20"
+ORACLE_LIB = Path(__file__).resolve().parent.parent / "oracle" / "libORACLE_HEVM.so"  # the checker, never the product
 
 
 def resnet20_files(tmpdir=None, variant=""):

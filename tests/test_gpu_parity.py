@@ -49,7 +49,7 @@ def test_keys_bit_exact(pair):
     assert g.lib.hevmx_param(g.vm, 5) == o.lib.hevmx_param(o.vm, 5) == 28
 
 
-@pytest.mark.parametrize("prime", [0, 5, 13])
+@pytest.mark.parametrize("prime", list(range(NPR)))  # every prime of the chain
 def test_ntt_bit_exact(pair, prime):
     g, o = pair
     rng = np.random.default_rng(prime)
@@ -62,7 +62,7 @@ def test_ntt_bit_exact(pair, prime):
     assert np.array_equal(g.ntt(F, prime, inverse=True), f)
 
 
-@pytest.mark.parametrize("lvl", [1, 2, 7, 13])
+@pytest.mark.parametrize("lvl", list(range(1, NPR)))  # every level of the modulus chain
 def test_elementwise_ops(pair, lvl):
     g, o = pair
     a, b, p = o.random_ct(lvl, lvl), o.random_ct(lvl, 100 + lvl), o.random_pt(lvl, 200 + lvl)
@@ -84,7 +84,7 @@ def test_elementwise_ops(pair, lvl):
         assert np.array_equal(g.ct_read(0), o.ct_read(0)) and g.ct_info(0)[0] == lvl - 1
 
 
-@pytest.mark.parametrize("lvl", [2, 3, 8, 13])
+@pytest.mark.parametrize("lvl", list(range(2, NPR)))
 def test_rescale(pair, lvl):
     g, o = pair
     a = o.random_ct(lvl, 300 + lvl)
@@ -96,11 +96,12 @@ def test_rescale(pair, lvl):
         assert g.ct_info(dst) == o.ct_info(dst)
 
 
-@pytest.mark.parametrize("lvl", [1, 2, 6, 13])
+@pytest.mark.parametrize("lvl", list(range(1, NPR)))
 def test_mulcc_relin(pair, lvl):
     g, o = pair
     a, b = o.random_ct(lvl, 400 + lvl), o.random_ct(lvl, 500 + lvl)
-    for dst, lhs, rhs in ((2, 0, 1), (0, 0, 1), (1, 0, 1), (2, 0, 0), (0, 0, 0)):
+    forms = ((2, 0, 1), (0, 0, 1), (1, 0, 1), (2, 0, 0), (0, 0, 0)) if lvl in (1, 2, 6, 13) else ((2, 0, 1), (0, 0, 0))
+    for dst, lhs, rhs in forms:
         for vm in pair:
             vm.ct_write(0, a, 2.0 ** 40)
             vm.ct_write(1, b, 2.0 ** 40)
@@ -109,7 +110,8 @@ def test_mulcc_relin(pair, lvl):
         assert g.ct_info(dst) == o.ct_info(dst)
 
 
-@pytest.mark.parametrize("lvl,step", [(1, 1), (2, -1), (5, 128), (13, 1), (13, -8192), (4, 12285), (3, -15360), (2, 0), (13, 16383)])
+@pytest.mark.parametrize("lvl,step", [(1, 1), (2, -1), (5, 128), (13, 1), (13, -8192), (4, 12285), (3, -15360), (2, 0), (13, 16383)]
+                         + [(l, (1, -2, 4096)[l % 3]) for l in range(3, 13)])  # + every remaining level with a single-key step
 def test_rotate(pair, lvl, step):
     g, o = pair
     a = o.random_ct(lvl, 600 + lvl)
@@ -157,6 +159,35 @@ def test_sharded_mulcc_stages_bit_exact(pair, lvl, ranks, inplace):
     g.lib.hevmx_sync(g.vm)
     assert np.array_equal(g.ct_read(dst), o.ct_read(dst)), (lvl, ranks, inplace)
     assert g.ct_info(dst) == o.ct_info(dst)
+
+
+@pytest.mark.parametrize("lvl,n", [(13, 3), (4, 5), (1, 2), (2, 35)])
+def test_batched_launch_bit_exact(oracle_lib, b200_lib, tmp_path_factory, lvl, n):
+    """hevmx_exec_batch: n independent rotate / mulcc / rescale ops in ONE persistent launch each (ks_fused.cuh; n = 35
+    spans two launches of KS_MAX_BATCH = 32) vs the oracle op by op; rotations of one batch use different Galois keys."""
+    d = str(tmp_path_factory.mktemp("keysb"))
+    g = VM(b200_lib, LOGN, NPR, keydir=d, nct=3 * n, npt=1)
+    o = VM(oracle_lib, LOGN, NPR, keydir=d, nct=3 * n, npt=1)
+    steps = [1, -1, 64, 2, -8192]
+    for k in range(n):
+        a = o.random_ct(lvl, 1000 + 7 * k) if k < 6 else None  # six distinct inputs are enough for n = 35
+        for vm in (g, o):
+            vm.ct_write(k, a if a is not None else vm.ct_read(k % 6), 2.0 ** 40)
+    src, dst, dst2 = list(range(n)), list(range(n, 2 * n)), list(range(2 * n, 3 * n))
+    rot = [steps[k % len(steps)] for k in range(n)]
+    g.exec_batch(asm.ROTATE, dst, src, rot)
+    g.exec_batch(asm.MULCC, dst2, dst, src)
+    if lvl > 1:
+        g.exec_batch(asm.RESCALE, dst2, dst2, [0] * n)  # in place
+    for k in range(n):
+        o.exec(asm.ROTATE, dst[k], src[k], rot[k])
+        o.exec(asm.MULCC, dst2[k], dst[k], src[k])
+        if lvl > 1:
+            o.exec(asm.RESCALE, dst2[k], dst2[k])
+    for k in range(n):
+        assert np.array_equal(g.ct_read(dst[k]), o.ct_read(dst[k])), ("rotate", k)
+        assert np.array_equal(g.ct_read(dst2[k]), o.ct_read(dst2[k])), ("mulcc+rescale", k)
+        assert g.ct_info(dst2[k]) == o.ct_info(dst2[k])
 
 
 def test_encode_decode_bit_exact(pair):
@@ -371,6 +402,47 @@ def test_accumulation_chain_bit_exact(pair, tmp_path):
     for (a, ia), (b, ib) in zip(*outs):
         assert ia == ib
         assert np.array_equal(a, b)
+    for vm in pair:
+        vm.lib.hevmx_resize(vm.vm, 8, 4)
+
+
+def test_replay_restores_register_metadata(pair, tmp_path):
+    """A program that OVERWRITES its argument register and returns it (hecate-opt's ReuseBuffer recycles dead argument
+    registers, ReuseBuffer.cpp:27-55): the second run() is a CUDA-graph replay and must leave the result register with
+    the level / scale of the first run, not with the argument's (encrypt() in between resets them)."""
+    g, o = pair
+    p = asm.Program(init_level=13)
+    x = p.arg(50, 4)
+    t = p.new_ct()
+    p.emit(asm.MULCC, t, x, x)
+    p.emit(asm.RESCALE, x, t)            # the argument register is recycled: level 3 from here on
+    p.rotate(x, x, 3)
+    p.emit(asm.MODSWITCH, x, x, 0)       # downFactor 0: a no-op that must not count as a write (ADVICE r1)
+    p.result(x, 60, 3)
+    cst, hv = tmp_path / "m.cst", tmp_path / "m.hevm"
+    p.save(cst, hv)
+    n = o.N // 2
+    xs = np.random.default_rng(31).uniform(-1, 1, n)
+    f64p = C.POINTER(C.c_double)
+    outs = {}
+    for name, vm in (("g", g), ("o", o)):
+        lib = vm.lib
+        lib.load(vm.vm, str(cst).encode(), str(hv).encode())
+        lib.preprocess(vm.vm)
+        for rep in range(3):
+            lib.hevmx_set_enc_counter(vm.vm, 40)
+            lib.encrypt(vm.vm, 0, xs.ctypes.data_as(f64p), n)
+            assert vm.ct_info(0)[0] == 4
+            lib.run(vm.vm)
+            res = np.zeros(n)
+            lib.decrypt_result(vm.vm, 0, res.ctypes.data_as(f64p))
+            outs[name, rep] = (vm.ct_info(0), vm.ct_read(0), res)
+    for rep in range(3):
+        (ig, cg, rg), (io, co, ro) = outs["g", rep], outs["o", rep]
+        assert ig == io and ig[0] == 3, rep
+        assert np.array_equal(cg, co), rep
+        assert np.array_equal(rg, ro), rep
+        assert np.max(np.abs(rg - np.roll(xs * xs, -3))) < 1e-5
     for vm in pair:
         vm.lib.hevmx_resize(vm.vm, 8, 4)
 

@@ -35,6 +35,10 @@ def emul(LOGN):
     lib.emul_keyswitch.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p, C.c_int, u64p, C.c_uint32]
     lib.emul_rescale.argtypes = [C.c_void_p, u64p, u64p, C.c_int]
     lib.emul_keyswitch_sharded.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p, C.c_int, u64p, C.c_uint32, C.c_int]
+    lib.emul_set_fused.argtypes = [C.c_void_p, C.c_int]
+    lib.emul_waits_checked.argtypes = [C.c_void_p]
+    lib.emul_waits_checked.restype = C.c_long
+    lib.emul_keyswitch_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, u64p, u64p, u64p, C.c_int, u64p, C.POINTER(C.c_uint32)]
     return lib, lib.emul_create(LOGN, NPR, 60)
 
 
@@ -150,3 +154,91 @@ def test_sharded_mulcc_kernels_vs_oracle(emul, vm, ranks):
     a2 = a.copy()
     lib.emul_keyswitch_sharded(h, 2, _p(a2), _p(b), _p(a2), lvl, _p(key), 0, ranks)
     assert np.array_equal(a2, exp)
+
+
+def test_fused_single_launch_vs_oracle(emul, vm):
+    """ks_fused.cuh: the single-launch key switch / rescale (ticket-ordered units + completion counters).  The emulator
+    replays the tickets in order and aborts if any unit's wait is not already satisfied by lower tickets; results must
+    equal the oracle's rotate / multiply+relinearize / rescale, also in place and for a batch with different Galois keys."""
+    lib, h = emul
+    lib.emul_set_fused(h, 1)
+    try:
+        w0 = lib.emul_waits_checked(h)
+        for lvl, step in ((3, 1), (1, -4), (2, 2)):
+            a = vm.random_ct(lvl, 40 + lvl)
+            vm.ct_write(0, a)
+            vm.exec(asm.ROTATE, 1, 0, step)
+            elt = vm.lib.hevmx_galois_elt(vm.vm, step)
+            got = a.copy()
+            lib.emul_keyswitch(h, 1, _p(got), None, _p(got), lvl, _p(vm.key(3, elt)), elt)
+            assert np.array_equal(got, vm.ct_read(1)), (lvl, step)
+        for lvl in (1, 3):
+            a, b = vm.random_ct(lvl, 50 + lvl), vm.random_ct(lvl, 60 + lvl)
+            vm.ct_write(0, a)
+            vm.ct_write(1, b)
+            vm.exec(asm.MULCC, 2, 0, 1)
+            a2 = a.copy()
+            lib.emul_keyswitch(h, 2, _p(a2), _p(b), _p(a2), lvl, _p(vm.key(2)), 0)
+            assert np.array_equal(a2, vm.ct_read(2)), lvl
+            vm.exec(asm.MULCC, 2, 0, 0)
+            a3 = a.copy()
+            lib.emul_keyswitch(h, 2, _p(a3), _p(a3), _p(a3), lvl, _p(vm.key(2)), 0)
+            assert np.array_equal(a3, vm.ct_read(2)), lvl
+        for lvl in (2, 3):
+            a = vm.random_ct(lvl, 70 + lvl)
+            vm.ct_write(0, a)
+            vm.exec(asm.RESCALE, 1, 0)
+            got = np.zeros((2, lvl - 1, vm.N), dtype=np.uint64)
+            lib.emul_rescale(h, _p(a), _p(got), lvl)
+            assert np.array_equal(got, vm.ct_read(1)), lvl
+        assert lib.emul_waits_checked(h) > w0
+        # batch of three ciphertexts with ONE key (same rotation step) in one launch
+        lvl, step, n = 2, 1, 3
+        elt = vm.lib.hevmx_galois_elt(vm.vm, step)
+        cts = np.stack([vm.random_ct(lvl, 80 + k) for k in range(n)])
+        exp = []
+        for k in range(n):
+            vm.ct_write(0, cts[k])
+            vm.exec(asm.ROTATE, 1, 0, step)
+            exp.append(vm.ct_read(1))
+        got = np.zeros_like(cts)
+        elts = (C.c_uint32 * n)(*([elt] * n))
+        lib.emul_keyswitch_batch(h, 1, n, _p(cts), None, _p(got), lvl, _p(vm.key(3, elt)), elts)
+        assert np.array_equal(got, np.stack(exp))
+    finally:
+        lib.emul_set_fused(h, 0)
+
+
+def test_more_than_15_digits_vs_oracle(oracle_lib):
+    """Levels above MAC_FLUSH_DIGITS = 15 take a second accumulation chunk in the key inner product (body_mac_dot):
+    N = 2^14, 18 primes, level 17 -- rotate, multiply + relinearise (separate launches, single-launch form and the
+    limb-sharded stages) against the oracle."""
+    logn, npr, lvl = 14, 18, 17
+    so = HERE / "emul" / "libwarp_emul.so"
+    lib = C.CDLL(str(so))
+    lib.emul_create.restype = C.c_void_p
+    lib.emul_create.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.emul_keyswitch.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p, C.c_int, u64p, C.c_uint32]
+    lib.emul_keyswitch_sharded.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p, C.c_int, u64p, C.c_uint32, C.c_int]
+    lib.emul_set_fused.argtypes = [C.c_void_p, C.c_int]
+    h = lib.emul_create(logn, npr, 60)
+    vm = VM(oracle_lib, logn, npr, nct=4, npt=1, galois_steps=(1,))
+    a, b = vm.random_ct(lvl, 91), vm.random_ct(lvl, 92)
+    vm.ct_write(0, a)
+    vm.ct_write(1, b)
+    vm.exec(asm.ROTATE, 2, 0, 1)
+    vm.exec(asm.MULCC, 3, 0, 1)
+    elt = vm.lib.hevmx_galois_elt(vm.vm, 1)
+    gk, rk = vm.key(3, elt), vm.key(2)
+    for fused in (0, 1):
+        lib.emul_set_fused(h, fused)
+        got = np.zeros_like(a)
+        lib.emul_keyswitch(h, 1, _p(a), None, _p(got), lvl, _p(gk), elt)
+        assert np.array_equal(got, vm.ct_read(2)), ("rotate", fused)
+        got = np.zeros_like(a)
+        lib.emul_keyswitch(h, 2, _p(a), _p(b), _p(got), lvl, _p(rk), 0)
+        assert np.array_equal(got, vm.ct_read(3)), ("mulcc", fused)
+    lib.emul_set_fused(h, 0)
+    got = np.zeros_like(a)
+    lib.emul_keyswitch_sharded(h, 1, _p(a), None, _p(got), lvl, _p(gk), elt, 4)
+    assert np.array_equal(got, vm.ct_read(2)), "sharded rotate"

@@ -10,13 +10,13 @@ import time
 import numpy as np
 import pytest
 
-from dacapo_b200 import fixtures
+import fixtures
 from util import make_vm
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("waterline", [40, 35, 50])
+@pytest.mark.parametrize("waterline", [40, 35])
 def test_encrypted_resnet20_matches_plaintext_model(b200_lib, tmp_path, waterline):
     cst, hv, x, expected, meta = fixtures.resnet20_files(tmp_path)
     if waterline != 40:  # waterline sweep programs share the constant pool (tests/golden/make_resnet_fixture.py)
@@ -39,7 +39,8 @@ def test_encrypted_resnet20_matches_plaintext_model(b200_lib, tmp_path, waterlin
     rms = float(np.sqrt(np.sum(err * err) / res.shape[-1]))
     print(f"encrypted ResNet-20 (waterline {waterline}): run() {latency:.3f}s rms {rms:.3e} argmax {int(np.argmax(res))} vs {int(np.argmax(expected))}")
     assert np.argmax(res) == np.argmax(expected)
-    assert rms < 5e-3, rms
+    assert rms < (1.5e-3 if waterline >= 35 else 5e-3), rms  # north star: ~1e-3 (README.md:187 reports 9.5e-4)
+    assert latency < 1.0, latency        # 0.12 s in round 1; a 5x regression must not pass
 
 
 def test_encrypted_resnet20_at_2_16_slots(b200_lib, tmp_path):
@@ -63,4 +64,48 @@ def test_encrypted_resnet20_at_2_16_slots(b200_lib, tmp_path):
     rms = float(np.sqrt(np.mean((res - expected) ** 2)))
     print(f"encrypted ResNet-20, nt = 2^16 (N = 2^17): run() {latency:.3f}s rms {rms:.3e} argmax {int(np.argmax(res))} vs {int(np.argmax(expected))}")
     assert np.argmax(res) == np.argmax(expected)
-    assert rms < 5e-3, rms
+    assert rms < 1.5e-3, rms
+    assert latency < 3.0, latency
+
+
+def test_resnet20_program_bit_exact_vs_oracle(b200_lib, oracle_lib, tmp_path, capsys):
+    """The whole compiled ResNet-20 program (20 202 ops: register renaming, deferred multi-term chains, ~300 in-graph
+    bootstraps, CUDA-graph replay) on the GPU and on the CPU oracle from the same key / parameter file and the same
+    encryption counter: the result CIPHERTEXT must be the same words, after the first run() and after a replay.  Also
+    reports the MEASURED time of the oracle's run() (the CPU port of this very program; reference flow:
+    examples/tests/ResNet.py:109-118)."""
+    cst, hv, x, expected, meta = fixtures.resnet20_files(tmp_path)
+    f64p = C.POINTER(C.c_double)
+    keydir = str(tmp_path / "keys")
+    (tmp_path / "keys").mkdir()
+    out = {}
+    for name, lib in (("gpu", b200_lib), ("oracle", oracle_lib)):
+        vm, _ = make_vm(lib, 15, 14, keydir=keydir)
+        lib.load(vm, cst.encode(), hv.encode())
+        lib.preprocess(vm)
+        runs = 2 if name == "gpu" else 1
+        for rep in range(runs):
+            lib.hevmx_set_enc_counter(vm, 1234)
+            lib.encrypt(vm, 0, x.ctypes.data_as(f64p), x.size)
+            t = time.perf_counter()
+            lib.run(vm)
+            dt = time.perf_counter() - t
+            r = lib.getResIdx(vm, 0)
+            lv, sc = C.c_int64(), C.c_double()
+            lib.hevmx_ct_info(vm, r, C.byref(lv), C.byref(sc))
+            ct = np.zeros((2, lv.value, 1 << 15), dtype=np.uint64)
+            lib.hevmx_ct_read(vm, r, ct.ctypes.data_as(C.POINTER(C.c_uint64)))
+            dec = np.zeros(1 << 14)
+            lib.decrypt_result(vm, 0, dec.ctypes.data_as(f64p))
+            out[name, rep] = (ct, (lv.value, sc.value), dec, dt)
+    ct_o, info_o, dec_o, t_oracle = out["oracle", 0]
+    for rep in range(2):
+        ct_g, info_g, dec_g, t_gpu = out["gpu", rep]
+        assert info_g == info_o, rep
+        assert np.array_equal(ct_g, ct_o), f"result ciphertext differs from the oracle (run {rep})"
+        assert np.array_equal(dec_g, dec_o)
+    res = dec_o[:meta["n_out"]] * meta["post_scale"]
+    rms = float(np.sqrt(np.sum((res - expected) ** 2) / res.shape[-1]))
+    assert rms < 1.5e-3
+    with capsys.disabled():
+        print(f"\nResNet-20 program: oracle (CPU port, 1 thread) run() {t_oracle:.1f} s | GPU first run {out['gpu', 0][3]:.3f} s, replay {out['gpu', 1][3]:.3f} s | bit-exact, rms {rms:.2e}")

@@ -9,8 +9,9 @@ _u64p = C.POINTER(C.c_uint64)
 _f64p = C.POINTER(C.c_double)
 
 
-def make_vm(lib, logn, nprimes, seed=0xDACA90, bits=60, keydir=None):
-    """create_context + initFullVM on `lib` with the given ring geometry."""
+def make_vm(lib, logn, nprimes, seed=0xDACA90, bits=60, keydir=None, galois_steps=None):
+    """create_context + initFullVM on `lib` with the given ring geometry.  `galois_steps`: generate Galois keys for
+    these rotation steps only (HEVM_GALOIS_STEPS, SEAL's create_galois_keys(steps)); default = SEAL's default set."""
     d = keydir or tempfile.mkdtemp(prefix="hevm_keys_")
     if not os.path.isfile(os.path.join(d, "hevm_params.bin")):
         old = {k: os.environ.get(k) for k in ("HEVM_LOGN", "HEVM_NUM_PRIMES", "HEVM_SEED", "HEVM_PRIME_BITS")}
@@ -23,16 +24,26 @@ def make_vm(lib, logn, nprimes, seed=0xDACA90, bits=60, keydir=None):
                     os.environ.pop(k, None)
                 else:
                     os.environ[k] = v
-    vm = lib.initFullVM(d.encode(), True)
+    old = os.environ.get("HEVM_GALOIS_STEPS")
+    if galois_steps is not None:
+        os.environ["HEVM_GALOIS_STEPS"] = ",".join(str(int(x)) for x in galois_steps)
+    try:
+        vm = lib.initFullVM(d.encode(), True)
+    finally:
+        if galois_steps is not None:
+            if old is None:
+                os.environ.pop("HEVM_GALOIS_STEPS", None)
+            else:
+                os.environ["HEVM_GALOIS_STEPS"] = old
     return vm, d
 
 
 class VM:
     """Thin convenience wrapper over the hevmx_* hooks of one library."""
 
-    def __init__(self, lib, logn, nprimes, seed=0xDACA90, keydir=None, nct=8, npt=4):
+    def __init__(self, lib, logn, nprimes, seed=0xDACA90, keydir=None, nct=8, npt=4, galois_steps=None):
         self.lib = lib
-        self.vm, self.keydir = make_vm(lib, logn, nprimes, seed, keydir=keydir)
+        self.vm, self.keydir = make_vm(lib, logn, nprimes, seed, keydir=keydir, galois_steps=galois_steps)
         self.logn, self.N, self.L = logn, 1 << logn, nprimes
         p = np.zeros(nprimes, dtype=np.uint64)
         lib.hevmx_primes(self.vm, p.ctypes.data_as(_u64p))
@@ -75,6 +86,14 @@ class VM:
 
     def exec(self, opcode, dst, lhs=0, rhs=0, sync=True):
         self.lib.hevmx_exec(self.vm, opcode, dst, lhs, rhs & 0xFFFF)
+        if sync:
+            self.lib.hevmx_sync(self.vm)
+
+    def exec_batch(self, opcode, dst, lhs, rhs, sync=True):
+        """n independent ops of one opcode in one batched launch (libB200_HEVM.so only)."""
+        arr = [np.ascontiguousarray(np.asarray(v, dtype=np.int64) & (0xFFFF if k == 2 else -1)) for k, v in enumerate((dst, lhs, rhs))]
+        i64p = C.POINTER(C.c_int64)
+        self.lib.hevmx_exec_batch(self.vm, opcode, len(arr[0]), *(a.ctypes.data_as(i64p) for a in arr))
         if sync:
             self.lib.hevmx_sync(self.vm)
 

@@ -3,7 +3,8 @@ import ctypes as C, os, sys, tempfile, time
 from pathlib import Path
 REPO = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(REPO)); sys.path.insert(0, str(REPO / "tests"))
-from dacapo_b200 import _binding, fixtures
+from dacapo_b200 import _binding
+import fixtures
 from util import make_vm
 lib = _binding.bind(os.environ.get("HEVM_LIB", _binding.B200_LIB))
 cst, hv, x, expected, meta = fixtures.resnet20_files(tempfile.mkdtemp())

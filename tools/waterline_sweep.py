@@ -6,7 +6,8 @@ from pathlib import Path
 import numpy as np
 REPO = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(REPO)); sys.path.insert(0, str(REPO / "tests"))
-from dacapo_b200 import _binding, fixtures
+from dacapo_b200 import _binding
+import fixtures
 from util import make_vm
 
 lib = _binding.bind(_binding.B200_LIB)
