@@ -202,9 +202,10 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "hevm_ops_per_s", "value": val, "unit": "ops/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": workload_config(cores, note="CPU restatement of SEAL 4.0 evaluator (oracle/); SEAL not installable offline"),
+        "config": workload_config(args.batch),
         "cpu_baseline": {"value": val, "unit": "ops/s", "cores": cores, "kind": "port",
-                         "sample": f"{cores} independent ciphertext chains (one per core, {ops_per_step // cores} HEVM ops each) per step"},
+                         "sample": f"bounded sample of the workload: {cores} of its independent ciphertext chains per step, one per host core "
+                                   f"({ops_per_step // cores} HEVM ops each); CPU restatement of the SEAL 4.0 evaluator (oracle/), SEAL itself is not installable offline"},
         "e2e": {"value": val, "unit": "ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -238,7 +239,7 @@ def resnet20_real(lib, vm, tmp, reps=3, variant="", cpu=False):
     lib.preprocess(vm)
     t_pre = time.perf_counter() - t0
     out = np.zeros(meta.get("slots", SLOTS))
-    lat, e2e = [], []
+    lat, e2e, first_run = [], [], None
     for i in range(reps + 1):
         t0 = time.perf_counter()
         lib.encrypt(vm, 0, x.ctypes.data_as(f64p), x.size)
@@ -250,6 +251,8 @@ def resnet20_real(lib, vm, tmp, reps=3, variant="", cpu=False):
         if i:
             lat.append(t2 - t1)
             e2e.append(t3 - t0)
+        else:
+            first_run = t2 - t1  # the cold run() of a process: schedule + CUDA-graph capture + instantiate + execute
     res = out[:meta["n_out"]] * meta["post_scale"]
     err = res - expected
     extra = {}
@@ -261,11 +264,14 @@ def resnet20_real(lib, vm, tmp, reps=3, variant="", cpu=False):
     return {**extra, "what": f"encrypted ResNet-20 (SiLU, nt=2^{int(np.log2(meta.get('slots', SLOTS)))} slots, N=2^{meta.get('logN', LOGN)}, 14x60-bit primes, waterline 40), "
                     "synthetic seeded input, weights examples/data/resnet20.silu.model; program compiled by dacapo_b200.compiler "
                     "(not hecate-opt), bootstrap levels from the measured cost profile",
-            "run_latency_s": float(np.median(lat)), "first_run_s": None, "e2e_latency_s": float(np.median(e2e)), "load_preprocess_s": t_pre,
+            "run_latency_s": float(np.median(lat)), "first_run_s": first_run,
+            "latency_note": "run_latency_s = warm run() (CUDA-graph replay); first_run_s = the first run() of the process, which is what one "
+                            "`hc-test` invocation of the reference times (examples/tests/ResNet.py:109-111: a single cold run() per process)",
+            "e2e_latency_s": float(np.median(e2e)), "load_preprocess_s": t_pre,
             "rms": float(np.sqrt(np.sum(err * err) / res.shape[-1])), "argmax_ok": bool(np.argmax(res) == np.argmax(expected)),
             "lowered_ops": meta["lowered_ops"], "hevm_ops": meta["hevm_ops"],
             "reference_README": {"latency_s": 53.726, "rms": 9.515e-4, "hardware": "unspecified CPU, SEAL single thread (README.md:186-187)"},
-            "speedup_vs_README_latency": 53.726 / float(np.median(lat))}
+            "speedup_vs_README_latency": 53.726 / float(np.median(lat)), "speedup_vs_README_latency_first_run": 53.726 / first_run}
 
 
 _CPU_OP_CACHE = {}
@@ -366,6 +372,111 @@ def resnet_mix(lib, vm, tmp, cpu=True, reps=3):
     return res
 
 
+def measure_traffic_ncu(level=TOP, timeout=240):
+    """LIVE DRAM traffic of one rotate at `level`: a short ncu pass over tools/ks_probe.py with --cache-control none (L2
+    residency as in a real run: the probe's warm-up ops ran just before, with other keys) -- dram__bytes_read + write
+    per kernel of the profiled rotate.  Returns None when ncu is not usable on this box."""
+    import csv
+    import io
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.isfile(ncu):
+        return None
+    log = tempfile.mktemp(prefix="ncu_traffic_", suffix=".csv")
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum", "--cache-control", "none",
+           "--clock-control", "none", "--profile-from-start", "off", "--print-units", "base", "--csv", "--log-file", log,
+           sys.executable, str(REPO / "tools" / "ks_probe.py"), str(level)]
+    env = dict(os.environ, HEVM_FUSED="0")
+    try:
+        subprocess.run(cmd, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=timeout, check=True)
+        rows = list(csv.reader(io.StringIO(open(log).read())))
+    except Exception as e:  # no profiling permission, ncu missing, timeout ...
+        return {"error": f"{type(e).__name__}"}
+    hdr = next((i for i, r in enumerate(rows) if r and r[0] == "ID"), None)
+    if hdr is None:
+        return {"error": "no ncu rows"}
+    ix = {h: i for i, h in enumerate(rows[hdr])}
+    kern = {}
+    for r in rows[hdr + 1:]:
+        if len(r) < len(ix):
+            continue
+        k = kern.setdefault(int(r[ix["ID"]]), {"name": r[ix["Kernel Name"]].split("(")[0]})
+        try:
+            k[r[ix["Metric Name"]]] = float(r[ix["Metric Value"]].replace(",", ""))
+        except ValueError:
+            pass
+    ids = sorted(kern)
+    rot = [kern[i] for i in ids[:5]]  # the probe's first profiled op is the rotate: 5 launches
+    if len(rot) < 5 or "k_mac" not in rot[2]["name"]:
+        return {"error": "unexpected launch list", "names": [k["name"] for k in rot]}
+    byt = lambda k: k.get("dram__bytes_read.sum", 0.0) + k.get("dram__bytes_write.sum", 0.0)
+    return {"level": level, "cache_control": "none", "k_mac_dram_bytes": byt(rot[2]), "rotate_dram_bytes": sum(byt(k) for k in rot),
+            "per_kernel": [{"kernel": k["name"].replace("void ", ""), "dram_bytes": byt(k), "ns_under_ncu": k.get("gpu__time_duration.sum")} for k in rot]}
+
+
+def batch_sweep(lib, vm, peak, levels=(1, 4, 8, 13), batches=(1, 8, 64, 256)):
+    """BASELINE.json configs[1] "batched ciphertexts": n independent ciphertexts per launch (hevmx_exec_batch, one
+    persistent kernel per op class over the whole batch; n = 1 is the ordinary op-by-op path) -- microseconds per op
+    and the fraction of the HBM roofline on SURVEY 8(d) algorithmic bytes (key bytes counted per ciphertext)."""
+    from dacapo_b200 import profile
+    u64p, i64p = C.POINTER(C.c_uint64), C.POINTER(C.c_int64)
+    nmax = max(batches)
+    primes = np.zeros(NPRIMES, dtype=np.uint64)
+    lib.hevmx_primes(vm, primes.ctypes.data_as(u64p))
+    lib.hevmx_resize(vm, 2 * nmax, 1)
+    rng = np.random.default_rng(11)
+    out = {}
+    for l in levels:
+        a = np.zeros((2, l, N), dtype=np.uint64)
+        for i in range(l):
+            a[:, i, :] = rng.integers(0, int(primes[i]), size=(2, N), dtype=np.uint64)
+        for r in range(nmax):
+            lib.hevmx_ct_write(vm, r, a.ctypes.data_as(u64p), l, 2.0 ** 40)
+        for name, opc in (("rotate", asm.ROTATE), ("mulcc", asm.MULCC), ("rescale", asm.RESCALE)):
+            if opc == asm.RESCALE and l < 2:
+                continue
+            row = {}
+            for n in batches:
+                src = np.arange(n, dtype=np.int64)
+                dst = src + nmax
+                steps = (1, -2, 4, -8, 16, -32, 64, -128)  # eight different Galois keys per batch: no key sits in L2 by construction
+                rhs = src.copy() if opc == asm.MULCC else (np.array([steps[k % 8] & 0xFFFF for k in range(n)], dtype=np.int64) if opc == asm.ROTATE else np.zeros(n, dtype=np.int64))
+                reps = max(2, 128 // n)
+                call = lambda: lib.hevmx_exec_batch(vm, opc, n, dst.ctypes.data_as(i64p), src.ctypes.data_as(i64p), rhs.ctypes.data_as(i64p))
+                call()
+                lib.hevmx_sync(vm)
+                lib.hevmx_timer(vm, 0)
+                for _ in range(reps):
+                    call()
+                us = lib.hevmx_timer(vm, 1) * 1e3 / (reps * n)
+                row[str(n)] = {"us_per_op": round(us, 2), "frac": round(profile.algorithmic_bytes(name, l) / (us * 1e-6) / 1e9 / peak, 4)}
+            out.setdefault(name, {})[str(l)] = row
+    return out
+
+
+def oracle_resnet_subprocess():
+    """Starts the CPU port (oracle, one thread) on the committed ResNet-20 program in a separate process: its run() time is
+    MEASURED (~70 s on the GPU box's host) while the GPU sections of the bench proceed; joined at the end."""
+    code = (
+        "import sys, time, json, ctypes as C, tempfile\n"
+        f"sys.path.insert(0, {str(REPO)!r}); sys.path.insert(0, {str(REPO / 'tests')!r})\n"
+        "import numpy as np, fixtures\n"
+        "from dacapo_b200 import _binding\n"
+        "from util import make_vm\n"
+        "lib = _binding.bind(fixtures.ORACLE_LIB)\n"
+        "cst, hv, x, expected, meta = fixtures.resnet20_files(tempfile.mkdtemp())\n"
+        "vm, _ = make_vm(lib, 15, 14)\n"
+        "t = time.perf_counter(); lib.load(vm, cst.encode(), hv.encode()); lib.preprocess(vm); tp = time.perf_counter() - t\n"
+        "f64p = C.POINTER(C.c_double)\n"
+        "lib.encrypt(vm, 0, x.ctypes.data_as(f64p), x.size)\n"
+        "t = time.perf_counter(); lib.run(vm); tr = time.perf_counter() - t\n"
+        "out = np.zeros(1 << 14); lib.decrypt_result(vm, 0, out.ctypes.data_as(f64p))\n"
+        "res = out[:meta['n_out']] * meta['post_scale']\n"
+        "print(json.dumps({'run_s': tr, 'load_preprocess_s': tp, 'rms': float(np.sqrt(np.sum((res - expected) ** 2) / res.shape[-1]))}))\n")
+    subprocess.run(["make", "-s", "-C", str(REPO / "oracle")], check=True)
+    return subprocess.Popen([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -411,6 +522,9 @@ def main():
         return D.max_over_ranks(x, device="cuda")
 
     lib = _binding.bind(_binding.B200_LIB)  # raises if the CUDA library is missing
+    oracle_proc = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.no_resnet_mix:
+        oracle_proc = oracle_resnet_subprocess()  # CPU port of the ResNet-20 program, measured while the GPU sections run
     keydir = tempfile.mkdtemp(prefix=f"hevm_bench_keys_r{rank}_")
     vm = make_vm(lib, keydir)
     prog, steps, nks = build_program(args.batch)
@@ -518,39 +632,54 @@ def main():
                 "ms_per_step": 1e3 * e2e_s / args.steps},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "op_roofline": op_roof,
         "keyswitch_per_s": nks * world * args.steps / (ms / 1e3), "hevm_ops_per_step": nops, "check_max_err": err,
-        "kernels": kern,
     }
+    details = {"kernels": kern}  # bulky tables go to bench_details.json (the JSON line stays readable in a log tail)
 
     if rank == 0 and world == 1 and not args.no_resnet_mix:
-        line["resnet20"] = resnet20_real(lib, vm, tmp, cpu=not args.no_cpu_baseline)
-        line["resnet20_nt16"] = resnet20_real(lib, vm, tempfile.mkdtemp(prefix="hevm_bench_nt16_"), reps=2, variant="_nt16")
-        line["resnet20_opmix"] = resnet_mix(lib, vm, tmp, cpu=not args.no_cpu_baseline)
+        r20 = resnet20_real(lib, vm, tmp, cpu=not args.no_cpu_baseline)
+        details["resnet20"] = dict(r20)
+        line["resnet20"] = {k: r20[k] for k in ("run_latency_s", "first_run_s", "e2e_latency_s", "rms", "argmax_ok", "hevm_ops", "speedup_vs_README_latency",
+                                                 "speedup_vs_README_latency_first_run", "cpu_port_estimate_s") if k in r20}
+        r16 = resnet20_real(lib, vm, tempfile.mkdtemp(prefix="hevm_bench_nt16_"), reps=2, variant="_nt16")
+        details["resnet20_nt16"] = r16
+        line["resnet20_nt16"] = {k: r16[k] for k in ("run_latency_s", "first_run_s", "rms", "argmax_ok", "hevm_ops")}
+        details["resnet20_opmix"] = resnet_mix(lib, vm, tmp, cpu=not args.no_cpu_baseline)
 
     if (args.op_table or world == 1) and not args.no_op_table and rank == 0:
         from dacapo_b200 import profile
         table, prof = profile.emit_profile(str(REPO / "profiled_B200_GPU.json"), lib, vm)
         kl13 = table.pop("_kernels_rotate_l13", None)
-        line["op_table_us"] = {op: {str(l): round(v, 2) for l, v in lv.items()} for op, lv in table.items()}
+        details["op_table_us"] = {op: {str(l): round(v, 2) for l, v in lv.items()} for op, lv in table.items()}
         if kl13 and "fwd_B_mac" in kl13:
-            # roofline of the dominant kernel on ONE well-defined launch shape: the key-switch MAC kernel at level 13
+            # roofline of the dominant kernel on ONE well-defined launch shape: the key-switch MAC kernel at level 13.
+            # Algorithmic (compulsory) bytes of that launch, SURVEY 8(d) style: the key 2l(l+1)B, the NTT-form target it
+            # multiplies on the diagonal lB and the accumulators it writes 2(l+1)B.  The half-transformed mod-up matrix
+            # l(l+1)B that the previous kernel hands over is NOT compulsory traffic and is reported separately.
             l = TOP
-            alg_bytes = (3 * l * l + 5 * l + 2) * BYTES_LIMB
+            alg_bytes = (2 * l * (l + 1) + l + 2 * (l + 1)) * BYTES_LIMB
+            inter_bytes = l * (l + 1) * BYTES_LIMB
             us = 1e3 * kl13["fwd_B_mac"]["ms"] / kl13["fwd_B_mac"]["launches"]
-            traffic = None
-            try:
-                traffic = json.loads((REPO / "profiles" / "r01_mac_traffic.json").read_text())["k_mac_l13_dram_bytes"]
-            except Exception:
-                pass
+            tr = measure_traffic_ncu(l)  # LIVE: ncu pass with --cache-control none inside this run
+            details["traffic_ncu"] = tr
             tot = sum(k["ms"] for k in kl13.values())
-            line["roofline_all_levels"] = line["roofline"]
+            details["roofline_all_levels"] = line["roofline"]
             line["roofline"] = {"bound": "hbm", "kernel": "k_mac (key-switch inner product + forward pass B), level 13", "achieved": alg_bytes / (us * 1e-6) / 1e9,
-                                "peak": peak, "unit": "GB/s", "frac": alg_bytes / (us * 1e-6) / 1e9 / peak, "traffic": traffic,
-                                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": us, "share_of_rotate_l13": kl13["fwd_B_mac"]["ms"] / tot,
-                                "peak_source": peak_src, "kernels_rotate_l13": kl13,
-                                "ceiling_note": "64-bit Shoup butterflies top out at 1.04e12/s on this GPU (tools/pipe_bench.cu): >= 0.236 us per limb-NTT, "
-                                                "i.e. integer pipes, not HBM, bound this kernel"}
-        line["op_roofline_l13"] = {op: {"us": table[op][13], "frac": profile.algorithmic_bytes(op, 13) / (table[op][13] * 1e-6) / 1e9 / peak}
+                                "peak": peak, "unit": "GB/s", "frac": alg_bytes / (us * 1e-6) / 1e9 / peak,
+                                "traffic": (tr or {}).get("k_mac_dram_bytes"), "traffic_source": "ncu --cache-control none, measured in this run" if tr and "k_mac_dram_bytes" in tr else f"unavailable: {tr}",
+                                "algorithmic_bytes_per_launch": alg_bytes, "intermediate_bytes_per_launch": inter_bytes,
+                                "frac_with_intermediate": (alg_bytes + inter_bytes) / (us * 1e-6) / 1e9 / peak,
+                                "avg_launch_us": us, "share_of_rotate_l13": kl13["fwd_B_mac"]["ms"] / tot,
+                                "rotate_l13_dram_bytes": (tr or {}).get("rotate_dram_bytes"), "rotate_l13_algorithmic_bytes": profile.algorithmic_bytes("rotate", l),
+                                "peak_source": peak_src,
+                                "ceiling_note": "issue-bound, not HBM-bound: IMAD / LOP3 / SHF issue at 0.5 per clk per SMSP and do not overlap (tools/pipe_bench2.cu), "
+                                                "a 64-bit Shoup butterfly costs 39 clk per warp => >= 0.236 us per limb-NTT vs 0.080 us at the HBM roofline"}
+            details["kernels_rotate_l13"] = kl13
+        line["op_roofline_l13"] = {op: {"us": round(table[op][13], 2), "frac": round(profile.algorithmic_bytes(op, 13) / (table[op][13] * 1e-6) / 1e9 / peak, 4)}
                                    for op in ("rotate", "mulcc", "rescale", "addcc", "mulcp")}
+        sweep = batch_sweep(lib, vm, peak)
+        details["batch_sweep"] = sweep
+        line["batch_sweep_us_per_op"] = {op: {l: {n: v["us_per_op"] for n, v in row.items()} for l, row in lv.items()} for op, lv in sweep.items()}
+        line["op_roofline_by_batch_l13"] = {op: {n: v["frac"] for n, v in lv["13"].items()} for op, lv in sweep.items()}
 
     if rank == 0 and world == 1 and not args.no_op_table:
         # stand-alone NTT / INTT throughput on device-resident limbs (metric row "NTT/INTT ops/s vs HBM roofline"):
@@ -577,6 +706,18 @@ def main():
         line["cpu_baseline"] = {"value": ops * reps / t, "unit": "ops/s", "cores": 1, "kind": "port",
                                 "sample": f"1 ciphertext chain ({ops} HEVM ops, levels 13..1) x {reps} repetitions on one host core "
                                           f"(the reference's SEAL evaluator is single-threaded); host has {os.cpu_count()} cores"}
+    if oracle_proc is not None:  # the MEASURED run() of the CPU port on the very ResNet-20 program
+        try:
+            o, _ = oracle_proc.communicate(timeout=600)
+            cpu = json.loads(o.strip().splitlines()[-1])
+            line["resnet20"]["cpu_port_s"] = cpu["run_s"]
+            line["resnet20"]["speedup_vs_cpu_port"] = cpu["run_s"] / line["resnet20"]["run_latency_s"]
+            line["resnet20"]["speedup_vs_cpu_port_first_run"] = cpu["run_s"] / line["resnet20"]["first_run_s"]
+            details["resnet20"]["cpu_port"] = cpu
+        except Exception as e:
+            line["resnet20"]["cpu_port_s"] = None
+            details["resnet20"]["cpu_port_error"] = repr(e)
+            oracle_proc.kill()
     if world > 1 and not args.no_sharded:
         # BASELINE.json configs[4]: RNS-limb-sharded key switch at N = 2^16 over the N GPUs (NCCL all-gather of the digits
         # + broadcast of the rounded special limb); not part of `value`, reported beside it
@@ -584,6 +725,10 @@ def main():
         sk = sharded.measure(lib, rank, world, logn=16, nprimes=30)
         line["sharded_keyswitch"] = sk
     if rank == 0:
+        try:
+            (REPO / "bench_details.json").write_text(json.dumps({**line, **details}, indent=1))
+        except OSError:
+            pass
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

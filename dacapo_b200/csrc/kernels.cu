@@ -126,10 +126,10 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
   return v;
 }
 #ifndef FUSED_POLL_ALL
-#define FUSED_POLL_ALL 0
+#define FUSED_POLL_ALL 1
 #endif
 #ifndef FUSED_POLL_NS
-#define FUSED_POLL_NS 64
+#define FUSED_POLL_NS 32
 #endif
 template <int LOGA, int MODE> __global__ void __launch_bounds__(CTA_THREADS, 4) k_ks_fused(KsFusedArgs A) {
   __shared__ int s_ticket, s_last;
@@ -364,6 +364,62 @@ INSTANTIATE(6)
 INSTANTIATE(7)
 INSTANTIATE(8)
 INSTANTIATE(9)
+
+// =====================================================================================
+// Peer-to-peer exchange kernels of the limb-sharded key switch: plain stores into peer HBM over NVLink (the peer blocks
+// are CUDA-IPC mappings), completion by an epoch flag written with system-scope release after a system-scope fence.
+// =====================================================================================
+__global__ void __launch_bounds__(256) k_p2p_push(const u64 *src, size_t words, PeerPtrs peer, size_t dst_off, int self, int world,
+                                                  unsigned *done_ctr, size_t flag_off, unsigned long long epoch) {
+  const size_t nvec = words / 2; // 16-byte pieces (limb rows are multiples of 16 bytes)
+  for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
+    u64 a, b;
+    asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(src + 2 * v) : "memory");
+    for (int g = 0; g < world; g++)
+      if (g != self) asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"(peer.p[g] + dst_off + 2 * v), "l"(a), "l"(b) : "memory");
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(done_ctr, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last) { // every CTA's stores are ordered before its increment: publish
+    if (threadIdx.x == 0) *done_ctr = 0;
+    if ((int)threadIdx.x < world && (int)threadIdx.x != self) {
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer.p[threadIdx.x] + flag_off + self), "l"(epoch) : "memory");
+    }
+  }
+}
+__global__ void k_p2p_wait(const u64 *block, size_t flag_off, int self, int world, int only, unsigned long long epoch) {
+  const int g = threadIdx.x;
+  if (g < world && g != self && (only < 0 || g == only)) {
+    unsigned long long v;
+    const long long t0 = clock64();
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(block + flag_off + g) : "memory");
+      if (v < epoch) {
+        __nanosleep(64);
+        if (clock64() - t0 > 20000000000ll) { // ~10 s: a peer never arrived -- fail loudly instead of hanging the GPU
+          printf("[b200-hevm] fatal: p2p wait timed out (rank %d waiting for rank %d, epoch %llu)\n", self, g, epoch);
+          __trap();
+        }
+      }
+    } while (v < epoch);
+  }
+}
+void launch_p2p_push(cudaStream_t s, const u64 *src, size_t words, const PeerPtrs &peer, size_t dst_off, int self, int world,
+                     unsigned *done_ctr, size_t flag_off, unsigned long long epoch) {
+  size_t g = (words / 2 + 255) / 256;
+  if (g < 1) g = 1;
+  if (g > 148 * 2) g = 148 * 2;
+  k_p2p_push<<<(unsigned)g, 256, 0, s>>>(src, words, peer, dst_off, self, world, done_ctr, flag_off, epoch);
+  POST_LAUNCH_S(s);
+}
+void launch_p2p_wait(cudaStream_t s, const u64 *block, size_t flag_off, int self, int world, int only, unsigned long long epoch) {
+  k_p2p_wait<<<1, 32, 0, s>>>(block, flag_off, self, world, only, epoch);
+  POST_LAUNCH_S(s);
+}
 
 // =====================================================================================
 // element-wise kernels.  One thread = 4 consecutive coefficients (256-bit accesses).

@@ -56,6 +56,18 @@ struct GpuLauncher {
   template <int LOGA, int MODE> void ks_fused(const KsFusedArgs &a);
 };
 
+// ---- peer-to-peer exchange of the limb-sharded key switch (NVLink, CUDA IPC mapped peer memory) ----
+// Every rank owns one exchange block with the same layout; peer.p[g] = that block of rank g mapped into this process.
+struct PeerPtrs {
+  u64 *p[8];
+};
+// copy `words` u64 from `src` (local) to offset `dst_off` of every peer's block, then -- once every CTA's stores are
+// system-visible -- write `epoch` into flag word `flag_off + self` of every peer's block
+void launch_p2p_push(cudaStream_t s, const u64 *src, size_t words, const PeerPtrs &peer, size_t dst_off, int self, int world,
+                     unsigned *done_ctr, size_t flag_off, unsigned long long epoch);
+// spin until flag word `flag_off + g` of the LOCAL block is >= epoch for every peer g (only >= 0: just that peer)
+void launch_p2p_wait(cudaStream_t s, const u64 *block, size_t flag_off, int self, int world, int only, unsigned long long epoch);
+
 // ---- element-wise ciphertext kernels (SEAL add/negate/add_plain/multiply_plain, limb drop) ----
 // out = acc + sum_k x[k] * p[k] (k < n <= 8): a chain of multiply_plain + add, one HBM pass
 struct MulpTerms {

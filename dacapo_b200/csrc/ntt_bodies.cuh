@@ -319,8 +319,9 @@ struct ArgsFwdB {
   int nd, prime0, pstep;
   int l, sp;
   // MAC
-  const u64 *key; // [L-1][2][L][N]
-  int Ltot;
+  const u64 *key; // [L-1][2][Ltot][N]; limb-sharded storage: only the limbs [key_t0, key_t0 + Ltot) of every key polynomial
+  int Ltot;       // limbs per stored key polynomial (L for a whole key); the special limb is always the LAST stored limb
+  int key_t0;     // prime index of the first stored limb (0 for a whole key)
   int ld;            // how the NTT-form target (diagonal term) is obtained: LD_*
   const u64 *tgt;    // PLAIN: target [l][N]; GALOIS: c1 (gather with elt); PRODUCT: a1
   const u64 *tgt2;   // PRODUCT: b1
@@ -425,13 +426,25 @@ template <int LOGA> HD void body_mac_warp(const ArgsFwdB &a, int job, int w, Lan
 #ifndef MAC_KEY_BATCH
 #define MAC_KEY_BATCH 4
 #endif
+#ifndef MAC_KEY_EVICT_FIRST
+#define MAC_KEY_EVICT_FIRST 1
+#endif
 struct U2 {
   u64 a, b;
 };
 HD U2 ldg_key2(const u64 *p) { // 16 bytes of key material (read-only for the life of the VM)
 #if defined(__CUDA_ARCH__)
+#if MAC_KEY_EVICT_FIRST
+  // every key byte is used exactly once per key switch: mark its L2 lines evict-first so that streaming 95 MB of key
+  // does not push the mod-up matrix s2 (written by the previous kernel, read by this one) out of the 126 MB L2
+  u64 pol, a, b;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u64 {%0,%1}, [%2], %3;" : "=l"(a), "=l"(b) : "l"(p), "l"(pol));
+  return U2{a, b};
+#else
   const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(p));
   return U2{v.x, v.y};
+#endif
 #else
   return U2{p[0], p[1]};
 #endif
@@ -470,7 +483,8 @@ template <int LOGA> HD void body_mac_dot(const ArgsFwdB &a, int job, int tid, co
   const int r = job & (Geo<LOGA>::ROWS - 1), Iidx = mac_Iidx<LOGA>(a, job), I = (Iidx == a.l) ? a.sp : Iidx;
   const ModQ m = T.mod[I];
   const size_t kstride = (size_t)a.Ltot * N; // words between key[J][0] and key[J][1]
-  const u64 *kp = a.key + (size_t)I * N + r * 256 + 2 * tid;
+  const int Iloc = (Iidx == a.l) ? a.Ltot - 1 : Iidx - a.key_t0; // stored limb index of target I
+  const u64 *kp = a.key + (size_t)Iloc * N + r * 256 + 2 * tid;
   const size_t dstride = 2 * kstride; // words between consecutive digits of the key
   const u64 pol = 0;
   (void)pol;

@@ -12,6 +12,7 @@
 // ring-size independent interface (the VM holds one of these per lane)
 struct OpsIface {
   Scratch sc;
+  int key_L = 0, key_t0 = 0; // limb-sharded KEY STORAGE (this rank stores limbs [key_t0, key_t0 + key_L) of every key); 0 = whole keys
   virtual ~OpsIface() {}
   // limb k is transformed under prime prime0 + (pmod ? k % pmod : k) * pstep (pmod: several polynomials of pmod limbs each)
   virtual void ntt_fwd(const u64 *src, u64 *dst, int nl, int prime0, int pstep, int pmod = 0) = 0;
@@ -208,7 +209,7 @@ template <class LA, int LOGA> struct HeOps : OpsIface {
       x.T = T, x.src = sc.t, x.dst = sc.s2, x.l = l, x.sp = sp(), x.t0 = tlo, x.nt = nt;
       la.template fwd_A<LOGA, PRE_MODUP>(x, nt * l * TILES_A);
       ArgsFwdB m{};
-      m.T = T, m.src = sc.s2, m.dst = sc.acc, m.l = l, m.sp = sp(), m.key = key, m.Ltot = L, m.ld = mode, m.elt = elt;
+      m.T = T, m.src = sc.s2, m.dst = sc.acc, m.l = l, m.sp = sp(), m.key = key, m.Ltot = key_L ? key_L : L, m.key_t0 = key_t0, m.ld = mode, m.elt = elt;
       m.tgt = a + pitch, m.tgt2 = (mode == LD_PRODUCT) ? b + pitch : nullptr, m.sp_rows = sc.s1, m.i_end = thi;
       la.template mac<LOGA>(m, nt * ROWS);
       if (own_sp) {

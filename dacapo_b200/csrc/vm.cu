@@ -105,6 +105,32 @@ struct VM {
   // to the key seed with hevmx_set_enc_counter.
   Seed256 seed{}, enc_seed{};
   u64 enc_counter = 0;
+  // Limb-sharded KEY STORAGE across the GPUs of one node ("each GPU holds only its limbs of every key"):
+  // with HEVM_SHARD_RANK / HEVM_SHARD_WORLD set, rank g keeps only the limbs [own_lo, own_hi) of the L key-level limbs
+  // of every key-switch key (static, contiguous, balanced; the special limb L-1 belongs to the last rank) and the VM
+  // only accepts the limb-sharded ops (hevmx_ks_shard_p2p).  At level l its key-switch targets are that range cut to l.
+  int shard_rank = 0, shard_world = 1, own_lo = 0, own_hi = 0;
+  bool keys_sharded() const { return shard_world > 1; }
+  int key_limbs() const { return keys_sharded() ? own_hi - own_lo : L; }
+  void my_targets(int l, int &tlo, int &thi) const {
+    tlo = std::min(own_lo, l);
+    thi = (own_hi == L) ? l + 1 : std::min(own_hi, l);
+  }
+  // peer-to-peer exchange block of the sharded key switch (one cudaMalloc, exported over CUDA IPC):
+  //   digits t[2][L][N] | rounded rows rnd[2][2][N] | flags[2][8] u64 | done counter      ([2] = double buffer by epoch parity)
+  struct P2P {
+    bool on = false;
+    int rank = 0, world = 1;
+    u64 *block = nullptr;
+    PeerPtrs peer{};
+    unsigned long long epoch = 0;
+    cudaEvent_t ev[6] = {};
+    bool timed = false;
+  } p2p;
+  size_t p2p_t_off(int parity) const { return (size_t)parity * L * N; }
+  size_t p2p_rnd_off(int parity) const { return (size_t)2 * L * N + (size_t)parity * 2 * N; }
+  size_t p2p_flag_off(int slot) const { return (size_t)2 * L * N + 4 * N + (size_t)slot * 8; }
+  size_t p2p_words() const { return (size_t)2 * L * N + 4 * N + 16 + 2; }
   u64 *d_ctr_base = nullptr; // device copy of the encryption counter base (read by the samplers)
   std::vector<Lane> lanes;
   Lane *ln = nullptr; // lane the host code is currently issuing on
@@ -158,6 +184,12 @@ struct VM {
       for (auto &w : enc_seed.k) w = rd();
     }
     pitch = (size_t)(L - 1) * N;
+    if (const char *e = std::getenv("HEVM_SHARD_WORLD")) {
+      shard_world = std::max(1, std::atoi(e));
+      shard_rank = std::getenv("HEVM_SHARD_RANK") ? std::atoi(std::getenv("HEVM_SHARD_RANK")) : 0;
+      if (shard_world > 8 || shard_rank < 0 || shard_rank >= shard_world) die("HEVM_SHARD_RANK / HEVM_SHARD_WORLD out of range (at most 8 ranks)");
+    }
+    own_lo = (int)((long)L * shard_rank / shard_world), own_hi = (int)((long)L * (shard_rank + 1) / shard_world);
     P.build(logN, L, (int)pf.bits);
     Tw *d_tw = upload(P.tw), *d_itw = upload(P.itw);
     P.tab.tw = d_tw, P.tab.itw = d_itw;
@@ -178,6 +210,7 @@ struct VM {
       l.la.stream = l.stream;
       l.ops = make_ops(l.la, dT, logN, L);
       l.ops->sc.carve(new_scratch(), L, N);
+      if (keys_sharded()) l.ops->key_L = key_limbs(), l.ops->key_t0 = own_lo;
       l.d_work = dalloc<double2>(N);
       l.d_maxbits = dalloc<unsigned long long>(1);
       l.d_vals = dalloc<double>(slots);
@@ -272,13 +305,23 @@ struct VM {
     ln->ops->ntt_fwd(ln->d_e, ln->d_e, L, 0, 1);
     launch_ksk_finish(ln->stream, dT, logN, L, c0, c1, d_sk, ln->d_e, newkey, digit);
   }
+  u64 *ksk_tmp = nullptr; // [2][L][N]: one digit of a key, before its owned limbs are kept (sharded storage only)
   u64 *make_ksk(u64 key_id, const u64 *newkey) {
-    u64 *key = dalloc<u64>((size_t)(L - 1) * 2 * L * N);
+    const size_t KL = (size_t)key_limbs();
+    u64 *key = dalloc<u64>((size_t)(L - 1) * 2 * KL * N);
+    if (keys_sharded() && !ksk_tmp) ksk_tmp = dalloc<u64>((size_t)2 * L * N);
     for (int J = 0; J < L - 1; J++) {
-      u64 *c0 = key + ((size_t)J * 2 + 0) * L * N, *c1 = key + ((size_t)J * 2 + 1) * L * N;
-      enc_zero_sym(ksk_stream(key_id, J, 0, 0), ksk_stream(key_id, J, 1, 0), c0, c1, newkey, J);
+      u64 *c0 = key + ((size_t)J * 2 + 0) * KL * N, *c1 = key + ((size_t)J * 2 + 1) * KL * N;
+      if (!keys_sharded()) {
+        enc_zero_sym(ksk_stream(key_id, J, 0, 0), ksk_stream(key_id, J, 1, 0), c0, c1, newkey, J);
+      } else { // the digit is generated whole (its randomness is defined over all limbs), then only the owned limbs are stored
+        u64 *t0 = ksk_tmp, *t1 = ksk_tmp + (size_t)L * N;
+        enc_zero_sym(ksk_stream(key_id, J, 0, 0), ksk_stream(key_id, J, 1, 0), t0, t1, newkey, J);
+        CUDA_CHECK(cudaMemcpyAsync(c0, t0 + (size_t)own_lo * N, KL * N * 8, cudaMemcpyDeviceToDevice, ln->stream));
+        CUDA_CHECK(cudaMemcpyAsync(c1, t1 + (size_t)own_lo * N, KL * N * 8, cudaMemcpyDeviceToDevice, ln->stream));
+      }
     }
-    launch_key_split(ln->stream, key, (size_t)(L - 1) * 2 * L * N); // storage format of the key inner product
+    launch_key_split(ln->stream, key, (size_t)(L - 1) * 2 * KL * N); // storage format of the key inner product
     return key;
   }
   u64 galois_elt_from_step(int step) const {
@@ -464,6 +507,7 @@ struct VM {
     case 1: { // rotate
       CtReg &s = ctr(op.lhs), &d = ctr(op.dst);
       if (s.level < 1) die("rotate: empty source register");
+      if (keys_sharded() && (int16_t)op.rhs != 0) die("this VM stores limb-sharded keys (HEVM_SHARD_WORLD): use the sharded ops");
       std::vector<int> steps;
       rotate_steps((int16_t)op.rhs, steps);
       if (steps.empty()) {
@@ -530,6 +574,7 @@ struct VM {
     case 8: { // mulcc = multiply + relinearize, one fused key-switch pipeline
       CtReg &a = ctr(op.lhs), &b = ctr(op.rhs), &d = ctr(op.dst);
       if (a.level != b.level || a.level < 1) die("mulcc: level mismatch");
+      if (keys_sharded()) die("this VM stores limb-sharded keys (HEVM_SHARD_WORLD): use the sharded ops");
       const int l = a.level;
       const double sc = a.scale * b.scale;
       ln->ops->keyswitch(LD_PRODUCT, a.d, b.d, d.d, pitch, l, d_relin, 0);
@@ -563,6 +608,55 @@ struct VM {
     }
     default: break; // 0 = encode (done in preprocess), 0xFFFF = tensor.empty placeholder
     }
+  }
+
+  // ---------------------------------------------------------------- limb-sharded key switch over peer memory
+  // One call = the whole sharded rotation / multiply+relinearise of this rank, no host synchronisation:
+  //   stage 1 (own data limbs -> coefficient digits, written into this rank's exchange block)
+  //   push the own digit rows into every peer's block over NVLink + epoch flag ; wait for every peer's flag
+  //   stage 2 (mod-up + key inner product for the own targets; the special limb's owner also rounds it)
+  //   owner of the special limb pushes the two rounded rows + flag ; the others wait for it
+  //   stage 3 (mod-down of the own data limbs)
+  // The exchange buffers are double-buffered by the parity of the key-switch sequence number: a rank that runs ahead
+  // writes buffer (n+1) & 1 while a slower peer may still read buffer n & 1; it cannot get two key switches ahead
+  // because each one needs every peer's digits.
+  void ks_shard_p2p(int mode, CtReg &d, const CtReg &a, const CtReg *b, const u64 *key, u32 elt) {
+    if (!p2p.on) die("hevmx_p2p_setup has not been called");
+    Lane &L0 = lanes[0];
+    ln = &L0;
+    const int l = a.level;
+    int tlo, thi;
+    my_targets(l, tlo, thi);
+    const int dhi = std::min(thi, l), nd = std::max(0, dhi - tlo);
+    const bool own_sp = thi == l + 1;
+    int sp_owner = p2p.world - 1;
+    const unsigned long long e = ++p2p.epoch;
+    const int par = (int)(e & 1);
+    Scratch &sc = L0.ops->sc;
+    u64 *save_t = sc.t, *save_rnd = sc.rnd;
+    sc.t = p2p.block + p2p_t_off(par), sc.rnd = p2p.block + p2p_rnd_off(par);
+    unsigned *done = reinterpret_cast<unsigned *>(p2p.block + p2p_words() - 2);
+    auto mark = [&](int i) {
+      if (p2p.timed) CUDA_CHECK(cudaEventRecord(p2p.ev[i], L0.stream));
+    };
+    const u64 *bd = b ? b->d : nullptr;
+    mark(0);
+    L0.ops->ks_shard_stage(1, mode, a.d, bd, d.d, pitch, l, key, elt, tlo, thi);
+    mark(1);
+    launch_p2p_push(L0.stream, sc.t + (size_t)tlo * N, (size_t)nd * N, p2p.peer, p2p_t_off(par) + (size_t)tlo * N, p2p.rank, p2p.world, done,
+                    p2p_flag_off(0), e);
+    launch_p2p_wait(L0.stream, p2p.block, p2p_flag_off(0), p2p.rank, p2p.world, -1, e);
+    mark(2);
+    L0.ops->ks_shard_stage(2, mode, a.d, bd, d.d, pitch, l, key, elt, tlo, thi);
+    mark(3);
+    if (own_sp)
+      launch_p2p_push(L0.stream, sc.rnd, (size_t)2 * N, p2p.peer, p2p_rnd_off(par), p2p.rank, p2p.world, done, p2p_flag_off(1), e);
+    else
+      launch_p2p_wait(L0.stream, p2p.block, p2p_flag_off(1), p2p.rank, p2p.world, sp_owner, e);
+    mark(4);
+    L0.ops->ks_shard_stage(3, mode, a.d, bd, d.d, pitch, l, key, elt, tlo, thi);
+    mark(5);
+    sc.t = save_t, sc.rnd = save_rnd;
   }
 
   // ---------------------------------------------------------------- batched ops (independent ciphertexts, one launch)
@@ -1290,7 +1384,7 @@ int64_t hevmx_key_read(void *h, int which, uint64_t elt, uint64_t *out) {
   VM *vm = V(h);
   const u64 *src = nullptr;
   size_t w = 0;
-  const size_t kw = (size_t)(vm->L - 1) * 2 * vm->L * vm->N;
+  const size_t kw = (size_t)(vm->L - 1) * 2 * vm->key_limbs() * vm->N; // limb-sharded storage: [L-1][2][own limbs][N]
   if (which == 0) src = vm->d_sk, w = (size_t)vm->L * vm->N;
   if (which == 1) src = vm->d_pk, w = (size_t)2 * vm->L * vm->N;
   if (which == 2) src = vm->d_relin, w = kw;
@@ -1351,6 +1445,119 @@ void hevmx_mulcc_shard_stage(void *h, int stage, int64_t dst, int64_t lhs, int64
   if (stage == 1) vm->shard_scale = a.scale * b.scale;
   vm->ln->ops->ks_shard_stage(stage, LD_PRODUCT, a.d, b.d, d.d, vm->pitch, l, vm->d_relin, 0, (int)tlo, (int)thi);
   if (stage == 3) d.level = l, d.scale = vm->shard_scale;
+}
+// ---- peer-to-peer limb-sharded key switch (include/hevm_ext.h) ----
+void hevmx_p2p_setup(void *h, int64_t rank, int64_t world, uint8_t *handle_out /*64 bytes*/) {
+  VM *vm = V(h);
+  if (world < 1 || world > 8 || rank < 0 || rank >= world) die("p2p_setup: at most 8 ranks");
+  if (vm->keys_sharded() && (vm->shard_rank != rank || vm->shard_world != world)) die("p2p_setup: rank / world differ from HEVM_SHARD_RANK / HEVM_SHARD_WORLD");
+  if (!vm->keys_sharded()) { // whole keys, sharded work only: same static ownership
+    vm->shard_rank = (int)rank, vm->shard_world = (int)world;
+    vm->own_lo = (int)((long)vm->L * rank / world), vm->own_hi = (int)((long)vm->L * (rank + 1) / world);
+    vm->shard_world = 1; // keys stay whole (keys_sharded() false); ownership is kept in own_lo / own_hi
+  }
+  auto &p = vm->p2p;
+  if (!p.block) {
+    p.block = dalloc<u64>(vm->p2p_words());
+    CUDA_CHECK(cudaMemset(p.block, 0, vm->p2p_words() * 8));
+    for (auto &e : p.ev) CUDA_CHECK(cudaEventCreate(&e));
+  }
+  p.rank = (int)rank, p.world = (int)world, p.on = true;
+  p.peer.p[rank] = p.block;
+  if (handle_out) {
+    cudaIpcMemHandle_t hd;
+    CUDA_CHECK(cudaIpcGetMemHandle(&hd, p.block));
+    static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(handle_out, &hd, 64);
+  }
+}
+// map a peer's exchange block: `handle` from its hevmx_p2p_setup (another process), or -- same process, for tests with
+// several VMs on one GPU -- the peer VM itself
+void hevmx_p2p_connect(void *h, int64_t peer, const uint8_t *handle, void *peer_vm_same_process) {
+  VM *vm = V(h);
+  if (peer < 0 || peer >= vm->p2p.world || peer == vm->p2p.rank) die("p2p_connect: bad peer");
+  if (peer_vm_same_process) {
+    vm->p2p.peer.p[peer] = V(peer_vm_same_process)->p2p.block;
+    return;
+  }
+  cudaIpcMemHandle_t hd;
+  std::memcpy(&hd, handle, 64);
+  void *ptr = nullptr;
+  CUDA_CHECK(cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+  vm->p2p.peer.p[peer] = (u64 *)ptr;
+}
+// asynchronous: opcode 1 = rotate by `rhs` (a step with its own Galois key), 8 = multiply + relinearise with register `rhs`
+void hevmx_ks_shard_p2p(void *h, int64_t opcode, int64_t dst, int64_t lhs, int64_t rhs) {
+  VM *vm = V(h);
+  CtReg &a = vm->ctr((size_t)lhs), &d = vm->ctr((size_t)dst);
+  if (a.level < 1) die("ks_shard_p2p: empty source register");
+  if (opcode == 1) {
+    const u64 elt = vm->galois_elt_from_step((int)(int16_t)rhs);
+    auto it = vm->d_gal.find(elt);
+    if (it == vm->d_gal.end()) die("ks_shard_p2p: no Galois key for this step");
+    const double sc = a.scale;
+    const int l = a.level;
+    vm->ks_shard_p2p(LD_GALOIS, d, a, nullptr, it->second, (u32)elt);
+    d.level = l, d.scale = sc;
+  } else if (opcode == 8) {
+    CtReg &b = vm->ctr((size_t)rhs);
+    if (a.level != b.level) die("ks_shard_p2p: level mismatch");
+    const double sc = a.scale * b.scale;
+    const int l = a.level;
+    vm->ks_shard_p2p(LD_PRODUCT, d, a, &b, vm->d_relin, 0);
+    d.level = l, d.scale = sc;
+  } else {
+    die("ks_shard_p2p: opcode must be 1 (rotate) or 8 (mulcc)");
+  }
+}
+// the owned key-switch targets [tlo, thi) of this rank at `level` (target `level` = the special limb)
+void hevmx_p2p_targets(void *h, int64_t level, int64_t *tlo, int64_t *thi) {
+  int a, b;
+  V(h)->my_targets((int)level, a, b);
+  *tlo = a, *thi = b;
+}
+// CUDA-event breakdown of the NEXT sharded key switch: on = 1 arms it; after hevmx_sync, on = 0 reads five durations (ms):
+// stage 1 | digit push + wait | stage 2 | rounded-row push / wait | stage 3
+void hevmx_p2p_timing(void *h, int on, double *out5) {
+  VM *vm = V(h);
+  if (on) {
+    vm->p2p.timed = true;
+    return;
+  }
+  vm->p2p.timed = false;
+  CUDA_CHECK(cudaEventSynchronize(vm->p2p.ev[5]));
+  for (int i = 0; i < 5; i++) {
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, vm->p2p.ev[i], vm->p2p.ev[i + 1]));
+    out5[i] = ms;
+  }
+}
+// key material from the host (canonical residues, SEAL layouts): which = 0 sk[L][N], 1 pk[2][L][N], 2 relin[L-1][2][L][N],
+// 3 Galois key of `elt` (created if absent).  Used by the .seal loader (dacapo_b200/seal_format.py).
+void hevmx_key_write(void *h, int which, uint64_t elt, const uint64_t *in) {
+  VM *vm = V(h);
+  if (vm->keys_sharded()) die("key_write: not available with limb-sharded key storage");
+  vm->invalidate_graph();
+  const size_t LN = (size_t)vm->L * vm->N, kw = (size_t)(vm->L - 1) * 2 * LN;
+  cudaStream_t st = vm->ln->stream;
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  if (which == 0) CUDA_CHECK(cudaMemcpy(vm->d_sk, in, LN * 8, cudaMemcpyHostToDevice));
+  if (which == 1) CUDA_CHECK(cudaMemcpy(vm->d_pk, in, 2 * LN * 8, cudaMemcpyHostToDevice));
+  if (which == 2 || which == 3) {
+    u64 *&dst = (which == 2) ? vm->d_relin : vm->d_gal[elt];
+    if (!dst) dst = dalloc<u64>(kw);
+    CUDA_CHECK(cudaMemcpy(dst, in, kw * 8, cudaMemcpyHostToDevice));
+    launch_key_split(st, dst, kw);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+}
+// drop every Galois key (before loading a foreign key set whose rotation steps differ from the default set)
+void hevmx_galois_clear(void *h) {
+  VM *vm = V(h);
+  vm->invalidate_graph();
+  for (auto &kv : vm->d_gal)
+    if (kv.second) CUDA_CHECK(cudaFree(kv.second));
+  vm->d_gal.clear();
 }
 void *hevmx_dev_ptr(void *h, int64_t which) {
   VM *vm = V(h);

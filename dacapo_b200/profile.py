@@ -18,6 +18,16 @@ from . import hevm_asm as asm
 
 _u64 = np.uint64
 
+# Noise rows of the reference's own SEAL profile (reference: profiled_SEAL_CPU.json:47-94, consumed by
+# EarthDialect.cpp:168-176).  This backend reproduces SEAL's evaluator bit for bit at N = 2^15 / 14 x 60-bit primes,
+# so the noise a ciphertext picks up per op and level is the same by construction; the rows are data, carried over so
+# that the DaCapo / ELASM error estimators see the same table for the `B200 GPU` target as for `SEAL CPU`.
+SEAL_NOISE_TABLE_N15 = {
+    "earth.rotate_single": [1243767652.125024, 3053517076.303607, 4202768329.642825, 5839542263.660615, 6982415435.517867, 9066416705.357107, 10703926878.339247, 13029700700.035797, 14563337546.892847, 15257531833.98208, 17555923920.67855, 18115173373.49996, 19223819509.410683],
+    "earth.rescale_single": [29041012.461168, 28989829.196367, 30513059.012577, 29249886.451856, 29939898.437991, 30011344.885873, 29425438.800167, 29278080.626328, 29791926.468794, 29763853.483675, 29026441.533765, 29574204.309626, 29574204.309626],
+    "earth.mul_double": [912420980.422666, 1626939697.436701, 2841237898.166427, 5216678287.872595, 4656426194.539523, 6498252289.502644, 4454104710.442873, 4809761973.565252, 4954123191.02746, 7101044074.407553, 8247373646.850708, 6977441673.353531, 8918871036.187374]
+}
+
 
 def _rand_ct(vm_primes, level, N, seed):
     rng = np.random.default_rng(seed)
@@ -133,7 +143,7 @@ def profile_json(table, logN=15, L=14):
         "levelLowerBound": 2, "levelUpperBound": top, "bootstrapLevelLowerBound": 2, "bootstrapLevelUpperBound": top,
         "latencyTable": {k: [max(1, int(math.ceil(v))) for v in vs] for k, vs in exact.items()},
         "latencyTableExact": {k: [round(v, 3) for v in vs] for k, vs in exact.items()},
-        "noiseTable": {},
+        "noiseTable": SEAL_NOISE_TABLE_N15 if (logN, L) == (15, 14) else {},
     }
 
 

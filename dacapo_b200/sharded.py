@@ -16,9 +16,17 @@ Two exchanges are needed per key switch and they are the only collectives on the
     exchange  broadcast of the two rounded special-limb rows: 2 * N * 8 bytes   (NCCL)
     stage 3   mod-down of the own data limbs                                    (stage 3)
 
-The collectives are issued on the VM's own CUDA stream (wrapped as a torch ExternalStream), so there is no host
-synchronisation between stages and exchanges.  Results are bit-identical to the single-GPU rotate.
-In this first version every rank still holds the whole key and ciphertext in memory; only the limbs it owns are read.
+Two implementations of the exchanges:
+
+  * `ShardedRotate` (round 1): NCCL broadcasts issued on the VM's own CUDA stream (torch ExternalStream); every rank
+    holds whole keys.  Kept as the comparison arm.
+  * `ShardedP2P` (round 2): the library does the exchanges itself over peer memory -- every rank maps the other ranks'
+    exchange blocks with CUDA IPC, a push kernel stores its digit rows straight into every peer's HBM over NVLink and
+    publishes an epoch flag, a one-warp kernel waits for the peers' flags (`hevmx_ks_shard_p2p`: ONE host call per
+    key switch, no NCCL on the data path) -- and the key STORAGE is sharded too: with HEVM_SHARD_RANK / HEVM_SHARD_WORLD
+    the VM keeps only its limbs of every key-switch key (28 GB -> 3.5 GB per GPU at N = 2^16, 30 primes, 8 GPUs).
+
+Results are bit-identical to the single-GPU rotate (and to the CPU oracle: tests/test_gpu_parity_l30.py).
 """
 from typing import List, Tuple
 
@@ -106,6 +114,49 @@ class ShardedRotate:
                     self.dist.broadcast(ct[k, a:b], src=owner, group=self.group)
 
 
+def static_targets(level: int, nprimes: int, rank: int, world: int) -> Tuple[int, int]:
+    """Round-2 ownership: rank g owns the limbs [L*g/G, L*(g+1)/G) of the key level (L = nprimes; the special limb L-1
+    belongs to the last rank) at EVERY level, so that key storage can be sharded once; at `level` the owned key-switch
+    targets are that range cut to [0, level) plus, for the last rank, the special target `level`."""
+    lo, hi = nprimes * rank // world, nprimes * (rank + 1) // world
+    return min(lo, level), (level + 1 if hi == nprimes else min(hi, level))
+
+
+class ShardedP2P:
+    """One instance per rank.  `vm` must have been created with HEVM_SHARD_RANK / HEVM_SHARD_WORLD in the environment for
+    sharded key storage (or without, for whole keys and sharded work only)."""
+
+    def __init__(self, lib, vm, rank: int, world: int, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        self.lib, self.vm, self.rank, self.world = lib, vm, rank, world
+        handle = C.create_string_buffer(64)
+        lib.hevmx_p2p_setup(vm, rank, world, handle)
+        handles = [None] * world
+        if world > 1:
+            dist.all_gather_object(handles, handle.raw, group=group)
+            for g in range(world):
+                if g != rank:
+                    lib.hevmx_p2p_connect(vm, g, handles[g], None)
+            dist.barrier(group=group)
+
+    def rotate(self, dst: int, src: int, step: int):
+        self.lib.hevmx_ks_shard_p2p(self.vm, 1, dst, src, step & 0xFFFF)
+
+    def mulcc(self, dst: int, lhs: int, rhs: int):
+        self.lib.hevmx_ks_shard_p2p(self.vm, 8, dst, lhs, rhs)
+
+    def timing(self, fn):
+        """Per-stage CUDA-event breakdown (microseconds) of one sharded op issued by `fn`."""
+        import ctypes as C
+        out = (C.c_double * 5)()
+        self.lib.hevmx_p2p_timing(self.vm, 1, out)
+        fn()
+        self.lib.hevmx_sync(self.vm)
+        self.lib.hevmx_p2p_timing(self.vm, 0, out)
+        return {k: round(v * 1e3, 1) for k, v in zip(("stage1", "digit_exchange", "stage2", "row_exchange", "stage3"), out)}
+
+
 def measure(lib, rank: int, world: int, logn: int = 16, nprimes: int = 30, levels=None, reps: int = 20, seed: int = 0xDACA90):
     """Bit-exactness and device-time of the sharded rotate against the single-GPU rotate on this node's GPUs.
     Every rank derives the same keys from `seed`.  Returns a dict (identical on all ranks).  Needs torch.distributed
@@ -135,6 +186,16 @@ def measure(lib, rank: int, world: int, logn: int = 16, nprimes: int = 30, level
     sr = ShardedRotate(lib, vm, rank, world)
     step = 4
     out = {"ring": f"N=2^{logn}, {nprimes} x 60-bit primes", "world": world, "rotate_step": step, "levels": {}}
+    # round-2 arm: a second VM whose key STORAGE is sharded (HEVM_SHARD_*), exchanges over peer memory
+    os.environ.update(HEVM_SHARD_RANK=str(rank), HEVM_SHARD_WORLD=str(world))
+    try:
+        vm2 = lib.initFullVM(keydir.encode(), True)
+    finally:
+        os.environ.pop("HEVM_SHARD_RANK", None), os.environ.pop("HEVM_SHARD_WORLD", None)
+    lib.hevmx_resize(vm2, 4, 1)
+    p2p = ShardedP2P(lib, vm2, rank, world)
+    kb = lambda v, which: lib.hevmx_key_read(v, which, 0, None) * 8
+    out["key_bytes_per_rank"] = {"whole_relin_key": kb(vm, 2), "sharded_relin_key": kb(vm2, 2), "keys_per_vm": 1 + lib.hevmx_param(vm, 5)}
 
     def timed(fn):
         for _ in range(3):
@@ -180,9 +241,54 @@ def measure(lib, rank: int, world: int, logn: int = 16, nprimes: int = 30, level
         dist.all_reduce(ok2, op=dist.ReduceOp.MIN)
         m_sh = timed(lambda: sr.mulcc(3, 0, 0, lvl))
         m_1 = timed(lambda: lib.hevmx_exec(vm, asm.MULCC, 1, 0, 0))
-        out["levels"][str(lvl)] = {"bit_exact_vs_single_gpu": bool(ok.item()) and bool(ok2.item()),
-                                   "rotate": {"sharded_us": round(t_sh, 1), "single_gpu_us": round(t_1, 1), "speedup": round(t_1 / t_sh, 3)},
-                                   "mulcc": {"sharded_us": round(m_sh, 1), "single_gpu_us": round(m_1, 1), "speedup": round(m_1 / m_sh, 3)},
+        # ---- peer-memory arm (sharded key storage): own limbs of the result vs the single-GPU result
+        tlo, thi = static_targets(lvl, nprimes, rank, world)
+        dhi = min(thi, lvl)
+
+        def timed2(fn):
+            for _ in range(3):
+                fn()
+            lib.hevmx_sync(vm2)
+            dist.barrier()
+            torch.cuda.synchronize()
+            lib.hevmx_timer(vm2, 0)
+            for _ in range(reps):
+                fn()
+            t = torch.tensor([lib.hevmx_timer(vm2, 1) / reps], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item()) * 1e3
+
+        def own_limbs_equal(reg, ref):
+            g2 = np.zeros_like(a)
+            lib.hevmx_sync(vm2)
+            lib.hevmx_ct_read(vm2, reg, g2.ctypes.data_as(u64p))
+            okk = torch.tensor([1 if np.array_equal(g2[:, tlo:dhi], ref[:, tlo:dhi]) else 0], device="cuda")
+            dist.all_reduce(okk, op=dist.ReduceOp.MIN)
+            return bool(okk.item())
+
+        lib.hevmx_ct_write(vm2, 0, a.ctypes.data_as(u64p), lvl, 2.0 ** 40)
+        lib.hevmx_ct_write(vm2, 2, np.zeros_like(a).ctypes.data_as(u64p), lvl, 2.0 ** 40)
+        lib.hevmx_ct_write(vm2, 3, np.zeros_like(a).ctypes.data_as(u64p), lvl, 2.0 ** 40)
+        lib.hevmx_exec(vm, asm.ROTATE, 1, 0, step)
+        lib.hevmx_ct_read(vm, 1, exp.ctypes.data_as(u64p))
+        p2p.rotate(2, 0, step)
+        ok3 = own_limbs_equal(2, exp)
+        lib.hevmx_exec(vm, asm.MULCC, 1, 0, 0)
+        lib.hevmx_ct_read(vm, 1, exp.ctypes.data_as(u64p))
+        p2p.mulcc(3, 0, 0)
+        ok4 = own_limbs_equal(3, exp)
+        t_p2p = timed2(lambda: p2p.rotate(2, 0, step))
+        m_p2p = timed2(lambda: p2p.mulcc(3, 0, 0))
+        dist.barrier()
+        stages = p2p.timing(lambda: p2p.rotate(2, 0, step))
+        out["levels"][str(lvl)] = {"bit_exact_vs_single_gpu": bool(ok.item()) and bool(ok2.item()) and ok3 and ok4,
+                                   "rotate": {"sharded_us": round(t_p2p, 1), "single_gpu_us": round(t_1, 1), "speedup": round(t_1 / t_p2p, 3),
+                                              "nccl_broadcast_arm_us": round(t_sh, 1), "nccl_broadcast_arm_speedup": round(t_1 / t_sh, 3),
+                                              "stages_us_rank0": stages},
+                                   "mulcc": {"sharded_us": round(m_p2p, 1), "single_gpu_us": round(m_1, 1), "speedup": round(m_1 / m_p2p, 3),
+                                             "nccl_broadcast_arm_us": round(m_sh, 1), "nccl_broadcast_arm_speedup": round(m_1 / m_sh, 3)},
+                                   "targets_per_rank_p2p": [static_targets(lvl, nprimes, g, world)[1] - static_targets(lvl, nprimes, g, world)[0] for g in range(world)],
+                                   "exchange": "peer-memory push over NVLink + epoch flags (CUDA IPC), sharded key storage",
                                    "targets_per_rank": [b - a_ for a_, b in partition_targets(lvl, world)],
                                    "allgather_bytes": lvl * N * 8, "broadcast_bytes": 2 * N * 8}
     return out

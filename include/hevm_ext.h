@@ -62,6 +62,22 @@ void hevmx_mulcc_shard_stage(void *vm, int stage, int64_t dst, int64_t lhs, int6
  * 16 + r = limb data of ciphertext register r ([2][L-1][N] u64) */
 void *hevmx_dev_ptr(void *vm, int64_t which);
 void *hevmx_stream(void *vm);                   /* the cudaStream_t the VM issues hevmx_* work on */
+/* --- the same key switch with the exchanges done by the library itself over peer memory (NVLink; CUDA IPC) ---
+ * hevmx_p2p_setup allocates this rank's exchange block (digits + rounded rows, double-buffered, + epoch flags) and
+ * returns its 64-byte cudaIpcMemHandle_t; hevmx_p2p_connect maps a peer's block (handle from another process, or the
+ * peer VM itself when several VMs share a process in tests).  hevmx_ks_shard_p2p = the whole sharded op of this rank,
+ * asynchronous: stage 1, push of the own digit rows into every peer + flag, wait, stage 2, push / wait of the rounded
+ * special-limb rows, stage 3.  Ownership of targets is static: rank g owns the limbs [L*g/G, L*(g+1)/G) of the key level
+ * (hevmx_p2p_targets gives the range at a level).  With HEVM_SHARD_RANK / HEVM_SHARD_WORLD set at initFullVM the VM
+ * also STORES only those limbs of every key-switch key (key memory / G) and accepts only the sharded ops. */
+void hevmx_p2p_setup(void *vm, int64_t rank, int64_t world, uint8_t *handle_out /*64 bytes or NULL*/);
+void hevmx_p2p_connect(void *vm, int64_t peer, const uint8_t *handle /*64 bytes*/, void *peer_vm_same_process /*or NULL*/);
+void hevmx_ks_shard_p2p(void *vm, int64_t opcode /*1 rotate, 8 mulcc*/, int64_t dst, int64_t lhs, int64_t rhs /*step | register*/);
+void hevmx_p2p_targets(void *vm, int64_t level, int64_t *tlo, int64_t *thi);
+void hevmx_p2p_timing(void *vm, int on, double *out5 /*ms: stage1, digit exchange, stage2, row exchange, stage3*/);
+/* --- key import (the .seal loader, dacapo_b200/seal_format.py): canonical residues in SEAL's layouts --- */
+void hevmx_key_write(void *vm, int which /*0 sk, 1 pk, 2 relin, 3 galois*/, uint64_t elt, const uint64_t *in);
+void hevmx_galois_clear(void *vm);
 
 #ifdef __cplusplus
 }

@@ -4,6 +4,10 @@ from pathlib import Path
 
 import pytest
 
+# several VMs share one GPU in the in-process multi-rank test (one spins on a flag another one's kernels set): give every
+# stream its own hardware queue so that no kernel is ever queued behind a waiting one (must be set before CUDA starts)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 REPO = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(REPO))
 sys.path.insert(0, str(REPO / "tests"))

@@ -190,6 +190,63 @@ def test_batched_launch_bit_exact(oracle_lib, b200_lib, tmp_path_factory, lvl, n
         assert g.ct_info(dst2[k]) == o.ct_info(dst2[k])
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_p2p_sharded_keyswitch_sharded_key_storage(oracle_lib, b200_lib, tmp_path_factory, world):
+    """hevmx_ks_shard_p2p with `world` ranks emulated by `world` VMs on ONE GPU in one process: every VM stores only its
+    limbs of every key (HEVM_SHARD_*), pushes its digit rows into the other VMs' exchange blocks and waits on their epoch
+    flags; three key switches back to back exercise the double-buffered exchange.  Own limbs of every rank, assembled,
+    must equal the oracle's rotate / multiply + relinearise."""
+    from dacapo_b200.sharded import static_targets
+    npr, steps = 7, (1, -2)
+    d = str(tmp_path_factory.mktemp(f"keysp2p{world}"))
+    o = VM(oracle_lib, LOGN, npr, keydir=d, nct=6, npt=1, galois_steps=steps)
+    vms = [VM(b200_lib, LOGN, npr, keydir=d, nct=6, npt=1, galois_steps=steps,
+              env={"HEVM_SHARD_RANK": g, "HEVM_SHARD_WORLD": world, "HEVM_STREAMS": 1}) for g in range(world)]
+    lib = b200_lib
+    whole = o.key(2).size
+    assert sum(v.key(2).size for v in vms) == whole and max(v.key(2).size for v in vms) <= whole // world + whole // (npr * 1)
+    for g, v in enumerate(vms):
+        lib.hevmx_p2p_setup(v.vm, g, world, None)
+    for g, v in enumerate(vms):
+        for h, w in enumerate(vms):
+            if h != g:
+                lib.hevmx_p2p_connect(v.vm, h, None, w.vm)
+    for lvl in (6, 3, 1):
+        a, b = o.random_ct(lvl, 700 + lvl), o.random_ct(lvl, 800 + lvl)
+        for vm in [o] + vms:
+            vm.ct_write(0, a, 2.0 ** 40)
+            vm.ct_write(1, b, 2.0 ** 40)
+            vm.ct_write(2, np.zeros_like(a), 2.0 ** 40)
+            vm.ct_write(3, np.zeros_like(a), 2.0 ** 40)
+        o.exec(asm.ROTATE, 2, 0, 1)
+        o.exec(asm.ROTATE, 2, 2, -2)
+        o.exec(asm.MULCC, 3, 0, 1)
+        # rank by rank, asynchronously: rotate(1) -> all ranks, then rotate(-2) of the result, then mulcc
+        for v in vms:
+            lib.hevmx_ks_shard_p2p(v.vm, 1, 2, 0, 1)
+        # the second rotation reads register 2, of which every rank only holds ITS limbs: gather them first
+        for v in vms:
+            lib.hevmx_sync(v.vm)
+        parts = [v.ct_read(2) for v in vms]
+        full = np.zeros_like(a)
+        for g in range(world):
+            tlo, thi = static_targets(lvl, npr, g, world)
+            full[:, tlo:min(thi, lvl)] = parts[g][:, tlo:min(thi, lvl)]
+        for v in vms:
+            v.ct_write(2, full, 2.0 ** 40)
+            lib.hevmx_ks_shard_p2p(v.vm, 1, 2, 2, -2 & 0xFFFF)
+        for v in vms:
+            lib.hevmx_ks_shard_p2p(v.vm, 8, 3, 0, 1)
+        for v in vms:
+            lib.hevmx_sync(v.vm)
+        for reg in (2, 3):
+            got = np.zeros_like(a)
+            for g, v in enumerate(vms):
+                tlo, thi = static_targets(lvl, npr, g, world)
+                got[:, tlo:min(thi, lvl)] = v.ct_read(reg)[:, tlo:min(thi, lvl)]
+            assert np.array_equal(got, o.ct_read(reg)), (lvl, reg)
+
+
 def test_encode_decode_bit_exact(pair):
     g, o = pair
     rng = np.random.default_rng(7)

@@ -9,7 +9,7 @@ _u64p = C.POINTER(C.c_uint64)
 _f64p = C.POINTER(C.c_double)
 
 
-def make_vm(lib, logn, nprimes, seed=0xDACA90, bits=60, keydir=None, galois_steps=None):
+def make_vm(lib, logn, nprimes, seed=0xDACA90, bits=60, keydir=None, galois_steps=None, env=None):
     """create_context + initFullVM on `lib` with the given ring geometry.  `galois_steps`: generate Galois keys for
     these rotation steps only (HEVM_GALOIS_STEPS, SEAL's create_galois_keys(steps)); default = SEAL's default set."""
     d = keydir or tempfile.mkdtemp(prefix="hevm_keys_")
@@ -24,26 +24,28 @@ def make_vm(lib, logn, nprimes, seed=0xDACA90, bits=60, keydir=None, galois_step
                     os.environ.pop(k, None)
                 else:
                     os.environ[k] = v
-    old = os.environ.get("HEVM_GALOIS_STEPS")
+    extra = dict(env or {})  # e.g. HEVM_SHARD_RANK / HEVM_SHARD_WORLD / HEVM_STREAMS, only while the VM is created
     if galois_steps is not None:
-        os.environ["HEVM_GALOIS_STEPS"] = ",".join(str(int(x)) for x in galois_steps)
+        extra["HEVM_GALOIS_STEPS"] = ",".join(str(int(x)) for x in galois_steps)
+    old = {k: os.environ.get(k) for k in extra}
+    os.environ.update({k: str(v) for k, v in extra.items()})
     try:
         vm = lib.initFullVM(d.encode(), True)
     finally:
-        if galois_steps is not None:
-            if old is None:
-                os.environ.pop("HEVM_GALOIS_STEPS", None)
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
             else:
-                os.environ["HEVM_GALOIS_STEPS"] = old
+                os.environ[k] = v
     return vm, d
 
 
 class VM:
     """Thin convenience wrapper over the hevmx_* hooks of one library."""
 
-    def __init__(self, lib, logn, nprimes, seed=0xDACA90, keydir=None, nct=8, npt=4, galois_steps=None):
+    def __init__(self, lib, logn, nprimes, seed=0xDACA90, keydir=None, nct=8, npt=4, galois_steps=None, env=None):
         self.lib = lib
-        self.vm, self.keydir = make_vm(lib, logn, nprimes, seed, keydir=keydir, galois_steps=galois_steps)
+        self.vm, self.keydir = make_vm(lib, logn, nprimes, seed, keydir=keydir, galois_steps=galois_steps, env=env)
         self.logn, self.N, self.L = logn, 1 << logn, nprimes
         p = np.zeros(nprimes, dtype=np.uint64)
         lib.hevmx_primes(self.vm, p.ctypes.data_as(_u64p))
