@@ -28,6 +28,8 @@ def build(force=False, verbose=False, out=OUT, defs=()):
             cmd.insert(1, "-Xptxas=-v")
         subprocess.run(cmd, check=True)
         objs.append(str(obj))
+    # (the driver API -- cuTensorMapEncodeTiled for the TMA tensor map of the cluster NTT -- is reached through
+    #  cudaGetDriverEntryPoint, so libcuda is not a link-time dependency and the library still loads on a CPU-only box)
     subprocess.run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(out), *objs], check=True)
     return out
 

@@ -8,6 +8,7 @@
 //  * fp64 CKKS encoder / decoder kernels (radix-2 special FFT, four stages per launch, explicit *_rn
 //    intrinsics so that no FMA contraction changes bits w.r.t. the host restatement)
 #include "kernels.h"
+#include "ntt_cluster.cuh"
 #include <algorithm>
 
 unsigned long long g_launch_count = 0;
@@ -312,6 +313,42 @@ template <int LOGA, int PRE> void GpuLauncher::invA_fwdA(const ArgsInvFwdA &a, i
   PRE_LAUNCH(stream, PRE == PRE_MODUP ? KC_INVA_FWDA_MODUP : KC_INVA_FWDA_ROUND);
   launch_pdl(k_invA_fwdA<LOGA, PRE>, ctas_for(njobs), CTA_THREADS, warp_smem<LOGA>(k_invA_fwdA<LOGA, PRE>), stream, a, njobs);
   POST_LAUNCH_S(stream);
+}
+
+// ---- single-pass cluster NTT (ntt_cluster.cuh): TMA tensor map over the source limbs, 8 CTAs per limb ----
+void launch_ntt_fwd_cluster(cudaStream_t s, const NttTables *T, int logN, const u64 *src, u64 *dst, int nl, int prime0, int pstep) {
+  if (logN != 15) {
+    std::fprintf(stderr, "[b200-hevm] fatal: the cluster NTT is built for N = 2^15\n");
+    std::abort();
+  }
+  typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                               const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+    if (!fn || qr != cudaDriverEntryPointSuccess) {
+      std::fprintf(stderr, "[b200-hevm] fatal: cuTensorMapEncodeTiled not available\n");
+      std::abort();
+    }
+    encode = (EncodeFn)fn;
+    CUDA_CHECK(cudaFuncSetAttribute((const void *)k_ntt_fwd_cluster<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NC_SMEM_WORDS * sizeof(u64))));
+  }
+  const size_t N = (size_t)1 << logN;
+  CUtensorMap map;
+  const cuuint64_t dims[3] = {256, N / 256, (cuuint64_t)nl};
+  const cuuint64_t strides[2] = {256 * sizeof(u64), N * sizeof(u64)};
+  const cuuint32_t box[3] = {4, (cuuint32_t)(N / 256), 1}, estr[3] = {1, 1, 1};
+  const CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, (void *)src, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    std::fprintf(stderr, "[b200-hevm] fatal: cuTensorMapEncodeTiled failed (%d)\n", (int)r);
+    std::abort();
+  }
+  PRE_LAUNCH(s, KC_OTHER);
+  k_ntt_fwd_cluster<7><<<nl * NC_CLUSTER, NC_WARPS * 32, NC_SMEM_WORDS * sizeof(u64), s>>>(map, T, dst, prime0, pstep);
+  POST_LAUNCH_S(s);
 }
 
 static int fused_grid_cap() {

@@ -56,6 +56,9 @@ struct GpuLauncher {
   template <int LOGA, int MODE> void ks_fused(const KsFusedArgs &a);
 };
 
+// ---- single-pass forward NTT of `nl` limbs (N = 2^15) in 8-CTA clusters: TMA tile loads + DSMEM transpose (ntt_cluster.cuh) ----
+void launch_ntt_fwd_cluster(cudaStream_t s, const NttTables *T, int logN, const u64 *src, u64 *dst, int nl, int prime0, int pstep);
+
 // ---- peer-to-peer exchange of the limb-sharded key switch (NVLink, CUDA IPC mapped peer memory) ----
 // Every rank owns one exchange block with the same layout; peer.p[g] = that block of rank g mapped into this process.
 struct PeerPtrs {

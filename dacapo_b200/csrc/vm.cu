@@ -110,6 +110,14 @@ struct VM {
   // of every key-switch key (static, contiguous, balanced; the special limb L-1 belongs to the last rank) and the VM
   // only accepts the limb-sharded ops (hevmx_ks_shard_p2p).  At level l its key-switch targets are that range cut to l.
   int shard_rank = 0, shard_world = 1, own_lo = 0, own_hi = 0;
+  // balanced contiguous ranges with the remainder on the FIRST ranks: the last rank, which also carries the special
+  // limb's extra work (inverse NTT + rounding of two rows, and every other rank waits for them), never has more limbs
+  // than anybody else
+  static void own_range(int L, int g, int G, int &lo, int &hi) {
+    const int base = L / G, rem = L % G;
+    lo = g * base + std::min(g, rem);
+    hi = lo + base + (g < rem ? 1 : 0);
+  }
   bool keys_sharded() const { return shard_world > 1; }
   int key_limbs() const { return keys_sharded() ? own_hi - own_lo : L; }
   void my_targets(int l, int &tlo, int &thi) const {
@@ -189,7 +197,7 @@ struct VM {
       shard_rank = std::getenv("HEVM_SHARD_RANK") ? std::atoi(std::getenv("HEVM_SHARD_RANK")) : 0;
       if (shard_world > 8 || shard_rank < 0 || shard_rank >= shard_world) die("HEVM_SHARD_RANK / HEVM_SHARD_WORLD out of range (at most 8 ranks)");
     }
-    own_lo = (int)((long)L * shard_rank / shard_world), own_hi = (int)((long)L * (shard_rank + 1) / shard_world);
+    own_range(L, shard_rank, shard_world, own_lo, own_hi);
     P.build(logN, L, (int)pf.bits);
     Tw *d_tw = upload(P.tw), *d_itw = upload(P.itw);
     P.tab.tw = d_tw, P.tab.itw = d_itw;
@@ -620,7 +628,10 @@ struct VM {
   // The exchange buffers are double-buffered by the parity of the key-switch sequence number: a rank that runs ahead
   // writes buffer (n+1) & 1 while a slower peer may still read buffer n & 1; it cannot get two key switches ahead
   // because each one needs every peer's digits.
-  void ks_shard_p2p(int mode, CtReg &d, const CtReg &a, const CtReg *b, const u64 *key, u32 elt) {
+  // `phase` 0 = the whole op; 1 / 2 / 3 = only up to the first push / from the first wait to the second push or wait /
+  // from there to the end -- a test that emulates several ranks with several VMs on ONE GPU issues the phases in
+  // lockstep, so that no wait kernel is ever queued in front of the kernels it waits for.
+  void ks_shard_p2p(int mode, CtReg &d, const CtReg &a, const CtReg *b, const u64 *key, u32 elt, int phase = 0) {
     if (!p2p.on) die("hevmx_p2p_setup has not been called");
     Lane &L0 = lanes[0];
     ln = &L0;
@@ -630,7 +641,8 @@ struct VM {
     const int dhi = std::min(thi, l), nd = std::max(0, dhi - tlo);
     const bool own_sp = thi == l + 1;
     int sp_owner = p2p.world - 1;
-    const unsigned long long e = ++p2p.epoch;
+    if (phase <= 1) ++p2p.epoch;
+    const unsigned long long e = p2p.epoch;
     const int par = (int)(e & 1);
     Scratch &sc = L0.ops->sc;
     u64 *save_t = sc.t, *save_rnd = sc.rnd;
@@ -640,22 +652,26 @@ struct VM {
       if (p2p.timed) CUDA_CHECK(cudaEventRecord(p2p.ev[i], L0.stream));
     };
     const u64 *bd = b ? b->d : nullptr;
-    mark(0);
-    L0.ops->ks_shard_stage(1, mode, a.d, bd, d.d, pitch, l, key, elt, tlo, thi);
-    mark(1);
-    launch_p2p_push(L0.stream, sc.t + (size_t)tlo * N, (size_t)nd * N, p2p.peer, p2p_t_off(par) + (size_t)tlo * N, p2p.rank, p2p.world, done,
-                    p2p_flag_off(0), e);
-    launch_p2p_wait(L0.stream, p2p.block, p2p_flag_off(0), p2p.rank, p2p.world, -1, e);
-    mark(2);
-    L0.ops->ks_shard_stage(2, mode, a.d, bd, d.d, pitch, l, key, elt, tlo, thi);
-    mark(3);
-    if (own_sp)
-      launch_p2p_push(L0.stream, sc.rnd, (size_t)2 * N, p2p.peer, p2p_rnd_off(par), p2p.rank, p2p.world, done, p2p_flag_off(1), e);
-    else
-      launch_p2p_wait(L0.stream, p2p.block, p2p_flag_off(1), p2p.rank, p2p.world, sp_owner, e);
-    mark(4);
-    L0.ops->ks_shard_stage(3, mode, a.d, bd, d.d, pitch, l, key, elt, tlo, thi);
-    mark(5);
+    if (phase <= 1) {
+      mark(0);
+      L0.ops->ks_shard_stage(1, mode, a.d, bd, d.d, pitch, l, key, elt, tlo, thi);
+      mark(1);
+      launch_p2p_push(L0.stream, sc.t + (size_t)tlo * N, (size_t)nd * N, p2p.peer, p2p_t_off(par) + (size_t)tlo * N, p2p.rank, p2p.world, done,
+                      p2p_flag_off(0), e);
+    }
+    if (phase == 0 || phase == 2) {
+      launch_p2p_wait(L0.stream, p2p.block, p2p_flag_off(0), p2p.rank, p2p.world, -1, e);
+      mark(2);
+      L0.ops->ks_shard_stage(2, mode, a.d, bd, d.d, pitch, l, key, elt, tlo, thi);
+      mark(3);
+      if (own_sp) launch_p2p_push(L0.stream, sc.rnd, (size_t)2 * N, p2p.peer, p2p_rnd_off(par), p2p.rank, p2p.world, done, p2p_flag_off(1), e);
+    }
+    if (phase == 0 || phase == 3) {
+      if (!own_sp) launch_p2p_wait(L0.stream, p2p.block, p2p_flag_off(1), p2p.rank, p2p.world, sp_owner, e);
+      mark(4);
+      L0.ops->ks_shard_stage(3, mode, a.d, bd, d.d, pitch, l, key, elt, tlo, thi);
+      mark(5);
+    }
     sc.t = save_t, sc.rnd = save_rnd;
   }
 
@@ -1317,7 +1333,9 @@ void hevmx_ntt(void *h, uint64_t *data, int64_t prime_idx, int64_t count, int in
   const size_t w = (size_t)count * vm->N;
   u64 *d = dalloc<u64>(w);
   CUDA_CHECK(cudaMemcpyAsync(d, data, w * 8, cudaMemcpyHostToDevice, vm->ln->stream));
-  if (inverse)
+  if (inverse == 2) // the single-pass cluster NTT (forward), for parity tests of the experiment
+    launch_ntt_fwd_cluster(vm->ln->stream, vm->dT, vm->logN, d, d, (int)count, (int)prime_idx, 0);
+  else if (inverse)
     vm->ln->ops->ntt_inv(d, d, (int)count, (int)prime_idx, 0);
   else
     vm->ln->ops->ntt_fwd(d, d, (int)count, (int)prime_idx, 0);
@@ -1337,7 +1355,9 @@ double hevmx_ntt_bench(void *h, int64_t batch, int64_t nprimes, int inverse, int
   auto pass = [&] {
     for (int64_t i = 0; i < nprimes; i++) {
       u64 *p = d + (size_t)i * batch * vm->N;
-      if (inverse)
+      if (inverse == 2)
+        launch_ntt_fwd_cluster(vm->ln->stream, vm->dT, vm->logN, p, p, (int)batch, (int)i, 0);
+      else if (inverse)
         vm->ln->ops->ntt_inv(p, p, (int)batch, (int)i, 0);
       else
         vm->ln->ops->ntt_fwd(p, p, (int)batch, (int)i, 0);
@@ -1453,7 +1473,7 @@ void hevmx_p2p_setup(void *h, int64_t rank, int64_t world, uint8_t *handle_out /
   if (vm->keys_sharded() && (vm->shard_rank != rank || vm->shard_world != world)) die("p2p_setup: rank / world differ from HEVM_SHARD_RANK / HEVM_SHARD_WORLD");
   if (!vm->keys_sharded()) { // whole keys, sharded work only: same static ownership
     vm->shard_rank = (int)rank, vm->shard_world = (int)world;
-    vm->own_lo = (int)((long)vm->L * rank / world), vm->own_hi = (int)((long)vm->L * (rank + 1) / world);
+    VM::own_range(vm->L, (int)rank, (int)world, vm->own_lo, vm->own_hi);
     vm->shard_world = 1; // keys stay whole (keys_sharded() false); ownership is kept in own_lo / own_hi
   }
   auto &p = vm->p2p;
@@ -1487,8 +1507,11 @@ void hevmx_p2p_connect(void *h, int64_t peer, const uint8_t *handle, void *peer_
   vm->p2p.peer.p[peer] = (u64 *)ptr;
 }
 // asynchronous: opcode 1 = rotate by `rhs` (a step with its own Galois key), 8 = multiply + relinearise with register `rhs`
-void hevmx_ks_shard_p2p(void *h, int64_t opcode, int64_t dst, int64_t lhs, int64_t rhs) {
+void hevmx_ks_shard_p2p_phase(void *h, int64_t phase, int64_t opcode, int64_t dst, int64_t lhs, int64_t rhs);
+void hevmx_ks_shard_p2p(void *h, int64_t opcode, int64_t dst, int64_t lhs, int64_t rhs) { hevmx_ks_shard_p2p_phase(h, 0, opcode, dst, lhs, rhs); }
+void hevmx_ks_shard_p2p_phase(void *h, int64_t phase, int64_t opcode, int64_t dst, int64_t lhs, int64_t rhs) {
   VM *vm = V(h);
+  if (phase < 0 || phase > 3) die("ks_shard_p2p_phase: phase must be 0..3");
   CtReg &a = vm->ctr((size_t)lhs), &d = vm->ctr((size_t)dst);
   if (a.level < 1) die("ks_shard_p2p: empty source register");
   if (opcode == 1) {
@@ -1497,15 +1520,15 @@ void hevmx_ks_shard_p2p(void *h, int64_t opcode, int64_t dst, int64_t lhs, int64
     if (it == vm->d_gal.end()) die("ks_shard_p2p: no Galois key for this step");
     const double sc = a.scale;
     const int l = a.level;
-    vm->ks_shard_p2p(LD_GALOIS, d, a, nullptr, it->second, (u32)elt);
-    d.level = l, d.scale = sc;
+    vm->ks_shard_p2p(LD_GALOIS, d, a, nullptr, it->second, (u32)elt, (int)phase);
+    if (phase == 0 || phase == 3) d.level = l, d.scale = sc;
   } else if (opcode == 8) {
     CtReg &b = vm->ctr((size_t)rhs);
     if (a.level != b.level) die("ks_shard_p2p: level mismatch");
-    const double sc = a.scale * b.scale;
+    if (phase <= 1) vm->shard_scale = a.scale * b.scale; // dst may alias an operand: fix the product scale before stage 3 overwrites it
     const int l = a.level;
-    vm->ks_shard_p2p(LD_PRODUCT, d, a, &b, vm->d_relin, 0);
-    d.level = l, d.scale = sc;
+    vm->ks_shard_p2p(LD_PRODUCT, d, a, &b, vm->d_relin, 0, (int)phase);
+    if (phase == 0 || phase == 3) d.level = l, d.scale = vm->shard_scale;
   } else {
     die("ks_shard_p2p: opcode must be 1 (rotate) or 8 (mulcc)");
   }

@@ -116,11 +116,25 @@ class Empty:
     __radd__ = __iadd__ = __sub__ = __rsub__ = __isub__ = __add__
 
 
+LIVE_LIST_BOOTSTRAPS = False
+
+
 def bootstrap(x):
-    """Manual bootstrap hint.  For iterables the reference discards the created ops and returns the
-    argument unchanged (expr.py:119-124); mirrored."""
+    """Manual bootstrap hint.  For iterables the reference creates one bootstrap op per element but returns the
+    ARGUMENT, so those ops are dead and disappear in the first canonicalisation (expr.py:115-127); mirrored: nothing is
+    recorded.  Every `hc.bootstrap(out)` of examples/benchmarks/ResNet.py is of that kind, which is why only the
+    `dacapo` pipeline (automatic placement) can compile it.  With LIVE_LIST_BOOTSTRAPS = True the hint is honoured
+    element-wise instead -- the hand placement the benchmark's author wrote down, used as the `pars` arm of the
+    DaCapo-vs-PARS comparison (BASELINE.json configs[3])."""
     if isinstance(x, Expr):
         return _emit("boot", x.idx)
+    if LIVE_LIST_BOOTSTRAPS and isinstance(x, Iterable):
+        if isinstance(x, np.ndarray):
+            out = np.empty(x.shape, dtype=object)
+            for idx in np.ndindex(x.shape):
+                out[idx] = bootstrap(x[idx])
+            return out
+        return type(x)(bootstrap(e) for e in x)
     return x
 
 

@@ -76,7 +76,9 @@ def setLibnHW(argv=None):
 class HEVM:
     """Mirror of the reference `HEVM` class (runner.py:174-271)."""
 
-    def __init__(self, path=None, option="full", lib=None):
+    def __init__(self, path=None, option="full", lib=None, seal_dir=None):
+        """`seal_dir`: a SEAL 4.0 key directory (parm/pub/sec/relin/gal.seal as written by SEAL_HEVM.cpp:56-88) whose keys
+        replace the seed-derived ones (dacapo_b200/seal_format.py)."""
         global lw
         self._lw = lib if lib is not None else reinit_lw()
         self.option = option
@@ -98,6 +100,9 @@ class HEVM:
             raise ValueError(option)
         self.slots = 1 << (self._lw.hevmx_param(self.vm, 0) - 1)
         self.hevm_path = ""
+        if seal_dir is not None:
+            from . import seal_format
+            seal_format.load_seal_keys(self._lw, self.vm, seal_dir)
 
     def load(self, const_path, hevm_path, preprocess=True):
         if not Path(const_path).is_file():

@@ -284,3 +284,61 @@ def read_key_dir(path) -> Dict:
         raise SealFormatError("relin.seal holds no key for s^2")
     return {"n": n, "primes": primes, "sk": sk.reshape(L, n), "pk": pk, "relin": relin[0],
             "galois": {2 * i + 1: k for i, k in gal.items()}}
+
+
+# ------------------------------------------------------------------------------------------------ VM <-> key directory
+def export_vm_keys(lib, vm, path, compr_mode: int = COMPR_NONE):
+    """Write the key material of a libB200_HEVM.so VM (hevmx_key_read: canonical residues) as a SEAL key directory."""
+    import ctypes as C
+    u64p = C.POINTER(C.c_uint64)
+    logn, L = lib.hevmx_param(vm, 0), lib.hevmx_param(vm, 1)
+    n = 1 << logn
+    primes = np.zeros(L, dtype=np.uint64)
+    lib.hevmx_primes(vm, primes.ctypes.data_as(u64p))
+
+    def read(which, elt=0):
+        w = lib.hevmx_key_read(vm, which, elt, None)
+        if w < 0:
+            return None
+        out = np.zeros(w, dtype=np.uint64)
+        lib.hevmx_key_read(vm, which, elt, out.ctypes.data_as(u64p))
+        return out
+
+    gal = {}
+    m = 2 * n
+    elts, pos, neg = [m - 1], 3, pow(3, -1, m)
+    for _ in range(logn - 1):  # GaloisTool::get_elts_all: 3^(+-2^i) and the conjugation
+        elts += [pos, neg]
+        pos, neg = pos * pos % m, neg * neg % m
+    for e in elts:
+        k = read(3, e)
+        if k is not None:
+            gal[e] = k.reshape(L - 1, 2, L, n)
+    write_key_dir(path, n, [int(q) for q in primes], read(0).reshape(L, n), read(1).reshape(2, L, n), read(2).reshape(L - 1, 2, L, n), gal, compr_mode)
+
+
+def load_seal_keys(lib, vm, path):
+    """Replace the VM's keys with those of a SEAL key directory (SEAL_HEVM.cpp:91-129 `loadSEAL`).  The directory's
+    parameters must be this VM's ring: same degree and the same prime chain (SEAL's CoeffModulus::Create order)."""
+    import ctypes as C
+    u64p = C.POINTER(C.c_uint64)
+    kd = read_key_dir(path)
+    logn, L = lib.hevmx_param(vm, 0), lib.hevmx_param(vm, 1)
+    primes = np.zeros(L, dtype=np.uint64)
+    lib.hevmx_primes(vm, primes.ctypes.data_as(u64p))
+    if kd["n"] != 1 << logn or [int(q) for q in primes] != [int(q) for q in kd["primes"]]:
+        raise SealFormatError("the key directory was made for other encryption parameters than this VM's")
+
+    def put(which, arr, elt=0):
+        a = np.ascontiguousarray(arr, dtype=np.uint64)
+        lib.hevmx_key_write(vm, which, elt, a.ctypes.data_as(u64p))
+
+    if kd["pk"].shape != (2, L, kd["n"]) or kd["relin"].shape != (L - 1, 2, L, kd["n"]):
+        raise SealFormatError("unexpected key shapes")
+    put(0, kd["sk"])
+    put(1, kd["pk"])
+    put(2, kd["relin"])
+    lib.hevmx_galois_clear(vm)
+    for elt, k in kd["galois"].items():
+        put(3, k, elt)
+    return kd

@@ -115,10 +115,12 @@ class ShardedRotate:
 
 
 def static_targets(level: int, nprimes: int, rank: int, world: int) -> Tuple[int, int]:
-    """Round-2 ownership: rank g owns the limbs [L*g/G, L*(g+1)/G) of the key level (L = nprimes; the special limb L-1
-    belongs to the last rank) at EVERY level, so that key storage can be sharded once; at `level` the owned key-switch
+    """Round-2 ownership: rank g owns a contiguous, balanced range of the L = nprimes limbs of the key level (the special
+    limb L-1 belongs to the last rank) at EVERY level, so that key storage can be sharded once; at `level` the owned key-switch
     targets are that range cut to [0, level) plus, for the last rank, the special target `level`."""
-    lo, hi = nprimes * rank // world, nprimes * (rank + 1) // world
+    base, rem = divmod(nprimes, world)  # the remainder goes to the FIRST ranks (VM::own_range): the special limb's owner is never the busiest
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
     return min(lo, level), (level + 1 if hi == nprimes else min(hi, level))
 
 

@@ -73,6 +73,9 @@ void *hevmx_stream(void *vm);                   /* the cudaStream_t the VM issue
 void hevmx_p2p_setup(void *vm, int64_t rank, int64_t world, uint8_t *handle_out /*64 bytes or NULL*/);
 void hevmx_p2p_connect(void *vm, int64_t peer, const uint8_t *handle /*64 bytes*/, void *peer_vm_same_process /*or NULL*/);
 void hevmx_ks_shard_p2p(void *vm, int64_t opcode /*1 rotate, 8 mulcc*/, int64_t dst, int64_t lhs, int64_t rhs /*step | register*/);
+/* the same op cut at its two exchanges (phase 1: stage 1 + digit push; 2: wait + stage 2 + row push; 3: wait + stage 3;
+ * 0 = all): lets a single-GPU test that emulates the ranks with several VMs issue the phases in lockstep */
+void hevmx_ks_shard_p2p_phase(void *vm, int64_t phase, int64_t opcode, int64_t dst, int64_t lhs, int64_t rhs);
 void hevmx_p2p_targets(void *vm, int64_t level, int64_t *tlo, int64_t *thi);
 void hevmx_p2p_timing(void *vm, int on, double *out5 /*ms: stage1, digit exchange, stage2, row exchange, stage3*/);
 /* --- key import (the .seal loader, dacapo_b200/seal_format.py): canonical residues in SEAL's layouts --- */

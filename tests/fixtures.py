@@ -33,3 +33,29 @@ def resnet20_files(tmpdir=None, variant=""):
     meta = json.loads((fixture / "meta.json").read_text())
     x = np.load(fixture / "input.npy") if (fixture / "input.npy").is_file() else np.load(fixture / "input.npz")["packed"]
     return str(cst), str(hv), x, np.load(fixture / "expected.npy"), meta
+
+
+ARMS = FIXTURE.parent / "resnet20_arms"
+
+
+def resnet20_arm_files(tmpdir, arm="dacapo", waterline=40):
+    """The ResNet-20 program compiled by the restated reference pipelines (tests/golden/make_resnet_pars_dacapo.py):
+    arm = "pars" (hand-placed bootstraps, ProactiveRescaling) | "dacapo" (automatic placement).  Input / expected logits
+    are those of the resnet20 fixture.  Returns (cst_path, hevm_path, input, expected, meta of the arm)."""
+    tmp = Path(tmpdir)
+    name = f"{arm}_w{waterline}"
+    allmeta = json.loads((ARMS / "meta.json").read_text())
+    meta = allmeta["arms"][name]
+    src = ARMS / (f"{name}.cst.xz" if meta.get("own_constant_pool") else "consts.cst.xz")
+    cst = tmp / src.name[:-3]
+    hv = tmp / f"{name}.hevm"
+    if not cst.is_file():
+        with lzma.open(src) as f, open(cst, "wb") as o:
+            while True:
+                b = f.read(1 << 24)
+                if not b:
+                    break
+                o.write(b)
+    hv.write_bytes((ARMS / f"{name}.hevm").read_bytes())
+    base = json.loads((FIXTURE / "meta.json").read_text())
+    return str(cst), str(hv), np.load(FIXTURE / "input.npy"), np.load(FIXTURE / "expected.npy"), {**base, **meta}

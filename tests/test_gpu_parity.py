@@ -62,6 +62,19 @@ def test_ntt_bit_exact(pair, prime):
     assert np.array_equal(g.ntt(F, prime, inverse=True), f)
 
 
+@pytest.mark.parametrize("prime", [0, 6, 13])
+def test_cluster_ntt_bit_exact(pair, prime):
+    """The single-pass cluster NTT (ntt_cluster.cuh: TMA tile loads, DSMEM transpose inside an 8-CTA cluster) must give
+    the same canonical residues as the oracle's forward NTT; 19 limbs = more clusters than fit the GPU at once."""
+    g, o = pair
+    rng = np.random.default_rng(50 + prime)
+    q = o.primes[prime]
+    f = rng.integers(0, q, size=(19, o.N), dtype=np.uint64)
+    f[0, :4] = [0, 1, q - 1, q // 2]
+    f[18, :] = q - 1
+    assert np.array_equal(g.ntt(f, prime, inverse=2), o.ntt(f, prime))
+
+
 @pytest.mark.parametrize("lvl", list(range(1, NPR)))  # every level of the modulus chain (SURVEY.md 4)
 def test_elementwise_ops(pair, lvl):
     g, o = pair
@@ -221,9 +234,14 @@ def test_p2p_sharded_keyswitch_sharded_key_storage(oracle_lib, b200_lib, tmp_pat
         o.exec(asm.ROTATE, 2, 0, 1)
         o.exec(asm.ROTATE, 2, 2, -2)
         o.exec(asm.MULCC, 3, 0, 1)
-        # rank by rank, asynchronously: rotate(1) -> all ranks, then rotate(-2) of the result, then mulcc
-        for v in vms:
-            lib.hevmx_ks_shard_p2p(v.vm, 1, 2, 0, 1)
+        # the ranks share one GPU here, so every op is issued phase by phase over all ranks (a rank's wait kernel is then
+        # never queued in front of the push it waits for): rotate(1), then rotate(-2) of the result, then mulcc
+        def sharded(opcode, dst, lhs, rhs):
+            for phase in (1, 2, 3):
+                for v in vms:
+                    lib.hevmx_ks_shard_p2p_phase(v.vm, phase, opcode, dst, lhs, rhs)
+
+        sharded(1, 2, 0, 1)
         # the second rotation reads register 2, of which every rank only holds ITS limbs: gather them first
         for v in vms:
             lib.hevmx_sync(v.vm)
@@ -234,9 +252,8 @@ def test_p2p_sharded_keyswitch_sharded_key_storage(oracle_lib, b200_lib, tmp_pat
             full[:, tlo:min(thi, lvl)] = parts[g][:, tlo:min(thi, lvl)]
         for v in vms:
             v.ct_write(2, full, 2.0 ** 40)
-            lib.hevmx_ks_shard_p2p(v.vm, 1, 2, 2, -2 & 0xFFFF)
-        for v in vms:
-            lib.hevmx_ks_shard_p2p(v.vm, 8, 3, 0, 1)
+        sharded(1, 2, 2, -2 & 0xFFFF)
+        sharded(8, 3, 0, 1)
         for v in vms:
             lib.hevmx_sync(v.vm)
         for reg in (2, 3):
@@ -245,6 +262,35 @@ def test_p2p_sharded_keyswitch_sharded_key_storage(oracle_lib, b200_lib, tmp_pat
                 tlo, thi = static_targets(lvl, npr, g, world)
                 got[:, tlo:min(thi, lvl)] = v.ct_read(reg)[:, tlo:min(thi, lvl)]
             assert np.array_equal(got, o.ct_read(reg)), (lvl, reg)
+
+
+def test_seal_key_directory_round_trip(b200_lib, tmp_path_factory):
+    """dacapo_b200/seal_format.py: VM A's keys are written as a SEAL key directory (parm / pub / sec / relin / gal .seal,
+    SEAL_HEVM.cpp:56-88), VM B -- created from ANOTHER seed -- loads them (loadSEAL, 91-129) and from then on computes the
+    very same words as A: the path a key set made by a real SEAL 4.0 would take into this backend."""
+    from dacapo_b200 import seal_format as sf
+    steps = (1, -2, 64)
+    a = VM(b200_lib, 14, 5, seed=0xA11CE, keydir=str(tmp_path_factory.mktemp("ka")), nct=4, npt=2, galois_steps=steps)
+    b = VM(b200_lib, 14, 5, seed=0xB0B, keydir=str(tmp_path_factory.mktemp("kb")), nct=4, npt=2, galois_steps=(1,))
+    assert not np.array_equal(a.key(0), b.key(0))
+    d = tmp_path_factory.mktemp("sealdir")
+    sf.export_vm_keys(b200_lib, a.vm, d, sf.COMPR_ZSTD)
+    kd = sf.load_seal_keys(b200_lib, b.vm, d)
+    assert kd["primes"] == a.primes and len(kd["galois"]) == len(steps)
+    for which in (0, 1, 2):
+        assert np.array_equal(a.key(which), b.key(which))
+    x = np.random.default_rng(5).uniform(-1, 1, a.N // 2)
+    a.encode(0, x, 4, 50)
+    a.encrypt_pt(0, 0, counter=7)
+    ct = a.ct_read(0)
+    b.ct_write(0, ct, 2.0 ** 50)
+    for vm in (a, b):
+        vm.exec(asm.ROTATE, 1, 0, 64)
+        vm.exec(asm.ROTATE, 1, 1, -2)
+        vm.exec(asm.MULCC, 2, 1, 0)
+        vm.exec(asm.RESCALE, 2, 2)
+    assert np.array_equal(a.ct_read(2), b.ct_read(2))
+    assert np.max(np.abs(b.decrypt_decode(2, 1) - np.roll(x, -62) * x)) < 1e-4   # decrypts under the imported secret key (scale 2^100 / q ~ 2^40)
 
 
 def test_encode_decode_bit_exact(pair):

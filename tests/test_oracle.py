@@ -313,3 +313,43 @@ def test_hevm_program_roundtrip(vm, tmp_path):
     exp = np.roll(w, 2) + w
     assert np.max(np.abs(out - exp)) < 1e-5
     vm.lib.hevmx_resize(vm.vm, 8, 4)
+
+
+# ---- known-answer tests for the externally documented SEAL facts the oracle relies on ----
+def test_kat_galois_elt_from_step(vm):
+    """SEAL GaloisTool::get_elt_from_step (util/galois.cpp): generator 3 modulo 2N; a positive step s (LEFT rotation) maps
+    to 3^s, a negative one to 3^(N/2 - |s|), step 0 to the conjugation element 2N - 1.  N = 2^11 here: 2N = 4096."""
+    m = 2 * vm.N
+    g = lambda st: vm.lib.hevmx_galois_elt(vm.vm, st)
+    assert g(1) == 3 and g(2) == 9 and g(3) == 27 and g(0) == m - 1
+    assert g(-1) == pow(3, vm.N // 2 - 1, m) and (g(-1) * 3) % m == 1  # 3^(N/2) = 1 mod 2N: the inverse rotation
+    assert g(5) == pow(3, 5, m) and g(-7) == pow(3, vm.N // 2 - 7, m)
+
+
+def test_kat_constant_vector_encodes_to_constant_polynomial(vm):
+    """CKKSEncoder: the all-c slot vector is the constant polynomial round(c * scale); in NTT form EVERY residue of limb i
+    is that constant mod q_i.  Hand-computable: c = 0.75, scale 2^40 -> 0x0C000000000."""
+    n = vm.N // 2
+    vm.encode(0, np.full(n, 0.75), 3, 40)
+    p = vm.pt_read(0)
+    assert p.shape == (3, vm.N)
+    for i in range(3):
+        assert np.all(p[i] == np.uint64((3 << 38) % vm.primes[i]))
+    vm.encode(0, np.full(n, -1.0), 2, 30)  # a negative constant is stored as q - |x|
+    p = vm.pt_read(0)
+    for i in range(2):
+        assert np.all(p[i] == np.uint64(vm.primes[i] - (1 << 30)))
+
+
+def test_kat_slot_zero_and_rotation_direction(vm):
+    """SEAL Evaluator::rotate_vector(ct, k): k > 0 rotates the slot vector to the LEFT (slot i receives slot i + k).  A unit
+    vector in slot 5 therefore shows up in slot 4 after rotate(1) and in slot 7 after rotate(-2); slot 0 wraps to slot n-1."""
+    n = vm.N // 2
+    e5, e0 = np.zeros(n), np.zeros(n)
+    e5[5], e0[0] = 1.0, 1.0
+    for vec, step, where in ((e5, 1, 4), (e5, -2, 7), (e0, 1, n - 1), (e0, -1, 1)):
+        vm.encode(0, vec, 3, 40)
+        vm.encrypt_pt(0, 0)
+        vm.exec(asm.ROTATE, 1, 0, step)
+        out = vm.decrypt_decode(1, 1)
+        assert int(np.argmax(out)) == where and abs(out[where] - 1.0) < 1e-6 and np.sum(np.abs(out)) - abs(out[where]) < 1e-3

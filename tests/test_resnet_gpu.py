@@ -109,3 +109,29 @@ def test_resnet20_program_bit_exact_vs_oracle(b200_lib, oracle_lib, tmp_path, ca
     assert rms < 1.5e-3
     with capsys.disabled():
         print(f"\nResNet-20 program: oracle (CPU port, 1 thread) run() {t_oracle:.1f} s | GPU first run {out['gpu', 0][3]:.3f} s, replay {out['gpu', 1][3]:.3f} s | bit-exact, rms {rms:.2e}")
+
+
+@pytest.mark.parametrize("arm", ["dacapo", "pars"])
+def test_resnet20_compiled_by_restated_reference_pipelines(b200_lib, tmp_path, arm):
+    """BASELINE.json configs[3]: the same benchmark compiled by the restated `dacapo` planner (automatic bootstrap
+    placement against profiled_B200_GPU.json) and by `pars` (the benchmark's hand placement), waterline 40."""
+    cst, hv, x, expected, meta = fixtures.resnet20_arm_files(tmp_path, arm, 40)
+    lib = b200_lib
+    vm, _ = make_vm(lib, 15, 14)
+    lib.load(vm, cst.encode(), hv.encode())
+    lib.preprocess(vm)
+    f64p = C.POINTER(C.c_double)
+    lib.encrypt(vm, 0, x.ctypes.data_as(f64p), x.size)
+    lib.run(vm)
+    lib.encrypt(vm, 0, x.ctypes.data_as(f64p), x.size)
+    t = time.perf_counter()
+    lib.run(vm)
+    latency = time.perf_counter() - t
+    out = np.zeros(1 << 14)
+    lib.decrypt_result(vm, 0, out.ctypes.data_as(f64p))
+    res = out[:meta["n_out"]] * meta["post_scale"]
+    rms = float(np.sqrt(np.sum((res - expected) ** 2) / res.shape[-1]))
+    print(f"ResNet-20 via restated {arm}: {meta['bootstraps']} bootstraps, estimated {meta['estimated_latency_s']:.3f} s, run() {latency:.3f} s, rms {rms:.2e}")
+    assert np.argmax(res) == np.argmax(expected)
+    assert rms < 1.5e-3, rms
+    assert latency < 1.0
