@@ -553,7 +553,7 @@ template <int LOGA> HD void body_mac_tail(const ArgsFwdB &a, int job, int K, Lan
   const ModQ m = T.mod[a.sp];
   LANE_DECL;
   FOR_LANES(S, st, {
-    stage_tw_B<LOGA>(tw_s, T.itwB + (size_t)a.sp * N, r, lane); // both warps stage the same table (identical bytes)
+    stage_tw_B<LOGA>(tw_s, T.itwB + (size_t)a.sp * N, r, lane); // `tw_s` is private to this warp (see the callers)
     _Pragma("unroll")
     for (int e = 0; e < 8; e++) S.x[e] = rows[K * 256 + lane * 8 + e];
     cp_async_wait();

@@ -65,6 +65,7 @@ __global__ void __cluster_dims__(NC_CLUSTER, 1, 1) __launch_bounds__(NC_WARPS * 
   }
   __syncwarp();
   stage_tw_A<LOGA>(tw, T->tw + (size_t)p * N, lane); // 128 pass-A twiddles of this prime (one cp.async batch)
+  cluster.sync(); // distributed shared memory may only be written once every CTA of the cluster is known to be running
   for (int k = 0; k < 2; k++) {
     const int c0 = (crank * 8 + warp * 2 + k) * Geo<LOGA>::C;
     if (lane == 0) {

@@ -114,7 +114,7 @@ struct EmuLauncher {
       if (mac_Iidx<LOGA>(a, j) == a.l)
         for (int K = 0; K < 2; K++) {
           LaneB8 st[32];
-          body_mac_tail<LOGA>(a, j, K, st, rowbufs + K * 2 * MAC_ROW_WORDS, tw_s, tiles);
+          body_mac_tail<LOGA>(a, j, K, st, rowbufs + K * 2 * MAC_ROW_WORDS, K ? tw_s : reinterpret_cast<Tw *>(tiles + 512), tiles);
         }
     }
   }
