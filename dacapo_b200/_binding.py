@@ -24,7 +24,7 @@ EXT_SYMBOLS = [
 
 B200_ONLY_SYMBOLS = ["hevmx_ntt_bench", "hevmx_timer", "hevmx_profile", "hevmx_profile_read", "hevmx_profiler_range",
                      "hevmx_ks_shard_stage", "hevmx_mulcc_shard_stage", "hevmx_dev_ptr", "hevmx_stream", "hevmx_exec_batch",
-                     "hevmx_p2p_setup", "hevmx_p2p_connect", "hevmx_ks_shard_p2p", "hevmx_ks_shard_p2p_phase", "hevmx_p2p_targets", "hevmx_p2p_timing",
+                     "hevmx_p2p_setup", "hevmx_p2p_connect", "hevmx_ks_shard_p2p", "hevmx_ks_shard_p2p_phase", "hevmx_p2p_targets", "hevmx_p2p_timing", "hevmx_p2p_bench",
                      "hevmx_key_write", "hevmx_galois_clear"]
 
 _u64p = C.POINTER(C.c_uint64)
@@ -108,6 +108,8 @@ def bind(path):
         lw.hevmx_p2p_connect.argtypes = [C.c_void_p, C.c_int64, C.c_char_p, C.c_void_p]
         lw.hevmx_ks_shard_p2p.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64]
         lw.hevmx_ks_shard_p2p_phase.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64]
+        lw.hevmx_p2p_bench.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+        lw.hevmx_p2p_bench.restype = C.c_double
         lw.hevmx_p2p_targets.argtypes = [C.c_void_p, C.c_int64, _i64p, _i64p]
         lw.hevmx_p2p_timing.argtypes = [C.c_void_p, C.c_int, _f64p]
         lw.hevmx_key_write.argtypes = [C.c_void_p, C.c_int, C.c_uint64, _u64p]

@@ -410,19 +410,58 @@ INSTANTIATE(9)
 // =====================================================================================
 __global__ void __launch_bounds__(256) k_p2p_push(const u64 *src, size_t words, PeerPtrs peer, size_t dst_off, int self, int world,
                                                   unsigned *done_ctr, size_t flag_off, unsigned long long epoch) {
+  // blockIdx.y = destination peer (one load + one 16-byte store per thread: many independent stores in flight per link)
   const size_t nvec = words / 2; // 16-byte pieces (limb rows are multiples of 16 bytes)
+  const int g = (self + 1 + blockIdx.y) % world;
   for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
     u64 a, b;
     asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(src + 2 * v) : "memory");
-    for (int g = 0; g < world; g++)
-      if (g != self) asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"(peer.p[g] + dst_off + 2 * v), "l"(a), "l"(b) : "memory");
+    asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"(peer.p[g] + dst_off + 2 * v), "l"(a), "l"(b) : "memory");
   }
   __threadfence_system();
   __syncthreads();
   __shared__ bool last;
-  if (threadIdx.x == 0) last = atomicAdd(done_ctr, 1u) == gridDim.x - 1;
+  if (threadIdx.x == 0) last = atomicAdd(done_ctr, 1u) == gridDim.x * gridDim.y - 1;
   __syncthreads();
   if (last) { // every CTA's stores are ordered before its increment: publish
+    if (threadIdx.x == 0) *done_ctr = 0;
+    if ((int)threadIdx.x < world && (int)threadIdx.x != self) {
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer.p[threadIdx.x] + flag_off + self), "l"(epoch) : "memory");
+    }
+  }
+}
+// The same push with the TMA engine: one elected thread per CTA bulk-loads a 16 KB chunk into shared memory
+// (cp.async.bulk global -> shared, mbarrier completion) and bulk-stores it into the peer's block (cp.async.bulk shared ->
+// global on the CUDA-IPC mapped address): large NVLink transactions instead of 16-byte stores.  grid = (chunks, peers).
+#define P2P_CHUNK_WORDS 2048
+__global__ void __launch_bounds__(32) k_p2p_push_tma(const u64 *src, size_t words, PeerPtrs peer, size_t dst_off, int self, int world,
+                                                     unsigned *done_ctr, size_t flag_off, unsigned long long epoch) {
+  __shared__ __align__(128) u64 buf[P2P_CHUNK_WORDS];
+  __shared__ __align__(8) u64 bar;
+  const int g = (self + 1 + blockIdx.y) % world;
+  const size_t off = (size_t)blockIdx.x * P2P_CHUNK_WORDS;
+  if (threadIdx.x == 0 && off < words) {
+    const unsigned bytes = (unsigned)((words - off < P2P_CHUNK_WORDS ? words - off : P2P_CHUNK_WORDS) * 8);
+    const unsigned sb = (unsigned)__cvta_generic_to_shared(buf), sbar = (unsigned)__cvta_generic_to_shared(&bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sbar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb), "l"(src + off), "r"(bytes), "r"(sbar)
+                 : "memory");
+    asm volatile("{\n\t.reg .pred p;\n\tW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra D_%=;\n\tbra W_%=;\n\tD_%=:\n\t}" ::"r"(sbar)
+                 : "memory");
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(peer.p[g] + dst_off + off), "r"(sb), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // the bulk store has completed (not merely been read out of shared memory)
+    asm volatile("fence.proxy.async;" ::: "memory");
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(done_ctr, 1u) == gridDim.x * gridDim.y - 1;
+  __syncthreads();
+  if (last) {
     if (threadIdx.x == 0) *done_ctr = 0;
     if ((int)threadIdx.x < world && (int)threadIdx.x != self) {
       __threadfence_system();
@@ -449,10 +488,25 @@ __global__ void k_p2p_wait(const u64 *block, size_t flag_off, int self, int worl
 }
 void launch_p2p_push(cudaStream_t s, const u64 *src, size_t words, const PeerPtrs &peer, size_t dst_off, int self, int world,
                      unsigned *done_ctr, size_t flag_off, unsigned long long epoch) {
+  static const int mode = std::getenv("HEVM_P2P_PUSH") ? std::atoi(std::getenv("HEVM_P2P_PUSH")) : 1; // 1 = TMA bulk copies, 0 = 16-byte stores
+  if (mode == 1 && words % 2 == 0) {
+    const size_t chunks = words ? (words + P2P_CHUNK_WORDS - 1) / P2P_CHUNK_WORDS : 1;
+    k_p2p_push_tma<<<dim3((unsigned)chunks, (unsigned)(world > 1 ? world - 1 : 1)), 32, 0, s>>>(src, words, peer, dst_off, self, world, done_ctr, flag_off, epoch);
+    POST_LAUNCH_S(s);
+    return;
+  }
   size_t g = (words / 2 + 255) / 256;
   if (g < 1) g = 1;
-  if (g > 148 * 2) g = 148 * 2;
-  k_p2p_push<<<(unsigned)g, 256, 0, s>>>(src, words, peer, dst_off, self, world, done_ctr, flag_off, epoch);
+  if (g > 148) g = 148;
+  k_p2p_push<<<dim3((unsigned)g, (unsigned)(world > 1 ? world - 1 : 1)), 256, 0, s>>>(src, words, peer, dst_off, self, world, done_ctr, flag_off, epoch);
+  POST_LAUNCH_S(s);
+}
+__global__ void k_p2p_flag(u64 *flag, unsigned long long epoch) {
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
+}
+void launch_p2p_flag(cudaStream_t s, u64 *flag, unsigned long long epoch) {
+  k_p2p_flag<<<1, 1, 0, s>>>(flag, epoch);
   POST_LAUNCH_S(s);
 }
 void launch_p2p_wait(cudaStream_t s, const u64 *block, size_t flag_off, int self, int world, int only, unsigned long long epoch) {

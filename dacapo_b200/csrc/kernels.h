@@ -68,6 +68,7 @@ struct PeerPtrs {
 // system-visible -- write `epoch` into flag word `flag_off + self` of every peer's block
 void launch_p2p_push(cudaStream_t s, const u64 *src, size_t words, const PeerPtrs &peer, size_t dst_off, int self, int world,
                      unsigned *done_ctr, size_t flag_off, unsigned long long epoch);
+void launch_p2p_flag(cudaStream_t s, u64 *flag, unsigned long long epoch); // one system-scope release store (after a copy-engine push)
 // spin until flag word `flag_off + g` of the LOCAL block is >= epoch for every peer g (only >= 0: just that peer)
 void launch_p2p_wait(cudaStream_t s, const u64 *block, size_t flag_off, int self, int world, int only, unsigned long long epoch);
 

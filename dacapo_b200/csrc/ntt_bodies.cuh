@@ -174,6 +174,7 @@ struct ArgsFwdA {
   int plast; // ROUND: prime index of the divided-out modulus
   // limb-sharded key switching: only the targets [t0, t0 + nt) are produced (nt = 0: all of them)
   int t0, nt;
+  int j0, nj; // MODUP: only the digits [j0, j0 + nj) (nj = 0: all l) -- the sharded key switch starts on a peer's digits as they arrive
   int pmod; // PRE_NONE: limb d uses prime prime0 + (d % pmod) * pstep (several polynomials in one launch); 0 = no wrap
 };
 template <int LOGA, int PRE> HD void body_fwd_A(const ArgsFwdA &a, int job, LaneA *st, u64 *sm) {
@@ -185,8 +186,9 @@ template <int LOGA, int PRE> HD void body_fwd_A(const ArgsFwdA &a, int job, Lane
     sl = d;
     ps = pd = a.prime0 + (a.pmod ? d % a.pmod : d) * a.pstep;
   } else if (PRE == PRE_MODUP) {
-    const int Iidx = d / a.l + a.t0; // job rows enumerate the owned targets only
-    sl = d - (Iidx - a.t0) * a.l;
+    const int nj = a.nj ? a.nj : a.l;
+    const int Iidx = d / nj + a.t0; // job rows enumerate the owned targets only
+    sl = a.j0 + d - (Iidx - a.t0) * nj;
     ps = sl;
     pd = (Iidx == a.l) ? a.sp : Iidx;
     if (pd == ps) return; // diagonal: the NTT-form input is used directly by the MAC kernel

@@ -12,6 +12,7 @@
 // ring-size independent interface (the VM holds one of these per lane)
 struct OpsIface {
   Scratch sc;
+  int shard_j0 = 0, shard_nj = 0; // ks_shard_stage(20, ...): the digit range of this call
   int key_L = 0, key_t0 = 0; // limb-sharded KEY STORAGE (this rank stores limbs [key_t0, key_t0 + key_L) of every key); 0 = whole keys
   virtual ~OpsIface() {}
   // limb k is transformed under prime prime0 + (pmod ? k % pmod : k) * pstep (pmod: several polynomials of pmod limbs each)
@@ -202,12 +203,19 @@ template <class LA, int LOGA> struct HeOps : OpsIface {
       ArgsInttA y{};
       y.T = T, y.src = sc.s1 + (size_t)tlo * N, y.dst = sc.t + (size_t)tlo * N, y.nl = nd, y.prime0 = tlo, y.pstep = 1, y.round = 0;
       la.template intt_A<LOGA>(y, nd * TILES_A);
-    } else if (stage == 2) {
+    } else if (stage == 2 || stage >= 20) {
+      // stage 2 = 20 (mod-up pass A of the digits [j0, j0 + nj), all of them by default) + 21 (inner product, rounding)
       const int nt = thi - tlo;
       if (nt <= 0) return;
-      ArgsFwdA x{};
-      x.T = T, x.src = sc.t, x.dst = sc.s2, x.l = l, x.sp = sp(), x.t0 = tlo, x.nt = nt;
-      la.template fwd_A<LOGA, PRE_MODUP>(x, nt * l * TILES_A);
+      if (stage != 21) {
+        const int j0 = stage == 20 ? shard_j0 : 0, nj = stage == 20 ? shard_nj : l;
+        if (nj > 0) {
+          ArgsFwdA x{};
+          x.T = T, x.src = sc.t, x.dst = sc.s2, x.l = l, x.sp = sp(), x.t0 = tlo, x.nt = nt, x.j0 = j0, x.nj = nj;
+          la.template fwd_A<LOGA, PRE_MODUP>(x, nt * nj * TILES_A);
+        }
+        if (stage == 20) return;
+      }
       ArgsFwdB m{};
       m.T = T, m.src = sc.s2, m.dst = sc.acc, m.l = l, m.sp = sp(), m.key = key, m.Ltot = key_L ? key_L : L, m.key_t0 = key_t0, m.ld = mode, m.elt = elt;
       m.tgt = a + pitch, m.tgt2 = (mode == LD_PRODUCT) ? b + pitch : nullptr, m.sp_rows = sc.s1, m.i_end = thi;

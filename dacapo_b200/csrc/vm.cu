@@ -134,7 +134,37 @@ struct VM {
     unsigned long long epoch = 0;
     cudaEvent_t ev[6] = {};
     bool timed = false;
+    // copy-engine push (HEVM_P2P_PUSH=2): the per-peer copies run on side streams, each followed by that peer's flag
+    cudaStream_t side[4] = {};
+    cudaEvent_t fork = nullptr, copied[2][4] = {};
+    bool copied_valid[2] = {false, false};
   } p2p;
+  // push `words` from `src` (in this rank's block, offset dst_off) into every peer's block + raise flag slot `flag_off`
+  void p2p_push(const u64 *src, size_t words, size_t dst_off, size_t flag_off, unsigned long long e, int par) {
+    Lane &L0 = lanes[0];
+    unsigned *done = reinterpret_cast<unsigned *>(p2p.block + p2p_words() - 2);
+    static const int mode = std::getenv("HEVM_P2P_PUSH") ? std::atoi(std::getenv("HEVM_P2P_PUSH")) : 1;
+    if (mode != 2 || p2p.world == 1) {
+      launch_p2p_push(L0.stream, src, words, p2p.peer, dst_off, p2p.rank, p2p.world, done, flag_off, e);
+      return;
+    }
+    if (!p2p.fork) {
+      CUDA_CHECK(cudaEventCreateWithFlags(&p2p.fork, cudaEventDisableTiming));
+      for (auto &st : p2p.side) CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      for (auto &row : p2p.copied)
+        for (auto &ev : row) CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
+    CUDA_CHECK(cudaEventRecord(p2p.fork, L0.stream));
+    for (int i = 0; i < 4; i++) CUDA_CHECK(cudaStreamWaitEvent(p2p.side[i], p2p.fork, 0));
+    for (int k = 0; k + 1 < p2p.world; k++) {
+      const int g = (p2p.rank + 1 + k) % p2p.world;
+      cudaStream_t st = p2p.side[k % 4];
+      if (words) CUDA_CHECK(cudaMemcpyAsync(p2p.peer.p[g] + dst_off, src, words * 8, cudaMemcpyDeviceToDevice, st));
+      launch_p2p_flag(st, p2p.peer.p[g] + flag_off + p2p.rank, e);
+    }
+    for (int i = 0; i < 4; i++) CUDA_CHECK(cudaEventRecord(p2p.copied[par][i], p2p.side[i]));
+    p2p.copied_valid[par] = true;
+  }
   size_t p2p_t_off(int parity) const { return (size_t)parity * L * N; }
   size_t p2p_rnd_off(int parity) const { return (size_t)2 * L * N + (size_t)parity * 2 * N; }
   size_t p2p_flag_off(int slot) const { return (size_t)2 * L * N + 4 * N + (size_t)slot * 8; }
@@ -644,10 +674,11 @@ struct VM {
     if (phase <= 1) ++p2p.epoch;
     const unsigned long long e = p2p.epoch;
     const int par = (int)(e & 1);
+    if (phase <= 1 && p2p.copied_valid[par])  // copy-engine pushes of the key switch before last read this parity's buffers
+      for (int i = 0; i < 4; i++) CUDA_CHECK(cudaStreamWaitEvent(L0.stream, p2p.copied[par][i], 0));
     Scratch &sc = L0.ops->sc;
     u64 *save_t = sc.t, *save_rnd = sc.rnd;
     sc.t = p2p.block + p2p_t_off(par), sc.rnd = p2p.block + p2p_rnd_off(par);
-    unsigned *done = reinterpret_cast<unsigned *>(p2p.block + p2p_words() - 2);
     auto mark = [&](int i) {
       if (p2p.timed) CUDA_CHECK(cudaEventRecord(p2p.ev[i], L0.stream));
     };
@@ -656,15 +687,33 @@ struct VM {
       mark(0);
       L0.ops->ks_shard_stage(1, mode, a.d, bd, d.d, pitch, l, key, elt, tlo, thi);
       mark(1);
-      launch_p2p_push(L0.stream, sc.t + (size_t)tlo * N, (size_t)nd * N, p2p.peer, p2p_t_off(par) + (size_t)tlo * N, p2p.rank, p2p.world, done,
-                      p2p_flag_off(0), e);
+      p2p_push(sc.t + (size_t)tlo * N, (size_t)nd * N, p2p_t_off(par) + (size_t)tlo * N, p2p_flag_off(0), e, par);
     }
     if (phase == 0 || phase == 2) {
-      launch_p2p_wait(L0.stream, p2p.block, p2p_flag_off(0), p2p.rank, p2p.world, -1, e);
       mark(2);
-      L0.ops->ks_shard_stage(2, mode, a.d, bd, d.d, pitch, l, key, elt, tlo, thi);
+      // HEVM_P2P_OVERLAP=1: mod-up pass A source rank by source rank, own digits first -- a peer's digits are waited for
+      // only when their turn comes, so the exchange overlaps the pass-A work on what has already arrived.  Measured on
+      // 8 B200s (N = 2^16, level 29) it LOSES: eight quarter-wave launches cost 224 us against 176 us for one launch
+      // behind one wait, so the default is to wait for every peer and transform all digits in one launch.
+      static const bool overlap = std::getenv("HEVM_P2P_OVERLAP") && std::atoi(std::getenv("HEVM_P2P_OVERLAP")) != 0;
+      if (!overlap) {
+        launch_p2p_wait(L0.stream, p2p.block, p2p_flag_off(0), p2p.rank, p2p.world, -1, e);
+        L0.ops->shard_j0 = 0, L0.ops->shard_nj = l;
+        L0.ops->ks_shard_stage(20, mode, a.d, bd, d.d, pitch, l, key, elt, tlo, thi);
+      }
+      for (int k = 0; overlap && k < p2p.world; k++) {
+        const int r = (p2p.rank + k) % p2p.world;
+        int rlo, rhi;
+        own_range(L, r, p2p.world, rlo, rhi);
+        const int j0 = std::min(rlo, l), j1 = std::min(rhi, l);
+        if (j1 <= j0) continue;
+        if (r != p2p.rank) launch_p2p_wait(L0.stream, p2p.block, p2p_flag_off(0), p2p.rank, p2p.world, r, e);
+        L0.ops->shard_j0 = j0, L0.ops->shard_nj = j1 - j0;
+        L0.ops->ks_shard_stage(20, mode, a.d, bd, d.d, pitch, l, key, elt, tlo, thi);
+      }
+      L0.ops->ks_shard_stage(21, mode, a.d, bd, d.d, pitch, l, key, elt, tlo, thi);
       mark(3);
-      if (own_sp) launch_p2p_push(L0.stream, sc.rnd, (size_t)2 * N, p2p.peer, p2p_rnd_off(par), p2p.rank, p2p.world, done, p2p_flag_off(1), e);
+      if (own_sp) p2p_push(sc.rnd, (size_t)2 * N, p2p_rnd_off(par), p2p_flag_off(1), e, par);
     }
     if (phase == 0 || phase == 3) {
       if (!own_sp) launch_p2p_wait(L0.stream, p2p.block, p2p_flag_off(1), p2p.rank, p2p.world, sp_owner, e);
@@ -1533,6 +1582,28 @@ void hevmx_ks_shard_p2p_phase(void *h, int64_t phase, int64_t opcode, int64_t ds
     die("ks_shard_p2p: opcode must be 1 (rotate) or 8 (mulcc)");
   }
 }
+// bandwidth probe of the exchange path: push `words` u64 of this rank's block into every peer `reps` times (no flags are
+// consumed: epoch 0); returns the average milliseconds of one push on this rank.  All ranks must call it together.
+double hevmx_p2p_bench(void *h, int64_t words, int64_t reps) {
+  VM *vm = V(h);
+  auto &p = vm->p2p;
+  if (!p.on || words < 0 || (size_t)words > (size_t)vm->L * vm->N) die("p2p_bench: bad arguments");
+  Lane &L0 = vm->lanes[0];
+  unsigned *done = reinterpret_cast<unsigned *>(p.block + vm->p2p_words() - 2);
+  cudaEvent_t a, b;
+  CUDA_CHECK(cudaEventCreate(&a));
+  CUDA_CHECK(cudaEventCreate(&b));
+  launch_p2p_push(L0.stream, p.block, (size_t)words, p.peer, 0, p.rank, p.world, done, vm->p2p_flag_off(1), 0);
+  CUDA_CHECK(cudaEventRecord(a, L0.stream));
+  for (int64_t r = 0; r < reps; r++) launch_p2p_push(L0.stream, p.block, (size_t)words, p.peer, 0, p.rank, p.world, done, vm->p2p_flag_off(1), 0);
+  CUDA_CHECK(cudaEventRecord(b, L0.stream));
+  CUDA_CHECK(cudaEventSynchronize(b));
+  float ms = 0;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+  CUDA_CHECK(cudaEventDestroy(a));
+  CUDA_CHECK(cudaEventDestroy(b));
+  return (double)ms / (double)reps;
+}
 // the owned key-switch targets [tlo, thi) of this rank at `level` (target `level` = the special limb)
 void hevmx_p2p_targets(void *h, int64_t level, int64_t *tlo, int64_t *thi) {
   int a, b;
@@ -1540,7 +1611,8 @@ void hevmx_p2p_targets(void *h, int64_t level, int64_t *tlo, int64_t *thi) {
   *tlo = a, *thi = b;
 }
 // CUDA-event breakdown of the NEXT sharded key switch: on = 1 arms it; after hevmx_sync, on = 0 reads five durations (ms):
-// stage 1 | digit push + wait | stage 2 | rounded-row push / wait | stage 3
+// stage 1 | digit push | stage 2 (mod-up pass A per source rank behind that rank's flag, then the inner product) |
+// rounded-row push / wait | stage 3
 void hevmx_p2p_timing(void *h, int on, double *out5) {
   VM *vm = V(h);
   if (on) {

@@ -156,7 +156,7 @@ class ShardedP2P:
         fn()
         self.lib.hevmx_sync(self.vm)
         self.lib.hevmx_p2p_timing(self.vm, 0, out)
-        return {k: round(v * 1e3, 1) for k, v in zip(("stage1", "digit_exchange", "stage2", "row_exchange", "stage3"), out)}
+        return {k: round(v * 1e3, 1) for k, v in zip(("stage1", "digit_push", "stage2_with_digit_waits", "row_exchange", "stage3"), out)}
 
 
 def measure(lib, rank: int, world: int, logn: int = 16, nprimes: int = 30, levels=None, reps: int = 20, seed: int = 0xDACA90):
@@ -212,6 +212,17 @@ def measure(lib, rank: int, world: int, logn: int = 16, nprimes: int = 30, level
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()) * 1e3
 
+    # bandwidth of the exchange path itself: every rank pushes `words` u64 into all peers at once (all-to-all over NVSwitch)
+    bw = {}
+    for words in (4 * N, nprimes * N):
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = lib.hevmx_p2p_bench(vm2, words, 10)
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        bw[f"{words * 8 / 1e6:.1f}MB_per_peer"] = {"us": round(float(t.item()) * 1e3, 1),
+                                                  "egress_GBps_per_gpu": round(words * 8 * (world - 1) / (float(t.item()) * 1e-3) / 1e9, 1)}
+    out["p2p_push_bandwidth"] = bw
     for lvl in levels or (nprimes - 1, (nprimes - 1) // 2):
         rng = np.random.default_rng(1000 + lvl)  # same ciphertext on every rank
         a = np.zeros((2, lvl, N), dtype=np.uint64)

@@ -76,6 +76,7 @@ void hevmx_ks_shard_p2p(void *vm, int64_t opcode /*1 rotate, 8 mulcc*/, int64_t 
 /* the same op cut at its two exchanges (phase 1: stage 1 + digit push; 2: wait + stage 2 + row push; 3: wait + stage 3;
  * 0 = all): lets a single-GPU test that emulates the ranks with several VMs issue the phases in lockstep */
 void hevmx_ks_shard_p2p_phase(void *vm, int64_t phase, int64_t opcode, int64_t dst, int64_t lhs, int64_t rhs);
+double hevmx_p2p_bench(void *vm, int64_t words, int64_t reps); /* ms per push of `words` u64 into every peer (all ranks together) */
 void hevmx_p2p_targets(void *vm, int64_t level, int64_t *tlo, int64_t *thi);
 void hevmx_p2p_timing(void *vm, int on, double *out5 /*ms: stage1, digit exchange, stage2, row exchange, stage3*/);
 /* --- key import (the .seal loader, dacapo_b200/seal_format.py): canonical residues in SEAL's layouts --- */

@@ -175,6 +175,33 @@ void emul_keyswitch_sharded(void *h, int mode, const u64 *a, const u64 *b, u64 *
       e->ops->ks_shard_stage(stage, mode, a, b, dst, (size_t)l * e->P.N, l, ks.data(), elt, tlo, thi);
     }
 }
+// the same, with stage 2 cut like the peer-to-peer path does: mod-up pass A per SOURCE rank (digit ranges, own rank first),
+// then the inner product
+void emul_keyswitch_sharded_split(void *h, int mode, const u64 *a, const u64 *b, u64 *dst, int l, const u64 *key, u32 elt, int ranks) {
+  auto e = (Emu *)h;
+  const size_t kw = (size_t)(e->P.L - 1) * 2 * e->P.L * e->P.N;
+  std::vector<u64> ks(kw);
+  for (size_t i = 0; i < kw; i++) ks[i] = split30(key[i]);
+  auto range = [&](int g, int &lo, int &hi) { lo = (int)((long)(l + 1) * g / ranks), hi = (int)((long)(l + 1) * (g + 1) / ranks); };
+  for (int stage = 1; stage <= 3; stage++)
+    for (int g = 0; g < ranks; g++) {
+      int tlo, thi;
+      range(g, tlo, thi);
+      if (stage != 2) {
+        e->ops->ks_shard_stage(stage, mode, a, b, dst, (size_t)l * e->P.N, l, ks.data(), elt, tlo, thi);
+        continue;
+      }
+      for (int k = 0; k < ranks; k++) {
+        int rlo, rhi;
+        range((g + k) % ranks, rlo, rhi);
+        if (rhi > l) rhi = l;
+        if (rhi <= rlo) continue;
+        e->ops->shard_j0 = rlo, e->ops->shard_nj = rhi - rlo;
+        e->ops->ks_shard_stage(20, mode, a, b, dst, (size_t)l * e->P.N, l, ks.data(), elt, tlo, thi);
+      }
+      e->ops->ks_shard_stage(21, mode, a, b, dst, (size_t)l * e->P.N, l, ks.data(), elt, tlo, thi);
+    }
+}
 void emul_set_fused(void *h, int on) { ((Emu *)h)->la.use_fused = on != 0; }
 long emul_waits_checked(void *h) { return ((Emu *)h)->la.waits_checked; }
 // batched single-launch key switch: n ciphertexts (compact [2][l][N] each, contiguous), one scratch area per ciphertext

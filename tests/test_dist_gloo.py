@@ -38,6 +38,24 @@ def test_two_rank_gloo(tmp_path):
     assert "rank0ok" in r.stdout and "rank1ok" in r.stdout
 
 
+def test_static_target_ownership():
+    """Round-2 static ownership of key-switch targets (sharded.static_targets == VM::own_range cut to a level): a partition
+    of [0, level], balanced to within one, the special target with the last rank, and the last rank never the busiest."""
+    sys.path.insert(0, str(REPO))
+    from dacapo_b200.sharded import static_targets
+    for L in (14, 30, 7):
+        for w in (1, 2, 3, 8):
+            full = [static_targets(L - 1, L, g, w) for g in range(w)]
+            sizes = [hi - lo for lo, hi in full]
+            assert full[0][0] == 0 and full[-1][1] == L and all(full[g][1] == full[g + 1][0] for g in range(w - 1))
+            assert max(sizes) - min(sizes) <= 1 and sizes[-1] == min(sizes)
+            for lvl in range(1, L):
+                parts = [static_targets(lvl, L, g, w) for g in range(w)]
+                cover = sorted(t for lo, hi in parts for t in range(lo, hi))
+                assert cover == list(range(lvl + 1)), (L, w, lvl, parts)
+                assert parts[-1][1] == lvl + 1
+
+
 def test_shard_balanced():
     sys.path.insert(0, str(REPO))
     from dacapo_b200 import dist as D

@@ -35,6 +35,7 @@ def emul(LOGN):
     lib.emul_keyswitch.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p, C.c_int, u64p, C.c_uint32]
     lib.emul_rescale.argtypes = [C.c_void_p, u64p, u64p, C.c_int]
     lib.emul_keyswitch_sharded.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p, C.c_int, u64p, C.c_uint32, C.c_int]
+    lib.emul_keyswitch_sharded_split.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p, C.c_int, u64p, C.c_uint32, C.c_int]
     lib.emul_set_fused.argtypes = [C.c_void_p, C.c_int]
     lib.emul_waits_checked.argtypes = [C.c_void_p]
     lib.emul_waits_checked.restype = C.c_long
@@ -135,6 +136,9 @@ def test_sharded_rotate_kernels_vs_oracle(emul, vm, ranks):
     got = np.zeros_like(a)
     lib.emul_keyswitch_sharded(h, 1, _p(a), None, _p(got), lvl, _p(key), elt, ranks)
     assert np.array_equal(got, exp)
+    got2 = np.zeros_like(a)  # stage 2 cut per source rank (the peer-to-peer path's order)
+    lib.emul_keyswitch_sharded_split(h, 1, _p(a), None, _p(got2), lvl, _p(key), elt, ranks)
+    assert np.array_equal(got2, exp)
 
 
 @pytest.mark.parametrize("ranks", [2, 3])
