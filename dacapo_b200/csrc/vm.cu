@@ -226,6 +226,7 @@ struct VM {
       shard_world = std::max(1, std::atoi(e));
       shard_rank = std::getenv("HEVM_SHARD_RANK") ? std::atoi(std::getenv("HEVM_SHARD_RANK")) : 0;
       if (shard_world > 8 || shard_rank < 0 || shard_rank >= shard_world) die("HEVM_SHARD_RANK / HEVM_SHARD_WORLD out of range (at most 8 ranks)");
+      if (2 * shard_world > (int)pf.L) die("limb-sharded key storage needs at least two limbs per rank");
     }
     own_range(L, shard_rank, shard_world, own_lo, own_hi);
     P.build(logN, L, (int)pf.bits);
@@ -1519,6 +1520,7 @@ void hevmx_mulcc_shard_stage(void *h, int stage, int64_t dst, int64_t lhs, int64
 void hevmx_p2p_setup(void *h, int64_t rank, int64_t world, uint8_t *handle_out /*64 bytes*/) {
   VM *vm = V(h);
   if (world < 1 || world > 8 || rank < 0 || rank >= world) die("p2p_setup: at most 8 ranks");
+  if (world > 1 && 2 * world > vm->L) die("p2p_setup: at least two limbs per rank");
   if (vm->keys_sharded() && (vm->shard_rank != rank || vm->shard_world != world)) die("p2p_setup: rank / world differ from HEVM_SHARD_RANK / HEVM_SHARD_WORLD");
   if (!vm->keys_sharded()) { // whole keys, sharded work only: same static ownership
     vm->shard_rank = (int)rank, vm->shard_world = (int)world;

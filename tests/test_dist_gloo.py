@@ -45,6 +45,8 @@ def test_static_target_ownership():
     from dacapo_b200.sharded import static_targets
     for L in (14, 30, 7):
         for w in (1, 2, 3, 8):
+            if w > L // 2:
+                continue  # every rank owns at least two limbs (the VM refuses anything else)
             full = [static_targets(L - 1, L, g, w) for g in range(w)]
             sizes = [hi - lo for lo, hi in full]
             assert full[0][0] == 0 and full[-1][1] == L and all(full[g][1] == full[g + 1][0] for g in range(w - 1))
