@@ -265,6 +265,7 @@ struct VM {
     ln = &lanes[0];
     init_encoder();
     for (int l = 1; l <= L - 1; l++) dec_tabs(l);
+    CUDA_CHECK(cudaDeviceSynchronize()); // the table uploads / memsets above ran on the legacy stream; the lanes do not wait for it
     keygen();
     CUDA_CHECK(cudaStreamSynchronize(ln->stream));
   }
@@ -1531,6 +1532,7 @@ void hevmx_p2p_setup(void *h, int64_t rank, int64_t world, uint8_t *handle_out /
   if (!p.block) {
     p.block = dalloc<u64>(vm->p2p_words());
     CUDA_CHECK(cudaMemset(p.block, 0, vm->p2p_words() * 8));
+    CUDA_CHECK(cudaDeviceSynchronize()); // legacy-stream memset: the (non-blocking) lane streams do not wait for it
     for (auto &e : p.ev) CUDA_CHECK(cudaEventCreate(&e));
   }
   p.rank = (int)rank, p.world = (int)world, p.on = true;
@@ -1638,15 +1640,17 @@ void hevmx_key_write(void *h, int which, uint64_t elt, const uint64_t *in) {
   const size_t LN = (size_t)vm->L * vm->N, kw = (size_t)(vm->L - 1) * 2 * LN;
   cudaStream_t st = vm->ln->stream;
   CUDA_CHECK(cudaStreamSynchronize(st));
-  if (which == 0) CUDA_CHECK(cudaMemcpy(vm->d_sk, in, LN * 8, cudaMemcpyHostToDevice));
-  if (which == 1) CUDA_CHECK(cudaMemcpy(vm->d_pk, in, 2 * LN * 8, cudaMemcpyHostToDevice));
+  // every copy is ordered on the lane's own (non-blocking) stream: a legacy-stream cudaMemcpy from pageable memory may
+  // return before its DMA has landed, and nothing orders it against kernels of a non-blocking stream
+  if (which == 0) CUDA_CHECK(cudaMemcpyAsync(vm->d_sk, in, LN * 8, cudaMemcpyHostToDevice, st));
+  if (which == 1) CUDA_CHECK(cudaMemcpyAsync(vm->d_pk, in, 2 * LN * 8, cudaMemcpyHostToDevice, st));
   if (which == 2 || which == 3) {
     u64 *&dst = (which == 2) ? vm->d_relin : vm->d_gal[elt];
     if (!dst) dst = dalloc<u64>(kw);
-    CUDA_CHECK(cudaMemcpy(dst, in, kw * 8, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpyAsync(dst, in, kw * 8, cudaMemcpyHostToDevice, st));
     launch_key_split(st, dst, kw);
-    CUDA_CHECK(cudaStreamSynchronize(st));
   }
+  CUDA_CHECK(cudaStreamSynchronize(st));
 }
 // drop every Galois key (before loading a foreign key set whose rotation steps differ from the default set)
 void hevmx_galois_clear(void *h) {

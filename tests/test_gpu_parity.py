@@ -284,12 +284,14 @@ def test_seal_key_directory_round_trip(b200_lib, tmp_path_factory):
     a.encrypt_pt(0, 0, counter=7)
     ct = a.ct_read(0)
     b.ct_write(0, ct, 2.0 ** 50)
-    for vm in (a, b):
-        vm.exec(asm.ROTATE, 1, 0, 64)
-        vm.exec(asm.ROTATE, 1, 1, -2)
-        vm.exec(asm.MULCC, 2, 1, 0)
-        vm.exec(asm.RESCALE, 2, 2)
-    assert np.array_equal(a.ct_read(2), b.ct_read(2))
+    for st in steps:
+        e = b200_lib.hevmx_galois_elt(a.vm, st)
+        assert e == b200_lib.hevmx_galois_elt(b.vm, st) and np.array_equal(a.key(3, e), b.key(3, e)), ("galois key", st)
+    assert np.array_equal(a.ct_read(0), b.ct_read(0))
+    for op in ((asm.ROTATE, 1, 0, 64), (asm.ROTATE, 1, 1, -2), (asm.MULCC, 2, 1, 0), (asm.RESCALE, 2, 2, 0)):
+        for vm in (a, b):
+            vm.exec(*op)
+        assert a.ct_info(op[1]) == b.ct_info(op[1]) and np.array_equal(a.ct_read(op[1]), b.ct_read(op[1])), op
     assert np.max(np.abs(b.decrypt_decode(2, 1) - np.roll(x, -62) * x)) < 1e-4   # decrypts under the imported secret key (scale 2^100 / q ~ 2^40)
 
 
