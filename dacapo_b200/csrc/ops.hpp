@@ -14,6 +14,12 @@ struct OpsIface {
   Scratch sc;
   int shard_j0 = 0, shard_nj = 0; // ks_shard_stage(20, ...): the digit range of this call
   int key_L = 0, key_t0 = 0; // limb-sharded KEY STORAGE (this rank stores limbs [key_t0, key_t0 + key_L) of every key); 0 = whole keys
+  // warp jobs a fused inverse+forward pass-A launch should reach (see pick_groups): more groups = lower latency of a lone
+  // op but the inverse pass is recomputed per group; the VM lowers it while many independent ops are in flight
+#ifndef GROUP_TARGET_WARPS
+#define GROUP_TARGET_WARPS 1184
+#endif
+  int group_warps = GROUP_TARGET_WARPS;
   virtual ~OpsIface() {}
   // limb k is transformed under prime prime0 + (pmod ? k % pmod : k) * pstep (pmod: several polynomials of pmod limbs each)
   virtual void ntt_fwd(const u64 *src, u64 *dst, int nl, int prime0, int pstep, int pmod = 0) = 0;
@@ -84,12 +90,9 @@ template <class LA, int LOGA> struct HeOps : OpsIface {
   }
   // how many target groups the fused inverse+forward pass-A kernel is split into: enough warp jobs to
   // cover the machine (148 SMs x 8 warps) without recomputing the inverse pass more than needed
-  static int pick_groups(int nsrc, int ntargets) {
-    const int base = nsrc * TILES_A;
-#ifndef GROUP_TARGET_WARPS
-#define GROUP_TARGET_WARPS 1184
-#endif
-    int g = (GROUP_TARGET_WARPS + base - 1) / base;
+  int pick_groups(int nsrc, int ntargets, int nct = 1) const { // nct: ciphertexts sharing the launch (batched forms)
+    const int base = nsrc * TILES_A * nct;
+    int g = (group_warps + base - 1) / base;
     if (g < 1) g = 1;
     if (g > ntargets) g = ntargets;
     return g;
@@ -158,7 +161,7 @@ template <class LA, int LOGA> struct HeOps : OpsIface {
       KsFusedArgs x{};
       x.T = T, x.l = l, x.sp = sp(), x.Ltot = L, x.pitch = pitch;
       x.nct = n - done < KS_MAX_BATCH ? n - done : KS_MAX_BATCH;
-      x.ng2 = pick_groups(l, l + 1), x.ng4 = pick_groups(2, l);
+      x.ng2 = pick_groups(l, l + 1, x.nct), x.ng4 = pick_groups(2, l, x.nct);
       for (int k = 0; k < x.nct; k++) x.ct[k] = items[done + k];
       if (mode == LD_GALOIS)
         la.template ks_fused<LOGA, LD_GALOIS>(x);
@@ -171,7 +174,7 @@ template <class LA, int LOGA> struct HeOps : OpsIface {
       KsFusedArgs x{};
       x.T = T, x.l = l, x.sp = sp(), x.Ltot = L, x.pitch = dst_pitch, x.spitch = src_pitch;
       x.nct = n - done < KS_MAX_BATCH ? n - done : KS_MAX_BATCH;
-      x.ng2 = 1, x.ng4 = pick_groups(2, l - 1);
+      x.ng2 = 1, x.ng4 = pick_groups(2, l - 1, x.nct);
       for (int k = 0; k < x.nct; k++) x.ct[k] = items[done + k];
       la.template ks_fused<LOGA, FUSED_RESCALE>(x);
     }

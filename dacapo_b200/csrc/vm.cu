@@ -93,6 +93,12 @@ struct Lane {
   u64 *d_u = nullptr, *d_e = nullptr, *d_ue = nullptr, *d_tmpct = nullptr, *d_coef = nullptr;
   PtReg boot_pt;
   double load = 0; // scheduling estimate
+  // asynchronous encrypt() calls issued on this lane (C ABI): private counter word, pinned staging copy of the caller's
+  // values, completion event; `async_pending` = lane 0 has not been ordered behind that work yet (VM::join_async)
+  u64 *d_ctr = nullptr;
+  double *h_stage = nullptr;
+  cudaEvent_t ev_async = nullptr;
+  bool async_pending = false, stage_busy = false;
 };
 
 struct VM {
@@ -250,6 +256,7 @@ struct VM {
       l.ops = make_ops(l.la, dT, logN, L);
       l.ops->sc.carve(new_scratch(), L, N);
       if (keys_sharded()) l.ops->key_L = key_limbs(), l.ops->key_t0 = own_lo;
+      if (const char *e = std::getenv("HEVM_GROUP_WARPS")) l.ops->group_warps = std::max(1, std::atoi(e));
       l.d_work = dalloc<double2>(N);
       l.d_maxbits = dalloc<unsigned long long>(1);
       l.d_vals = dalloc<double>(slots);
@@ -261,7 +268,11 @@ struct VM {
       l.d_coef = dalloc<u64>((size_t)L * N);
       l.boot_pt.d = dalloc<u64>((size_t)(L - 1) * N); // never reallocated (graph capture forbids cudaMalloc)
       l.boot_pt.cap = L - 1;
+      l.d_ctr = dalloc<u64>(1);
+      CUDA_CHECK(cudaMallocHost(&l.h_stage, slots * sizeof(double)));
+      CUDA_CHECK(cudaEventCreateWithFlags(&l.ev_async, cudaEventDisableTiming));
     }
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev_front, cudaEventDisableTiming));
     ln = &lanes[0];
     init_encoder();
     for (int l = 1; l <= L - 1; l++) dec_tabs(l);
@@ -467,12 +478,13 @@ struct VM {
   // prime, add the plaintext.  Reference call sites SEAL_HEVM.cpp:333,444.
   // The sampler stream id is enc_stream(*d_ctr_base + k, which): `k` is static (position of the
   // encryption inside run()), the base lives on the device so that graph replays advance it.
-  void encrypt_pt(const PtReg &p, CtReg &out, u64 k) {
+  void encrypt_pt(const PtReg &p, CtReg &out, u64 k, const u64 *ctr_base = nullptr) {
+    if (!ctr_base) ctr_base = d_ctr_base;
     const int l = p.level, nl = l + 1;
     const u64 counter = k;
     // u, e0, e1 live back to back in d_ue ([3][nl][N]) so that one launch pair transforms all three
     u64 *u = ln->d_ue, *e01 = ln->d_ue + (size_t)nl * N;
-    launch_sample_enc(ln->stream, dT, logN, u, nl, enc_seed, enc_stream(counter, 0), d_ctr_base); // streams +0 (u), +1, +2 (e0, e1)
+    launch_sample_enc(ln->stream, dT, logN, u, nl, enc_seed, enc_stream(counter, 0), ctr_base); // streams +0 (u), +1, +2 (e0, e1)
     if (3 * nl <= L * (L - 1)) {
       ln->ops->ntt_fwd(u, u, 3 * nl, 0, 1, nl);
     } else {
@@ -485,9 +497,92 @@ struct VM {
   }
   // eager single encryption (encrypt() ABI call, hevmx hook): publish the counter, use offset 0
   void encrypt_pt_now(const PtReg &p, CtReg &out) {
-    CUDA_CHECK(cudaMemcpyAsync(d_ctr_base, &enc_counter, 8, cudaMemcpyHostToDevice, ln->stream));
-    encrypt_pt(p, out, 0);
+    // the counter word is the issuing lane's own: encrypt() calls on different lanes run concurrently
+    CUDA_CHECK(cudaMemcpyAsync(ln->d_ctr, &enc_counter, 8, cudaMemcpyHostToDevice, ln->stream));
+    encrypt_pt(p, out, 0, ln->d_ctr);
     enc_counter++;
+  }
+  // ---- asynchronous API work (encrypt() of independent arguments, decrypt_result() of all results) -----------------
+  // encrypt(i) is issued on lane i mod #lanes and returns without waiting; every other entry point first orders lane 0
+  // behind that work (join_async, called by V()).  decrypt_result() decrypts ALL result registers at its first call
+  // after a run -- one per lane, concurrently -- into pinned host memory and serves the later calls from there.
+  cudaEvent_t ev_front = nullptr; // "everything issued on lane 0 so far"
+  void join_async() {
+    for (Lane &l : lanes)
+      if (l.async_pending) {
+        CUDA_CHECK(cudaStreamWaitEvent(lanes[0].stream, l.ev_async, 0));
+        l.async_pending = false;
+      }
+    ln = &lanes[0];
+  }
+  void encrypt_async(size_t i, const double *dat, size_t len) {
+    Lane &l = lanes[i % lanes.size()];
+    const size_t n = std::min(len, N / 2);
+    if (len == 0) die("empty value vector");
+    if (l.stage_busy) CUDA_CHECK(cudaEventSynchronize(l.ev_async)); // the lane's previous encrypt still owns the staging buffer
+    std::memcpy(l.h_stage, dat, n * sizeof(double));                // the caller may reuse `dat` as soon as we return
+    if (&l != &lanes[0]) { // ordered behind whatever lane 0 was given so far (it may still read or write the register)
+      CUDA_CHECK(cudaEventRecord(ev_front, lanes[0].stream));
+      CUDA_CHECK(cudaStreamWaitEvent(l.stream, ev_front, 0));
+    }
+    ln = &l;
+    CUDA_CHECK(cudaMemcpyAsync(l.d_vals_in, l.h_stage, n * sizeof(double), cudaMemcpyHostToDevice, l.stream));
+    encode_internal(l.boot_pt, l.d_vals_in, (int)n, (int64_t)arg_level[i], (int64_t)arg_scale[i]);
+    CtReg &c = ctr(i);
+    rehome(c);
+    encrypt_pt_now(l.boot_pt, c);
+    CUDA_CHECK(cudaEventRecord(l.ev_async, l.stream));
+    l.async_pending = &l != &lanes[0];
+    l.stage_busy = true;
+    ln = &lanes[0];
+  }
+  struct ResCache {
+    bool valid = false;
+    double *d = nullptr, *h = nullptr; // [n_res][N/2] device / pinned host
+    size_t cap = 0;
+    std::vector<cudaEvent_t> ev;
+    std::vector<char> ok;
+  } res_cache;
+  void decrypt_all_results() {
+    const size_t nres = res_dst.size(), slots = N / 2;
+    ResCache &rc = res_cache;
+    if (rc.cap < nres) {
+      if (rc.d) {
+        CUDA_CHECK(cudaFree(rc.d));
+        CUDA_CHECK(cudaFreeHost(rc.h));
+      }
+      rc.d = dalloc<double>(nres * slots);
+      CUDA_CHECK(cudaMallocHost(&rc.h, nres * slots * sizeof(double)));
+      rc.cap = nres;
+      while (rc.ev.size() < nres) {
+        cudaEvent_t e;
+        CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        rc.ev.push_back(e);
+      }
+    }
+    rc.ok.assign(nres, 0);
+    CUDA_CHECK(cudaEventRecord(ev_front, lanes[0].stream));
+    for (size_t r = 0; r < nres; r++) {
+      if (res_dst[r] >= ct.size() || ct[res_dst[r]].level < 1 || !ct[res_dst[r]].d) continue; // decrypt() reports it
+      Lane &l = lanes[r % lanes.size()];
+      if (&l != &lanes[0]) CUDA_CHECK(cudaStreamWaitEvent(l.stream, ev_front, 0));
+      ln = &l;
+      decrypt_to_pt(ct[res_dst[r]], l.boot_pt);
+      decode_pt(l.boot_pt, rc.d + r * slots);
+      CUDA_CHECK(cudaMemcpyAsync(rc.h + r * slots, rc.d + r * slots, slots * sizeof(double), cudaMemcpyDeviceToHost, l.stream));
+      CUDA_CHECK(cudaEventRecord(rc.ev[r], l.stream));
+      rc.ok[r] = 1;
+    }
+    ln = &lanes[0];
+    // lane 0 must not run ahead of the readers (a later run() or encrypt() overwrites the registers): wait for the last
+    // event of every other lane that was given work
+    for (size_t k = 1; k < lanes.size(); k++) {
+      long last = -1;
+      for (size_t r = k; r < nres; r += lanes.size())
+        if (rc.ok[r]) last = (long)r;
+      if (last >= 0) CUDA_CHECK(cudaStreamWaitEvent(lanes[0].stream, rc.ev[(size_t)last], 0));
+    }
+    rc.valid = true;
   }
   void decrypt_to_pt(const CtReg &c, PtReg &p) {
     pt_reserve(p, c.level);
@@ -841,7 +936,23 @@ struct VM {
     if (r < home.size()) c.d = home[r];
   }
   // issue every op of the program over the lanes with event dependencies
+  // While a whole program is scheduled over the lanes the machine is shared by many independent ops, so the fused pass-A
+  // launches are cut into as few target groups as possible (every extra group recomputes the inverse pass: measured
+  // +10 % ops/s on the op microbench, -4 % ResNet-20 latency against the single-op setting); a lone op issued through
+  // hevmx_exec keeps the latency-oriented split.  HEVM_GROUP_WARPS_RUN overrides.
+  struct GroupWarpsScope {
+    VM &vm;
+    std::vector<int> saved;
+    explicit GroupWarpsScope(VM &v) : vm(v) {
+      static const int run_warps = std::getenv("HEVM_GROUP_WARPS_RUN") ? std::max(1, std::atoi(std::getenv("HEVM_GROUP_WARPS_RUN"))) : 148;
+      for (Lane &l : vm.lanes) saved.push_back(l.ops->group_warps), l.ops->group_warps = std::min(l.ops->group_warps, run_warps);
+    }
+    ~GroupWarpsScope() {
+      for (size_t i = 0; i < vm.lanes.size(); i++) vm.lanes[i].ops->group_warps = saved[i];
+    }
+  };
   void issue_scheduled() {
+    GroupWarpsScope group_scope(*this);
     const int nl = (int)lanes.size();
     struct BufState { // dependency state of one PHYSICAL buffer
       cudaEvent_t wr = nullptr;
@@ -1149,7 +1260,9 @@ struct VM {
         entry_meta.resize(ct.size());
         for (size_t r = 0; r < ct.size(); r++) entry_meta[r] = {ct[r].level, ct[r].scale};
         cudaGraph_t g = nullptr;
-        g_pdl_suspended = true;
+        // HEVM_GRAPH_PDL=1: keep programmatic dependent launch while capturing (programmatic edges inside the graph)
+        static const bool graph_pdl = std::getenv("HEVM_GRAPH_PDL") && std::atoi(std::getenv("HEVM_GRAPH_PDL")) != 0;
+        g_pdl_suspended = !graph_pdl;
         const unsigned long long c0 = g_launch_count;
         CUDA_CHECK(cudaStreamBeginCapture(lanes[0].stream, cudaStreamCaptureModeRelaxed));
         issue_scheduled();
@@ -1175,7 +1288,15 @@ struct VM {
   }
 };
 
-VM *V(void *h) { return static_cast<VM *>(h); }
+// Every entry point that touches VM state goes through V(): lane 0 is ordered behind the asynchronous encrypt() calls
+// and the cached results of decrypt_result() are dropped.  Vq() = pure queries / the decrypt_result path itself.
+VM *Vq(void *h) { return static_cast<VM *>(h); }
+VM *V(void *h) {
+  VM *vm = static_cast<VM *>(h);
+  vm->join_async();
+  vm->res_cache.valid = false;
+  return vm;
+}
 
 void read_params(const char *dir, ParamFile &pf) {
   std::ifstream f(std::string(dir) + "/hevm_params.bin", std::ios::binary);
@@ -1266,13 +1387,13 @@ void preprocess(void *h) { // SEAL_HEVM.cpp:242-254: encode every opcode-0 const
   CUDA_CHECK(cudaStreamSynchronize(vm->ln->stream));
 }
 void encrypt(void *h, int64_t i, double *dat, int len) {
-  VM *vm = V(h);
+  // SEAL_HEVM.cpp:436-446.  Asynchronous: the values are copied to a pinned staging buffer, encode + encrypt are issued on
+  // lane i mod #lanes (independent arguments overlap) and the call returns; run() / decrypt() / every other entry point
+  // is ordered behind it.
+  VM *vm = Vq(h);
+  vm->res_cache.valid = false;
   if ((size_t)i >= vm->arg_level.size()) die("encrypt: argument index out of range");
-  vm->stage_host_values(dat, (size_t)len);
-  vm->encode_internal(vm->ln->boot_pt, vm->ln->d_vals_in, (int)std::min((size_t)len, vm->N / 2), (int64_t)vm->arg_level[i], (int64_t)vm->arg_scale[i]);
-  vm->rehome(vm->ctr((size_t)i));
-  vm->encrypt_pt_now(vm->ln->boot_pt, vm->ctr((size_t)i));
-  CUDA_CHECK(cudaStreamSynchronize(vm->ln->stream));
+  vm->encrypt_async((size_t)i, dat, (size_t)len);
 }
 void decrypt(void *h, int64_t i, double *dat) {
   VM *vm = V(h);
@@ -1283,15 +1404,25 @@ void decrypt(void *h, int64_t i, double *dat) {
   CUDA_CHECK(cudaMemcpyAsync(dat, vm->ln->d_vals, (vm->N / 2) * sizeof(double), cudaMemcpyDeviceToHost, vm->ln->stream));
   CUDA_CHECK(cudaStreamSynchronize(vm->ln->stream));
 }
-void decrypt_result(void *h, int64_t i, double *dat) { decrypt(h, (int64_t)V(h)->res_dst.at((size_t)i), dat); }
-int64_t getResIdx(void *h, int64_t i) { return (int64_t)V(h)->res_dst.at((size_t)i); }
+void decrypt_result(void *h, int64_t i, double *dat) { // SEAL_HEVM.cpp:459-461
+  VM *vm = Vq(h);
+  vm->join_async();
+  if (!vm->res_cache.valid) vm->decrypt_all_results(); // all results at once, one per lane; later calls only copy
+  if ((size_t)i >= vm->res_dst.size() || !vm->res_cache.ok[(size_t)i]) {
+    decrypt(h, (int64_t)vm->res_dst.at((size_t)i), dat); // reports the error
+    return;
+  }
+  CUDA_CHECK(cudaEventSynchronize(vm->res_cache.ev[(size_t)i]));
+  std::memcpy(dat, vm->res_cache.h + (size_t)i * (vm->N / 2), (vm->N / 2) * sizeof(double));
+}
+int64_t getResIdx(void *h, int64_t i) { return (int64_t)Vq(h)->res_dst.at((size_t)i); }
 void *getCtxt(void *h, int64_t id) { return &V(h)->ctr((size_t)id); }
 void run(void *h) { // SEAL_HEVM.cpp:336-401; returns only when the results are complete
   VM *vm = V(h);
   vm->run_program();
 }
-int64_t getArgLen(void *h) { return (int64_t)V(h)->head.n_args; }
-int64_t getResLen(void *h) { return (int64_t)V(h)->head.n_res; }
+int64_t getArgLen(void *h) { return (int64_t)Vq(h)->head.n_args; }
+int64_t getResLen(void *h) { return (int64_t)Vq(h)->head.n_res; }
 void setDebug(void *h, bool e) { V(h)->debug = e; }
 void setToGPU(void *, bool) {} // always resident on the GPU
 void printMem(void *h) {

@@ -404,6 +404,61 @@ def test_program_through_c_abi(pair, tmp_path):
         vm.lib.hevmx_resize(vm.vm, 8, 4)
 
 
+def test_async_encrypt_and_batched_results_bit_exact(pair, tmp_path):
+    """encrypt() is asynchronous on the GPU (argument i goes to lane i mod #lanes, vm.cu `encrypt_async`) and
+    decrypt_result() decrypts all results at its first call (`decrypt_all_results`): 20 arguments (more than lanes) and
+    20 results, two rounds with re-encrypted arguments in between (the cached results must be dropped), an argument
+    encrypted twice in a row, and a plain decrypt() in the middle -- ciphertexts and decoded values equal the oracle's."""
+    g, o = pair
+    nargs = 20
+    p = asm.Program(init_level=13)
+    xs = [p.arg(40, 2 + (i % 3)) for i in range(nargs)]
+    outs = [p.new_ct() for _ in range(nargs)]
+    for i in range(nargs):
+        p.emit(asm.ADDCC, outs[i], xs[i], xs[i])
+        p.result(outs[i], 40, 2 + (i % 3))
+    cst, hv = tmp_path / "a.cst", tmp_path / "a.hevm"
+    p.save(cst, hv)
+    n = o.N // 2
+    f64p = C.POINTER(C.c_double)
+    got = []
+    for vm in pair:
+        lib, rng = vm.lib, np.random.default_rng(21)
+        lib.load(vm.vm, str(cst).encode(), str(hv).encode())
+        lib.preprocess(vm.vm)
+        lib.hevmx_set_enc_counter(vm.vm, 1000)
+        rounds = []
+        for rnd in range(2):
+            vals = rng.uniform(-1, 1, (nargs, n))
+            buf = np.empty(n)
+            for i in range(nargs):
+                buf[:] = vals[i]
+                lib.encrypt(vm.vm, i, buf.ctypes.data_as(f64p), n)  # the caller's buffer is reused at once
+            if rnd == 1:  # argument 3 again, with other values: the second encryption wins
+                vals[3] = rng.uniform(-1, 1, n)
+                buf[:] = vals[3]
+                lib.encrypt(vm.vm, 3, buf.ctypes.data_as(f64p), n)
+            buf[:] = 7.0
+            lib.run(vm.vm)
+            res = np.zeros((nargs, n))
+            for i in range(nargs):
+                lib.decrypt_result(vm.vm, i, res[i].ctypes.data_as(f64p))
+                if i == 5:  # any other entry point in between drops the cached results; the answers do not change
+                    one = np.zeros(n)
+                    lib.decrypt(vm.vm, lib.getResIdx(vm.vm, 0), one.ctypes.data_as(f64p))
+                    assert np.array_equal(one, res[0])
+            cts = [vm.ct_read(lib.getResIdx(vm.vm, i)) for i in (0, 3, 17, 19)]
+            assert np.max(np.abs(res - 2 * vals)) < 1e-6
+            rounds.append((res, cts))
+        got.append(rounds)
+    for rnd in range(2):
+        assert np.array_equal(got[0][rnd][0], got[1][rnd][0])
+        for a, b in zip(got[0][rnd][1], got[1][rnd][1]):
+            assert np.array_equal(a, b)
+    for vm in pair:
+        vm.lib.hevmx_resize(vm.vm, 8, 4)
+
+
 def test_fused_mulcp_addcc_bit_exact(pair, tmp_path):
     """The scheduler fuses `mulcp t; addcc d <- t + y` (t dead afterwards) into one kernel: every aliasing form, plus the
     forms that must NOT be fused (t read again later), against the oracle's sequential interpreter."""
