@@ -87,18 +87,18 @@ struct HostParams {
   size_t N = 0;
   std::vector<u64> q, psi;
   std::vector<Tw> tw, itw; // [L][N]
-  // pass-B copies: twB[prime][row][256] holds the 255 twiddles row `row` needs, contiguous and in the order the warp
-  // kernels stage them (entry 2^k - 1 + g  <-  tw[(rows << k) + (row << k) + g], k < 8, g < 2^k; entry 255 unused)
+  // pass-B copies: twB[prime][row][TWB_ROW] holds the 255 twiddles row `row` needs, contiguous and in the (bank-conflict
+  // free, padded) order the warp kernels stage them (entry twB_pos(k, g)  <-  tw[(rows << k) + (row << k) + g], k < 8, g < 2^k)
   std::vector<Tw> twB, itwB;
   void build_rowwise() {
     const size_t rows = N >> 8;
-    twB.assign((size_t)L * N, Tw{0, 0});
-    itwB.assign((size_t)L * N, Tw{0, 0});
+    twB.assign((size_t)L * rows * TWB_ROW, Tw{0, 0});
+    itwB.assign((size_t)L * rows * TWB_ROW, Tw{0, 0});
     for (int i = 0; i < L; i++)
       for (size_t r = 0; r < rows; r++)
         for (int k = 0; k < 8; k++)
           for (size_t g = 0; g < ((size_t)1 << k); g++) {
-            const size_t dst = (size_t)i * N + r * 256 + (((size_t)1 << k) - 1) + g, src = (size_t)i * N + (rows << k) + (r << k) + g;
+            const size_t dst = ((size_t)i * rows + r) * TWB_ROW + (size_t)twB_pos(k, (int)g), src = (size_t)i * N + (rows << k) + (r << k) + g;
             twB[dst] = tw[src];
             itwB[dst] = itw[src];
           }

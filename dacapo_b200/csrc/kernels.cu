@@ -111,7 +111,7 @@ template <int LOGA> __global__ void __launch_bounds__(MAC_WARPS * 32, MAC_MIN_CT
     __syncthreads();
     // the two tail warps each stage the row's inverse twiddles into a table of their own (warp 1: the CTA's table, warp 0:
     // the free words behind the two accumulator rows kept in `tiles`), so nothing is written or read across warps
-    if (warp < 2) body_mac_tail<LOGA>(a, job, warp, st, rowbufs + warp * 2 * MAC_ROW_WORDS, warp ? tw_s : reinterpret_cast<Tw *>(tiles + 512), tiles);
+    if (warp < 2) body_mac_tail<LOGA>(a, job, warp, st, mac_tail_tile(rowbufs, warp), mac_tail_tw(tiles, tw_s, warp), tiles);
   }
 }
 
@@ -201,7 +201,7 @@ template <int LOGA, int MODE> __global__ void __launch_bounds__(CTA_THREADS, 4) 
         body_mac_dot<LOGA>(a, un.u, threadIdx.x, xbuf, tiles);
         if (mac_Iidx<LOGA>(a, un.u) == a.l) {
           __syncthreads();
-          if (warp < 2) body_mac_tail<LOGA>(a, un.u, warp, st, rowbufs + warp * 2 * MAC_ROW_WORDS, warp ? tw_s : reinterpret_cast<Tw *>(tiles + 512), tiles);
+          if (warp < 2) body_mac_tail<LOGA>(a, un.u, warp, st, mac_tail_tile(rowbufs, warp), mac_tail_tw(tiles, tw_s, warp), tiles);
         }
         break;
       }

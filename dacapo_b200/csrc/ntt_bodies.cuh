@@ -25,10 +25,22 @@ enum { EPI_CANON = 0, EPI_MAC = 1, EPI_MODDOWN_GALOIS = 2, EPI_MODDOWN_RELIN = 3
 #define MAC_WARPS 4
 // shared memory of one MAC CTA (words): staged twiddles | MAC_WARPS NTT tiles | MAC_WARPS staged rows | l transformed digit rows
 #define TILE_B_WORDS 272 // 256 values + 256/16 padding
-#define MAC_TW_WORDS 512  // 256 staged twiddles
+#define MAC_TW_WORDS (2 * TWB_ROW) // the staged (padded) twiddle row
 #define MAC_ROW_WORDS 256 // per warp: staged pass-A row of the next digit
 #define MAC_FIXED_WORDS (MAC_TW_WORDS + MAC_WARPS * TILE_B_WORDS + MAC_WARPS * MAC_ROW_WORDS)
-HD size_t mac_smem_words(int l) { return MAC_FIXED_WORDS + (size_t)256 * l; }
+// transformed digit rows: 256 values + two unused words after every 16 (the 64-byte lane stride of the layout-C
+// stores would otherwise put four lanes of a quarter-warp on the same banks; 16-byte alignment is kept)
+#define MAC_XROW 288
+HD int xpad(int i) { return i + ((i >> 4) << 1); }
+HD size_t mac_smem_words(int l) { return MAC_FIXED_WORDS + (size_t)MAC_XROW * l; }
+// special-prime CTAs, phase 3 (after the last CTA barrier everything but the two accumulator rows in tiles[0, 512) is
+// dead): warp K transforms row K with a twiddle table and an exchange tile of its own --
+//   K = 1: the CTA's table, tile rowbufs[512, 784);  K = 0: table tiles[512, 512 + 2 TWB_ROW) (runs 64 words into
+//   rowbufs), tile rowbufs[64, 336)
+HD u64 *mac_tail_tile(u64 *rowbufs, int K) { return rowbufs + (K ? 512 : 64); }
+HD Tw *mac_tail_tw(u64 *tiles, Tw *tw_s, int K) { return K ? tw_s : reinterpret_cast<Tw *>(tiles + 512); }
+static_assert(512 + 2 * TWB_ROW <= MAC_WARPS * TILE_B_WORDS + 64, "tail table of warp 0 overlaps its tile");
+static_assert(64 + TILE_B_WORDS <= 512 && 512 + TILE_B_WORDS <= MAC_WARPS * MAC_ROW_WORDS, "tail tiles do not fit the row buffers");
 // radix-2^30 split of a value < 2^60 + 2^36: low 30 bits in the low word, the rest in the high word.  Key-switch keys
 // are stored this way, and the transformed digits are converted to it, so that the key inner product is four
 // 32x32->64 multiply-adds per term into four 64-bit column accumulators with no carries at all
@@ -81,7 +93,7 @@ template <int LOGA, int LD> HD void body_intt_B(const ArgsInttB &a, int job, Lan
   LANE_DECL;
   FOR_LANES(S, st, {
     grid_dep_launch();
-    stage_tw_B<LOGA>(tw, T.itwB + (size_t)p * N, r, lane);
+    stage_tw_B<LOGA>(tw, T.itwB + (size_t)p * twB_prime_stride(N), r, lane);
     grid_dep_wait();
     const int base = r * 256 + lane * 8;
     if (LD == LD_PLAIN) {
@@ -351,7 +363,7 @@ template <int LOGA> HD void body_mac_stage(const ArgsFwdB &a, int job, int tid, 
   const int N = 1 << T.logN;
   const int r = job & (Geo<LOGA>::ROWS - 1), Iidx = mac_Iidx<LOGA>(a, job), I = (Iidx == a.l) ? a.sp : Iidx;
   grid_dep_launch();
-  stage_tw_B<LOGA>(tw_s, T.twB + (size_t)I * N, r, tid, MAC_WARPS * 32);
+  stage_tw_B<LOGA>(tw_s, T.twB + (size_t)I * twB_prime_stride(N), r, tid, MAC_WARPS * 32);
   grid_dep_wait();
   cp_async_wait();
 }
@@ -413,10 +425,11 @@ template <int LOGA> HD void body_mac_warp(const ArgsFwdB &a, int job, int w, Lan
     }
     if (p + MAC_WARPS < a.l) stage(digit_of(p + MAC_WARPS)); // every lane has drained rowbuf
     if (J != I) warp_fwdB8_regs(st, tile, tw_s, m);
-    u64 *xo = xbuf + (size_t)J * 256;
+    u64 *xo = xbuf + (size_t)J * MAC_XROW;
     FOR_LANES(S, st, {
+      u64 *xl = xo + xpad(lane * 8); // 8 consecutive words (four 16-byte stores): the pad never splits them
       _Pragma("unroll")
-      for (int e = 0; e < 8; e++) xo[lane * 8 + e] = split30(fold60(S.x[e], m.delta));
+      for (int e = 0; e < 8; e++) xl[e] = split30(fold60(S.x[e], m.delta));
     });
   }
 }
@@ -500,7 +513,7 @@ template <int LOGA> HD void body_mac_dot(const ArgsFwdB &a, int job, int tid, co
       for (int j = 0; j < 2; j++) c[K][j][0] = c[K][j][1] = c[K][j][2] = c[K][j][3] = 0;
     // running pointers: key rows of digit J (kq: poly 0, kq + kstride: poly 1) and its x row
     const u64 *kq = kp + (size_t)Jb * dstride;
-    const u64 *xq = xbuf + (size_t)Jb * 256 + 2 * tid;
+    const u64 *xq = xbuf + (size_t)Jb * MAC_XROW + xpad(2 * tid);
     int J = Jb;
     for (; J + MAC_KEY_BATCH <= Je; J += MAC_KEY_BATCH) { // full batches: the key rows of MAC_KEY_BATCH digits in flight
       U2 k[MAC_KEY_BATCH][2];
@@ -512,13 +525,13 @@ template <int LOGA> HD void body_mac_dot(const ArgsFwdB &a, int job, int tid, co
       }
       _Pragma("unroll")
       for (int b = 0; b < MAC_KEY_BATCH; b++) {
-        const u64 xa = xq[b * 256], xb = xq[b * 256 + 1];
+        const u64 xa = xq[b * MAC_XROW], xb = xq[b * MAC_XROW + 1];
         mac30(c[0][0], xa, k[b][0].a);
         mac30(c[0][1], xb, k[b][0].b);
         mac30(c[1][0], xa, k[b][1].a);
         mac30(c[1][1], xb, k[b][1].b);
       }
-      xq += MAC_KEY_BATCH * 256;
+      xq += MAC_KEY_BATCH * MAC_XROW;
     }
     for (; J < Je; J++) { // remaining digits one by one
       const U2 k0 = ldg_key2(kq), k1 = ldg_key2(kq + kstride);
@@ -528,7 +541,7 @@ template <int LOGA> HD void body_mac_dot(const ArgsFwdB &a, int job, int tid, co
       mac30(c[1][0], xa, k1.a);
       mac30(c[1][1], xb, k1.b);
       kq += dstride;
-      xq += 256;
+      xq += MAC_XROW;
     }
     _Pragma("unroll")
     for (int K = 0; K < 2; K++)
@@ -555,7 +568,7 @@ template <int LOGA> HD void body_mac_tail(const ArgsFwdB &a, int job, int K, Lan
   const ModQ m = T.mod[a.sp];
   LANE_DECL;
   FOR_LANES(S, st, {
-    stage_tw_B<LOGA>(tw_s, T.itwB + (size_t)a.sp * N, r, lane); // `tw_s` is private to this warp (see the callers)
+    stage_tw_B<LOGA>(tw_s, T.itwB + (size_t)a.sp * twB_prime_stride(N), r, lane); // `tw_s` is private to this warp (see the callers)
     _Pragma("unroll")
     for (int e = 0; e < 8; e++) S.x[e] = rows[K * 256 + lane * 8 + e];
     cp_async_wait();
@@ -580,7 +593,7 @@ template <int LOGA, int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, Lane
     const u64 *src = a.src + (size_t)d * N + r * 256;
     FOR_LANES(S, st, {
       grid_dep_launch();
-      stage_tw_B<LOGA>(tw, T.twB + (size_t)p * N, r, lane);
+      stage_tw_B<LOGA>(tw, T.twB + (size_t)p * twB_prime_stride(N), r, lane);
       grid_dep_wait();
       _Pragma("unroll")
       for (int e = 0; e < 8; e++) S.x[e] = ldg_stream(src + idxH(lane, e));
@@ -609,7 +622,7 @@ template <int LOGA, int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, Lane
       FOR_LANES(S, st, {
         if (K == 0) {
           grid_dep_launch();
-          stage_tw_B<LOGA>(tw, T.twB + (size_t)i * N, r, lane);
+          stage_tw_B<LOGA>(tw, T.twB + (size_t)i * twB_prime_stride(N), r, lane);
           grid_dep_wait();
         }
         if (K == 1) {
@@ -657,7 +670,7 @@ template <int LOGA, int EPI> HD void body_fwd_B(const ArgsFwdB &a, int job, Lane
     const u64 *src = a.src + ((size_t)K * a.l + i) * N + r * 256;
     FOR_LANES(S, st, {
       grid_dep_launch();
-      stage_tw_B<LOGA>(tw, T.twB + (size_t)i * N, r, lane);
+      stage_tw_B<LOGA>(tw, T.twB + (size_t)i * twB_prime_stride(N), r, lane);
       grid_dep_wait();
       _Pragma("unroll")
       for (int e = 0; e < 8; e++) S.x[e] = ldg_stream(src + idxH(lane, e));

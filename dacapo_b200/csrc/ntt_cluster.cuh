@@ -17,7 +17,8 @@
 #define NC_TILE_WORDS 512                 // one dense TMA tile: 128 rows x 4 columns
 // shared memory (words): rows[16][264] | per warp: TMA box 512 = exchange tile 544 (aliased: the box is in registers before
 // the exchange tile is written, the next box is requested after it was read) | twiddles 2 x 256 | mbarrier 2
-#define NC_WARP_WORDS (WARP_TILE_WORDS + 512 + 16) // multiple of 16 words: every TMA box stays 128-byte aligned
+#define NC_TW_WORDS (2 * TWB_ROW)          // staged (padded) pass-B twiddle row; the pass-A table (128 entries) uses the same words
+#define NC_WARP_WORDS (WARP_TILE_WORDS + NC_TW_WORDS + 16) // multiple of 16 words: every TMA box stays 128-byte aligned
 #define NC_SMEM_WORDS (NC_ROWS_PER_CTA * NC_ROWPITCH + NC_WARPS * NC_WARP_WORDS)
 
 __device__ __forceinline__ void nc_mbar_init(u64 *bar) {
@@ -57,7 +58,7 @@ __global__ void __cluster_dims__(NC_CLUSTER, 1, 1) __launch_bounds__(NC_WARPS * 
   u64 *wbase = nc_smem + NC_ROWS_PER_CTA * NC_ROWPITCH + warp * NC_WARP_WORDS;
   u64 *tile = wbase, *xch = wbase;
   Tw *tw = reinterpret_cast<Tw *>(xch + WARP_TILE_WORDS);
-  u64 *bar = wbase + WARP_TILE_WORDS + 512;
+  u64 *bar = wbase + WARP_TILE_WORDS + NC_TW_WORDS;
   // ---- pass A: tiles crank*8 + warp*2 + k ------------------------------------------------------------------------
   if (lane == 0) {
     nc_mbar_init(bar);
@@ -102,7 +103,7 @@ __global__ void __cluster_dims__(NC_CLUSTER, 1, 1) __launch_bounds__(NC_WARPS * 
   LaneB8 st[1];
   for (int k = 0; k < 4; k++) {
     const int lrow = warp * 4 + k, r = crank * NC_ROWS_PER_CTA + lrow;
-    stage_tw_B<LOGA>(tw, T->twB + (size_t)p * N, r, lane);
+    stage_tw_B<LOGA>(tw, T->twB + (size_t)p * twB_prime_stride(N), r, lane);
 #pragma unroll
     for (int e = 0; e < 8; e++) st[0].x[e] = rows[lrow * NC_ROWPITCH + idxH(lane, e)];
     cp_async_wait();

@@ -28,11 +28,19 @@
 
 #define HEVM_MAXL 32
 
+// Row-wise pass-B twiddle table: the 255 twiddles of one 256-point row, local stage k (2^k groups), group g.
+// Stages 0..5 sit at 2^k - 1 + g.  In the last two stages every lane reads its own 2 / 4 consecutive entries (layout C:
+// g = 2 lane + j / 4 lane + j), i.e. 32- / 64-byte lane strides that put 2 / 4 lanes of a quarter-warp on the same banks
+// (LDS.128); one unused entry after every 2 / 4 entries makes the lane stride 48 / 80 bytes = conflict-free.
+#define TWB_ROW 320 // entries per row (319 used)
+HD constexpr int twB_pos(int k, int g) { return k < 6 ? (1 << k) - 1 + g : k == 6 ? 63 + g + (g >> 1) : 159 + g + (g >> 2); }
+HD size_t twB_prime_stride(size_t N) { return (N >> 8) * TWB_ROW; }
+
 struct NttTables {
   int logN, L;
   const Tw *tw;  // [L][N]  forward twiddles, tw[m+i] for stage with m groups, group i
   const Tw *itw; // [L][N]  inverses of the above
-  const Tw *twB, *itwB; // [L][rows][256] the same values regrouped per pass-B row (host_params.hpp build_rowwise)
+  const Tw *twB, *itwB; // [L][rows][TWB_ROW] the same values regrouped per pass-B row (host_params.hpp build_rowwise)
   ModQ mod[HEVM_MAXL];
   Tw invn[HEVM_MAXL];           // N^-1
   Tw invn_w[HEVM_MAXL];         // N^-1 * itw[1]
@@ -129,7 +137,7 @@ template <int LOGA> struct Geo {
   // staged twiddles per warp: pass B 255; fused inverse+forward pass A: ROWS + 2 x ROWS (the forward table is
   // double-buffered up to 256 rows; at 512 rows it is single-buffered to keep two CTAs per SM)
   static constexpr bool TW_DOUBLE = LOGA <= 8;
-  static constexpr int TW = (TW_DOUBLE ? 3 : 2) * ROWS > 256 ? (TW_DOUBLE ? 3 : 2) * ROWS : 256;
+  static constexpr int TW = (TW_DOUBLE ? 3 : 2) * ROWS > TWB_ROW ? (TW_DOUBLE ? 3 : 2) * ROWS : TWB_ROW;
   static constexpr int WARP_WORDS = WARP_TILE_WORDS + 2 * TW;
 };
 
@@ -139,14 +147,14 @@ template <int LOGA> HD void stage_tw_A(Tw *dst, const Tw *table, int lane) {
   _Pragma("unroll")
   for (int i = 0; i < Geo<LOGA>::ROWS / 32; i++) cp_async16(dst + lane + 32 * i, table + lane + 32 * i);
 }
-// pass B, row r: local entry (2^k - 1 + g) = table[(ROWS << k) + (r << k) + g],  k < 8, g < 2^k.
+// pass B, row r: local entry twB_pos(k, g) = table[(ROWS << k) + (r << k) + g],  k < 8, g < 2^k.
 // `tid`/`nthr`: the threads sharing the copy.
-// `tableB` = the prime's row-wise copy (NttTables::twB / itwB): one contiguous 4 KB block per row, eight 16-byte
-// cp.async per lane with immediate offsets
+// `tableB` = the prime's row-wise copy (NttTables::twB / itwB): one contiguous 5 KB block per row, already in the padded
+// order, ten 16-byte cp.async per lane with immediate offsets
 template <int LOGA> HD void stage_tw_B(Tw *dst, const Tw *tableB, int r, int tid, int nthr = 32) {
-  const Tw *src = tableB + ((size_t)r << 8);
+  const Tw *src = tableB + (size_t)r * TWB_ROW;
   _Pragma("unroll")
-  for (int g = tid; g < 256; g += nthr) cp_async16(dst + g, src + g);
+  for (int g = tid; g < TWB_ROW; g += nthr) cp_async16(dst + g, src + g);
 }
 
 // =====================================================================================
@@ -259,7 +267,7 @@ HD void invA_stages_R(u64 (&x)[16], const Tw *itw, u64 q, u64 q2, u64 dl, Tw inv
 //   layout C ("consecutive"):            x[e] <-> idx = lane*8 + e
 // forward: stages k=0..2 in H (distance 128,64,32), k=3..5 in M (16,8,4), k=6,7 in C (2,1)
 // inverse: gaps 1,2 in C; 4,8,16 in M; 32,64,128 in H
-// `tw` points at the staged row table: entry (2^k - 1 + g) = twiddle of local stage k, local group g.
+// `tw` points at the staged row table: entry twB_pos(k, g) = twiddle of local stage k, local group g.
 // =====================================================================================
 HD int idxH(int lane, int e) { return e * 32 + lane; }
 HD int idxM8(int lane, int e) { return ((((lane >> 2) & 3) * 2 + (lane >> 4)) << 5) + e * 4 + (lane & 3); }
@@ -271,7 +279,7 @@ HD void fwdB8_stages_H(u64 (&x)[8], const Tw *tw, u64 q, u64 q2) { // in < 2q, o
     const int half = 4 >> k;
     Tw t[4];
     _Pragma("unroll")
-    for (int g = 0; g < (1 << k); g++) t[g] = ldtw(tw + ((1 << k) - 1) + g);
+    for (int g = 0; g < (1 << k); g++) t[g] = ldtw(tw + twB_pos(k, g));
     _Pragma("unroll")
     for (int e = 0; e < 8; e++)
       if (!(e & half)) ct_bfly_lazy(x[e], x[e + half], t[e >> (3 - k)], q, q2);
@@ -285,7 +293,7 @@ HD void fwdB8_stages_M(u64 (&x)[8], int lane, const Tw *tw, u64 q, u64 q2) { // 
     _Pragma("unroll")
     for (int e = 0; e < 8; e++)
       if (!(e & half)) {
-        Tw t = ldtw(tw + ((1 << k) - 1) + ((base + e * 4) >> (8 - k)));
+        Tw t = ldtw(tw + twB_pos(k, (base + e * 4) >> (8 - k)));
         ct_bfly_lazy(x[e], x[e + half], t, q, q2);
       }
   }
@@ -298,7 +306,7 @@ HD void fwdB8_stages_C(u64 (&x)[8], int lane, const Tw *tw, u64 q, u64 q2) { // 
     _Pragma("unroll")
     for (int e = 0; e < 8; e++)
       if (!(e & half)) {
-        Tw t = ldtw(tw + ((1 << k) - 1) + ((base + e) >> (8 - k)));
+        Tw t = ldtw(tw + twB_pos(k, (base + e) >> (8 - k)));
         ct_bfly_lazy(x[e], x[e + half], t, q, q2);
       }
   }
@@ -312,7 +320,7 @@ HD void invB8_stages_C(u64 (&x)[8], int lane, const Tw *itw, u64 q, u64 q2, u64 
     _Pragma("unroll")
     for (int e = 0; e < 8; e++)
       if (!(e & half)) {
-        Tw t = ldtw(itw + (ml - 1) + ((base + e) >> (j + 1)));
+        Tw t = ldtw(itw + twB_pos(7 - j, (base + e) >> (j + 1)));
         gs_bfly_fold(x[e], x[e + half], t, q, q2, dl);
       }
   }
@@ -325,7 +333,7 @@ HD void invB8_stages_M(u64 (&x)[8], int lane, const Tw *itw, u64 q, u64 q2, u64 
     _Pragma("unroll")
     for (int e = 0; e < 8; e++)
       if (!(e & half)) {
-        Tw t = ldtw(itw + (ml - 1) + ((base + e * 4) >> (j + 1)));
+        Tw t = ldtw(itw + twB_pos(7 - j, (base + e * 4) >> (j + 1)));
         gs_bfly_fold(x[e], x[e + half], t, q, q2, dl);
       }
   }
@@ -336,7 +344,7 @@ HD void invB8_stages_H(u64 (&x)[8], const Tw *itw, u64 q, u64 q2, u64 dl) {
     const int half = 1 << (j - 5), ml = 128 >> j;
     Tw t[4];
     _Pragma("unroll")
-    for (int g = 0; g < ml; g++) t[g] = ldtw(itw + (ml - 1) + g);
+    for (int g = 0; g < ml; g++) t[g] = ldtw(itw + twB_pos(7 - j, g));
     _Pragma("unroll")
     for (int e = 0; e < 8; e++)
       if (!(e & half)) gs_bfly_fold(x[e], x[e + half], t[e >> (j - 4)], q, q2, dl);

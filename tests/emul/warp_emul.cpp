@@ -114,7 +114,7 @@ struct EmuLauncher {
       if (mac_Iidx<LOGA>(a, j) == a.l)
         for (int K = 0; K < 2; K++) {
           LaneB8 st[32];
-          body_mac_tail<LOGA>(a, j, K, st, rowbufs + K * 2 * MAC_ROW_WORDS, K ? tw_s : reinterpret_cast<Tw *>(tiles + 512), tiles);
+          body_mac_tail<LOGA>(a, j, K, st, mac_tail_tile(rowbufs, K), mac_tail_tw(tiles, tw_s, K), tiles);
         }
     }
   }
