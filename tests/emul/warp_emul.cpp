@@ -203,6 +203,8 @@ void emul_keyswitch_sharded_split(void *h, int mode, const u64 *a, const u64 *b,
     }
 }
 void emul_set_fused(void *h, int on) { ((Emu *)h)->la.use_fused = on != 0; }
+// warp-job target of the fused pass-A launches (OpsIface::group_warps): 1 184 = lone op, 148 = scheduled program
+void emul_set_group_warps(void *h, int w) { ((Emu *)h)->ops->group_warps = w; }
 long emul_waits_checked(void *h) { return ((Emu *)h)->la.waits_checked; }
 // batched single-launch key switch: n ciphertexts (compact [2][l][N] each, contiguous), one scratch area per ciphertext
 void emul_keyswitch_batch(void *h, int mode, int n, const u64 *a, const u64 *b, u64 *dst, int l, const u64 *key, const u32 *elts) {

@@ -37,6 +37,7 @@ def emul(LOGN):
     lib.emul_keyswitch_sharded.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p, C.c_int, u64p, C.c_uint32, C.c_int]
     lib.emul_keyswitch_sharded_split.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p, C.c_int, u64p, C.c_uint32, C.c_int]
     lib.emul_set_fused.argtypes = [C.c_void_p, C.c_int]
+    lib.emul_set_group_warps.argtypes = [C.c_void_p, C.c_int]
     lib.emul_waits_checked.argtypes = [C.c_void_p]
     lib.emul_waits_checked.restype = C.c_long
     lib.emul_keyswitch_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, u64p, u64p, u64p, C.c_int, u64p, C.POINTER(C.c_uint32)]
@@ -120,6 +121,35 @@ def test_rotate_kernels_vs_oracle(emul, vm, step):
     got = a.copy()  # in place
     lib.emul_keyswitch(h, 1, _p(got), None, _p(got), lvl, _p(key), elt)
     assert np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize("group_warps", [1, 148, 400, 100000])
+def test_target_groups_do_not_change_the_result(emul, vm, group_warps):
+    """ops.hpp pick_groups: the fused inverse + forward pass-A launches are cut into 1 .. l+1 target groups depending on
+    how many independent ops are in flight (vm.cu GroupWarpsScope); rotate, multiply + relinearise and rescale must give
+    the oracle's words for every split."""
+    lib, h = emul
+    lvl = 3
+    lib.emul_set_group_warps(h, group_warps)
+    try:
+        a, b = vm.random_ct(lvl, 31), vm.random_ct(lvl, 32)
+        vm.ct_write(0, a)
+        vm.ct_write(1, b)
+        vm.exec(asm.ROTATE, 2, 0, 1)
+        elt = vm.lib.hevmx_galois_elt(vm.vm, 1)
+        got = np.zeros_like(a)
+        lib.emul_keyswitch(h, 1, _p(a), None, _p(got), lvl, _p(vm.key(3, elt)), elt)
+        assert np.array_equal(got, vm.ct_read(2))
+        vm.exec(asm.MULCC, 2, 0, 1)
+        got = np.zeros_like(a)
+        lib.emul_keyswitch(h, 2, _p(a), _p(b), _p(got), lvl, _p(vm.key(2)), 0)
+        assert np.array_equal(got, vm.ct_read(2))
+        vm.exec(asm.RESCALE, 3, 2)
+        out = np.zeros((2, lvl - 1, vm.N), dtype=np.uint64)
+        lib.emul_rescale(h, _p(got), _p(out), lvl)
+        assert np.array_equal(out, vm.ct_read(3))
+    finally:
+        lib.emul_set_group_warps(h, 1184)
 
 
 @pytest.mark.parametrize("ranks", [1, 2, 3, 5])
@@ -225,6 +255,7 @@ def test_more_than_15_digits_vs_oracle(oracle_lib):
     lib.emul_keyswitch.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p, C.c_int, u64p, C.c_uint32]
     lib.emul_keyswitch_sharded.argtypes = [C.c_void_p, C.c_int, u64p, u64p, u64p, C.c_int, u64p, C.c_uint32, C.c_int]
     lib.emul_set_fused.argtypes = [C.c_void_p, C.c_int]
+    lib.emul_set_group_warps.argtypes = [C.c_void_p, C.c_int]
     h = lib.emul_create(logn, npr, 60)
     vm = VM(oracle_lib, logn, npr, nct=4, npt=1, galois_steps=(1,))
     a, b = vm.random_ct(lvl, 91), vm.random_ct(lvl, 92)
