@@ -239,8 +239,8 @@ def resnet20_real(lib, vm, tmp, reps=3, variant="", cpu=False):
     lib.preprocess(vm)
     t_pre = time.perf_counter() - t0
     out = np.zeros(meta.get("slots", SLOTS))
-    lat, e2e, first_run = [], [], None
-    for i in range(reps + 1):
+    lat, e2e, first_run, capture_run = [], [], None, None
+    for i in range(reps + 2):
         t0 = time.perf_counter()
         lib.encrypt(vm, 0, x.ctypes.data_as(f64p), x.size)
         t1 = time.perf_counter()
@@ -248,11 +248,13 @@ def resnet20_real(lib, vm, tmp, reps=3, variant="", cpu=False):
         t2 = time.perf_counter()
         lib.decrypt_result(vm, 0, out.ctypes.data_as(f64p))
         t3 = time.perf_counter()
-        if i:
+        if i == 0:
+            first_run = t2 - t1    # the cold run() of a process: the schedule is issued on the lanes, no graph yet
+        elif i == 1:
+            capture_run = t2 - t1  # second run(): stream capture + graph instantiate + launch
+        else:
             lat.append(t2 - t1)
             e2e.append(t3 - t0)
-        else:
-            first_run = t2 - t1  # the cold run() of a process: schedule + CUDA-graph capture + instantiate + execute
     res = out[:meta["n_out"]] * meta["post_scale"]
     err = res - expected
     extra = {}
@@ -264,9 +266,11 @@ def resnet20_real(lib, vm, tmp, reps=3, variant="", cpu=False):
     return {**extra, "what": f"encrypted ResNet-20 (SiLU, nt=2^{int(np.log2(meta.get('slots', SLOTS)))} slots, N=2^{meta.get('logN', LOGN)}, 14x60-bit primes, waterline 40), "
                     "synthetic seeded input, weights examples/data/resnet20.silu.model; program compiled by dacapo_b200.compiler "
                     "(not hecate-opt), bootstrap levels from the measured cost profile",
-            "run_latency_s": float(np.median(lat)), "first_run_s": first_run,
-            "latency_note": "run_latency_s = warm run() (CUDA-graph replay); first_run_s = the first run() of the process, which is what one "
-                            "`hc-test` invocation of the reference times (examples/tests/ResNet.py:109-111: a single cold run() per process)",
+            "run_latency_s": float(np.median(lat)), "first_run_s": first_run, "graph_capture_run_s": capture_run,
+            "latency_note": "run_latency_s = warm run() (CUDA-graph replay, third run on); first_run_s = the first run() of the process "
+                            "(issued on the lanes without a graph), which is what one `hc-test` invocation of the reference times "
+                            "(examples/tests/ResNet.py:109-111: a single cold run() per process); graph_capture_run_s = the second run(), "
+                            "which captures and instantiates the graph",
             "e2e_latency_s": float(np.median(e2e)), "load_preprocess_s": t_pre,
             "rms": float(np.sqrt(np.sum(err * err) / res.shape[-1])), "argmax_ok": bool(np.argmax(res) == np.argmax(expected)),
             "lowered_ops": meta["lowered_ops"], "hevm_ops": meta["hevm_ops"],
@@ -355,7 +359,7 @@ def resnet_mix(lib, vm, tmp, cpu=True, reps=3):
         t2 = time.perf_counter()
         lib.decrypt_result(vm, 0, out.ctypes.data_as(f64p))
         t3 = time.perf_counter()
-        if i:  # first run builds the CUDA graph
+        if i:  # (run 0 is issued on the lanes, run 1 captures the CUDA graph: the median below is a replay)
             lat.append(t2 - t1)
             e2e.append(t3 - t0)
     res = {"what": "ResNet-20 op-mix replay, NOT the compiled network (hecate-opt/MLIR unavailable): op counts of "

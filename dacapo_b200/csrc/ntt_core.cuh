@@ -311,12 +311,12 @@ HD void fwdB8_stages_C(u64 (&x)[8], int lane, const Tw *tw, u64 q, u64 q2) { // 
       }
   }
 }
-// inverse: gap 2^j <-> m_loc = 128>>j groups, staged entry (m_loc - 1 + group); in/out < 2q
+// inverse: gap 2^j <-> 128>>j groups = local stage k = 7 - j, staged entry twB_pos(k, group); in/out < 2q
 HD void invB8_stages_C(u64 (&x)[8], int lane, const Tw *itw, u64 q, u64 q2, u64 dl) {
   const int base = lane * 8;
   _Pragma("unroll")
   for (int j = 0; j < 2; j++) {
-    const int half = 1 << j, ml = 128 >> j;
+    const int half = 1 << j;
     _Pragma("unroll")
     for (int e = 0; e < 8; e++)
       if (!(e & half)) {
@@ -329,7 +329,7 @@ HD void invB8_stages_M(u64 (&x)[8], int lane, const Tw *itw, u64 q, u64 q2, u64 
   const int base = idxM8(lane, 0);
   _Pragma("unroll")
   for (int j = 2; j < 5; j++) {
-    const int half = 1 << (j - 2), ml = 128 >> j;
+    const int half = 1 << (j - 2);
     _Pragma("unroll")
     for (int e = 0; e < 8; e++)
       if (!(e & half)) {

@@ -447,6 +447,7 @@ struct VM {
   }
   void resize_regs(size_t nct, size_t npt) {
     invalidate_graph();
+    eager_run_done = false;
     for (size_t r = 0; r < home.size(); r++) ct[r].d = home[r]; // so that each home buffer is freed exactly once
     home.clear();
     final_map.clear();
@@ -913,6 +914,11 @@ struct VM {
       if (o.dst < ct.size()) written[o.dst] = 1;
     }
   }
+  bool eager_run_done = false; // this program has been run once without a graph (see run_program)
+  static bool lazy_graph() {
+    static const bool on = !(std::getenv("HEVM_GRAPH_LAZY") && std::atoi(std::getenv("HEVM_GRAPH_LAZY")) == 0);
+    return on;
+  }
   void invalidate_graph() {
     if (graph_exec) CUDA_CHECK(cudaGraphExecDestroy(graph_exec));
     graph_exec = nullptr;
@@ -1250,6 +1256,13 @@ struct VM {
     } else if (!use_graph) {
       issue_scheduled();
       enc_counter += boot_index;
+    } else if (!graph_exec && !eager_run_done && lazy_graph()) {
+      // FIRST run() of a program: issue the schedule on the lanes directly.  Capturing + instantiating a graph of tens of
+      // thousands of nodes costs 2-3x the run itself, and the reference's hc-test flow is ONE cold run per process
+      // (examples/tests/ResNet.py:109-111); the graph is built by the second run() and replayed from the third on.
+      issue_scheduled();
+      enc_counter += boot_index;
+      eager_run_done = true;
     } else {
       if (graph_exec) { // the captured kernels are specialised for the entry levels of the live-in registers
         for (size_t r = 0; r < ct.size() && graph_exec; r++)

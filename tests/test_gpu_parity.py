@@ -495,8 +495,9 @@ def test_fused_mulcp_addcc_bit_exact(pair, tmp_path):
         lib.hevmx_set_enc_counter(vm.vm, 9)
         for i, dd in enumerate((xs, ys)):
             lib.encrypt(vm.vm, i, dd.ctypes.data_as(C.POINTER(C.c_double)), n)
-        lib.run(vm.vm)
-        lib.run(vm.vm)  # second run = graph replay on the GPU; inputs are untouched by the program
+        lib.run(vm.vm)  # GPU: issued on the lanes
+        lib.run(vm.vm)  # GPU: captured into a CUDA graph and launched; inputs are untouched by the program
+        lib.run(vm.vm)  # GPU: graph replay
         outs.append([(vm.ct_read(r), vm.ct_info(r)) for r in (t, d, acc, u, w, z)])
     for (a, ia), (b, ib) in zip(*outs):
         assert ia == ib
@@ -556,8 +557,8 @@ def test_accumulation_chain_bit_exact(pair, tmp_path):
         lib.preprocess(vm.vm)
         lib.hevmx_set_enc_counter(vm.vm, 11)
         lib.encrypt(vm.vm, 0, xs.ctypes.data_as(C.POINTER(C.c_double)), n)
-        lib.run(vm.vm)
-        lib.run(vm.vm)
+        for _ in range(3):  # GPU: lanes / graph capture / graph replay
+            lib.run(vm.vm)
         outs.append([(vm.ct_read(reg), vm.ct_info(reg)) for reg in (acc, acc2, z, r, cur, nxt)])
     for (a, ia), (b, ib) in zip(*outs):
         assert ia == ib
@@ -706,15 +707,17 @@ def test_scheduler_random_program_bit_exact(pair, tmp_path, seed):
             lib.encrypt(vm.vm, i, d.ctypes.data_as(C.POINTER(C.c_double)), n)
         lib.run(vm.vm)
         res[name] = [vm.ct_read(lib.getResIdx(vm.vm, i)) for i in range(len(live))]
-        if name == "g":  # second run = CUDA-graph replay from re-encrypted inputs must give the same registers
-            lib.hevmx_set_enc_counter(vm.vm, 9)
-            for i, d in enumerate(xs):
-                lib.encrypt(vm.vm, i, d.ctypes.data_as(C.POINTER(C.c_double)), n)
-            lib.run(vm.vm)
-            res["g2"] = [vm.ct_read(lib.getResIdx(vm.vm, i)) for i in range(len(live))]
-    for a, b, c in zip(res["g"], res["o"], res["g2"]):
+        if name == "g":  # second run = graph capture + launch, third = replay: from re-encrypted inputs, the same registers
+            for rep in ("g2", "g3"):
+                lib.hevmx_set_enc_counter(vm.vm, 9)
+                for i, d in enumerate(xs):
+                    lib.encrypt(vm.vm, i, d.ctypes.data_as(C.POINTER(C.c_double)), n)
+                lib.run(vm.vm)
+                res[rep] = [vm.ct_read(lib.getResIdx(vm.vm, i)) for i in range(len(live))]
+    for a, b, c, d in zip(res["g"], res["o"], res["g2"], res["g3"]):
         assert np.array_equal(a, b)
         assert np.array_equal(c, b)
+        assert np.array_equal(d, b)
     for vm in pair:
         vm.lib.hevmx_resize(vm.vm, 8, 4)
 

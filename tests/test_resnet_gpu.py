@@ -27,10 +27,14 @@ def test_encrypted_resnet20_matches_plaintext_model(b200_lib, tmp_path, waterlin
     lib.preprocess(vm)
     f64p = C.POINTER(C.c_double)
     lib.encrypt(vm, 0, x.ctypes.data_as(f64p), x.size)
-    lib.run(vm)                       # first run builds the schedule / CUDA graph
+    t = time.perf_counter()
+    lib.run(vm)                       # first run: the schedule is issued on the lanes (what one hc-test invocation times)
+    first = time.perf_counter() - t
+    lib.encrypt(vm, 0, x.ctypes.data_as(f64p), x.size)
+    lib.run(vm)                       # second run: captured into a CUDA graph
     lib.encrypt(vm, 0, x.ctypes.data_as(f64p), x.size)
     t = time.perf_counter()
-    lib.run(vm)
+    lib.run(vm)                       # graph replay
     latency = time.perf_counter() - t
     out = np.zeros(1 << 14)
     lib.decrypt_result(vm, 0, out.ctypes.data_as(f64p))
@@ -40,7 +44,7 @@ def test_encrypted_resnet20_matches_plaintext_model(b200_lib, tmp_path, waterlin
     print(f"encrypted ResNet-20 (waterline {waterline}): run() {latency:.3f}s rms {rms:.3e} argmax {int(np.argmax(res))} vs {int(np.argmax(expected))}")
     assert np.argmax(res) == np.argmax(expected)
     assert rms < (1.5e-3 if waterline >= 35 else 5e-3), rms  # north star: ~1e-3 (README.md:187 reports 9.5e-4)
-    assert latency < 1.0, latency        # 0.12 s in round 1; a 5x regression must not pass
+    assert latency < 0.6 and first < 1.5, (latency, first)   # 0.12 s / 0.25 s measured; a 5x regression must not pass
 
 
 def test_encrypted_resnet20_at_2_16_slots(b200_lib, tmp_path):
@@ -52,11 +56,12 @@ def test_encrypted_resnet20_at_2_16_slots(b200_lib, tmp_path):
     lib.load(vm, cst.encode(), hv.encode())
     lib.preprocess(vm)
     f64p = C.POINTER(C.c_double)
-    lib.encrypt(vm, 0, x.ctypes.data_as(f64p), x.size)
-    lib.run(vm)
+    for _ in range(2):                # lanes, then graph capture
+        lib.encrypt(vm, 0, x.ctypes.data_as(f64p), x.size)
+        lib.run(vm)
     lib.encrypt(vm, 0, x.ctypes.data_as(f64p), x.size)
     t = time.perf_counter()
-    lib.run(vm)
+    lib.run(vm)                       # graph replay
     latency = time.perf_counter() - t
     out = np.zeros(meta["slots"])
     lib.decrypt_result(vm, 0, out.ctypes.data_as(f64p))
@@ -83,7 +88,7 @@ def test_resnet20_program_bit_exact_vs_oracle(b200_lib, oracle_lib, tmp_path, ca
         vm, _ = make_vm(lib, 15, 14, keydir=keydir)
         lib.load(vm, cst.encode(), hv.encode())
         lib.preprocess(vm)
-        runs = 2 if name == "gpu" else 1
+        runs = 3 if name == "gpu" else 1  # GPU: issued on the lanes / graph capture + launch / graph replay
         for rep in range(runs):
             lib.hevmx_set_enc_counter(vm, 1234)
             lib.encrypt(vm, 0, x.ctypes.data_as(f64p), x.size)
@@ -99,7 +104,7 @@ def test_resnet20_program_bit_exact_vs_oracle(b200_lib, oracle_lib, tmp_path, ca
             lib.decrypt_result(vm, 0, dec.ctypes.data_as(f64p))
             out[name, rep] = (ct, (lv.value, sc.value), dec, dt)
     ct_o, info_o, dec_o, t_oracle = out["oracle", 0]
-    for rep in range(2):
+    for rep in range(3):
         ct_g, info_g, dec_g, t_gpu = out["gpu", rep]
         assert info_g == info_o, rep
         assert np.array_equal(ct_g, ct_o), f"result ciphertext differs from the oracle (run {rep})"
@@ -108,7 +113,7 @@ def test_resnet20_program_bit_exact_vs_oracle(b200_lib, oracle_lib, tmp_path, ca
     rms = float(np.sqrt(np.sum((res - expected) ** 2) / res.shape[-1]))
     assert rms < 1.5e-3
     with capsys.disabled():
-        print(f"\nResNet-20 program: oracle (CPU port, 1 thread) run() {t_oracle:.1f} s | GPU first run {out['gpu', 0][3]:.3f} s, replay {out['gpu', 1][3]:.3f} s | bit-exact, rms {rms:.2e}")
+        print(f"\nResNet-20 program: oracle (CPU port, 1 thread) run() {t_oracle:.1f} s | GPU first run {out['gpu', 0][3]:.3f} s, capture run {out['gpu', 1][3]:.3f} s, replay {out['gpu', 2][3]:.3f} s | bit-exact, rms {rms:.2e}")
 
 
 @pytest.mark.parametrize("arm", ["dacapo", "pars"])
@@ -121,11 +126,12 @@ def test_resnet20_compiled_by_restated_reference_pipelines(b200_lib, tmp_path, a
     lib.load(vm, cst.encode(), hv.encode())
     lib.preprocess(vm)
     f64p = C.POINTER(C.c_double)
-    lib.encrypt(vm, 0, x.ctypes.data_as(f64p), x.size)
-    lib.run(vm)
+    for _ in range(2):                # lanes, then graph capture
+        lib.encrypt(vm, 0, x.ctypes.data_as(f64p), x.size)
+        lib.run(vm)
     lib.encrypt(vm, 0, x.ctypes.data_as(f64p), x.size)
     t = time.perf_counter()
-    lib.run(vm)
+    lib.run(vm)                       # graph replay
     latency = time.perf_counter() - t
     out = np.zeros(1 << 14)
     lib.decrypt_result(vm, 0, out.ctypes.data_as(f64p))
