@@ -209,7 +209,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": "ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def workload_config(batch, note=None):
@@ -733,10 +733,35 @@ def main():
             (REPO / "bench_details.json").write_text(json.dumps({**line, **details}, indent=1))
         except OSError:
             pass
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _main_with_clean_stdout():
+    """The driver reads ONE JSON line from stdout: anything a library prints there (NCCL's version banner, setDebug traces)
+    goes to stderr instead; the real stdout is restored only around the final print (json lines go through _emit)."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        main()
+    finally:
+        sys.stdout.flush()
+        os.dup2(_REAL_STDOUT, 1)
+
+
+_REAL_STDOUT = None
+
+
+def _emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+    else:
+        print(json.dumps(line), flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    _main_with_clean_stdout()

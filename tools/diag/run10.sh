@@ -1,0 +1,6 @@
+set -x
+nvidia-smi -L
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/r02_bench_2gpu.json 2> gpurun_out/r02_bench_2gpu.err
+echo "exit $?"
+tail -20 gpurun_out/r02_bench_2gpu.err
+head -c 400 gpurun_out/r02_bench_2gpu.json
