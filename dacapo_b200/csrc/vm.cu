@@ -793,8 +793,23 @@ struct VM {
       // only when their turn comes, so the exchange overlaps the pass-A work on what has already arrived.  Measured on
       // 8 B200s (N = 2^16, level 29) it LOSES: eight quarter-wave launches cost 224 us against 176 us for one launch
       // behind one wait, so the default is to wait for every peer and transform all digits in one launch.
-      static const bool overlap = std::getenv("HEVM_P2P_OVERLAP") && std::atoi(std::getenv("HEVM_P2P_OVERLAP")) != 0;
-      if (!overlap) {
+      static const int overlap_mode = std::getenv("HEVM_P2P_OVERLAP") ? std::atoi(std::getenv("HEVM_P2P_OVERLAP")) : 0;
+      const bool overlap = overlap_mode == 1;
+      if (overlap_mode == 2 && nd > 0) {
+        // HEVM_P2P_OVERLAP=2: only the OWN digits (already local) are transformed while the push is in flight, then one
+        // wait for every peer, then the digits below and above the own range
+        L0.ops->shard_j0 = tlo, L0.ops->shard_nj = nd;
+        L0.ops->ks_shard_stage(20, mode, a.d, bd, d.d, pitch, l, key, elt, tlo, thi);
+        launch_p2p_wait(L0.stream, p2p.block, p2p_flag_off(0), p2p.rank, p2p.world, -1, e);
+        if (tlo > 0) {
+          L0.ops->shard_j0 = 0, L0.ops->shard_nj = tlo;
+          L0.ops->ks_shard_stage(20, mode, a.d, bd, d.d, pitch, l, key, elt, tlo, thi);
+        }
+        if (dhi < l) {
+          L0.ops->shard_j0 = dhi, L0.ops->shard_nj = l - dhi;
+          L0.ops->ks_shard_stage(20, mode, a.d, bd, d.d, pitch, l, key, elt, tlo, thi);
+        }
+      } else if (!overlap) {
         launch_p2p_wait(L0.stream, p2p.block, p2p_flag_off(0), p2p.rank, p2p.world, -1, e);
         L0.ops->shard_j0 = 0, L0.ops->shard_nj = l;
         L0.ops->ks_shard_stage(20, mode, a.d, bd, d.d, pitch, l, key, elt, tlo, thi);
