@@ -654,6 +654,9 @@ def main():
         table, prof = profile.emit_profile(str(REPO / "profiled_B200_GPU.json"), lib, vm)
         kl13 = table.pop("_kernels_rotate_l13", None)
         details["op_table_us"] = {op: {str(l): round(v, 2) for l, v in lv.items()} for op, lv in table.items()}
+        # the same ops with 32 independent instances in flight through run() (profile.measure_throughput_table): the
+        # table the bootstrap planner of dacapo_b200.compiler minimises
+        details["op_table_throughput_us"] = prof.get("latencyTableThroughput")
         if kl13 and "fwd_B_mac" in kl13:
             # roofline of the dominant kernel on ONE well-defined launch shape: the key-switch MAC kernel at level 13.
             # Algorithmic (compulsory) bytes of that launch, SURVEY 8(d) style: the key 2l(l+1)B, the NTT-form target it

@@ -92,7 +92,10 @@ def make(nt_bits, logN, out, cost, do_sweep):
 
 
 def main():
-    cost15 = json.loads((REPO / "profiled_B200_GPU.json").read_text())["latencyTableExact"]
+    # planner cost = per-op time with many independent ops in flight (profile.measure_throughput_table): the backend overlaps
+    # independent ops on 16 lanes, so the sum a planner minimises must be built from those, not from lone-op latencies
+    prof15 = json.loads((REPO / "profiled_B200_GPU.json").read_text())
+    cost15 = prof15.get("latencyTableThroughput") or prof15["latencyTableExact"]
     make(14, 15, HERE / "resnet20", cost15, True)
     # BASELINE.json configs[2]: nt = 2^16 slots (the benchmark's own default) => N = 2^17; same 14 x 60-bit chain
     cost17 = json.loads((REPO / "profiles" / "profiled_B200_GPU_N17_L30.json").read_text())["latencyTableExact"]

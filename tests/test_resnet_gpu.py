@@ -74,7 +74,7 @@ def test_encrypted_resnet20_at_2_16_slots(b200_lib, tmp_path):
 
 
 def test_resnet20_program_bit_exact_vs_oracle(b200_lib, oracle_lib, tmp_path, capsys):
-    """The whole compiled ResNet-20 program (20 202 ops: register renaming, deferred multi-term chains, ~300 in-graph
+    """The whole compiled ResNet-20 program (21 703 ops: register renaming, deferred multi-term chains, 674 in-graph
     bootstraps, CUDA-graph replay) on the GPU and on the CPU oracle from the same key / parameter file and the same
     encryption counter: the result CIPHERTEXT must be the same words, after the first run() and after a replay.  Also
     reports the MEASURED time of the oracle's run() (the CPU port of this very program; reference flow:
