@@ -145,3 +145,31 @@ def test_composite_rotation_is_split_into_naf_steps():
     assert sorted(steps) == sorted([-1, 8, 1, -4])  # 7 = -1 + 8, -3 = +1 - 4
     cmp_ = compiler.Compiler(g, compiler.Options(logN=LOGN, num_primes=NPR))
     assert cmp_.naf_terms(7) == [-1, 8] and cmp_.naf_terms(-3) == [1, -4] and cmp_.naf_terms(64) == [64]
+
+
+def test_profile_json_schema_with_throughput_table():
+    """dacapo_b200/profile.py: the emitted cost profile keeps the reference loader's schema (EarthDialect.cpp:130-180: integer
+    microseconds >= 1, entry k <=> level k + 1, rescale / modswitch rows padded at level 1) and carries the under-load table
+    (`latencyTableThroughput`) with the same keys and indexing; the committed profiled_B200_GPU.json has both, and the
+    throughput row of a key switch is below its lone-op latency at every level."""
+    import json
+    from dacapo_b200 import profile
+    top = 13
+    ops = ("rotate", "mulcc", "rescale", "modswitch", "addcc", "addcp", "mulcp", "negate", "bootstrap")
+    lone = {op: {l: 10.0 * l + 0.4 for l in range(1 if op not in ("rescale", "modswitch") else 2, top + 1)} for op in ops}
+    tp = {op: {l: v / 4 for l, v in lv.items()} for op, lv in lone.items()}
+    prof = profile.profile_json(lone, 15, 14, tp)
+    keys = {"earth.rotate_single", "earth.rescale_single", "earth.modswitch_single", "earth.add_single", "earth.add_double",
+            "earth.mul_single", "earth.mul_double", "earth.negate_single", "earth.bootstrap_single"}
+    for tab in ("latencyTable", "latencyTableExact", "latencyTableThroughput"):
+        assert set(prof[tab]) == keys and all(len(v) == top for v in prof[tab].values()), tab
+    assert all(isinstance(x, int) and x >= 1 for v in prof["latencyTable"].values() for x in v)
+    assert prof["latencyTable"]["earth.rotate_single"][3] == 41 and prof["latencyTableThroughput"]["earth.rotate_single"][3] == 10.1
+    assert prof["latencyTableThroughput"]["earth.rescale_single"][0] == prof["latencyTableThroughput"]["earth.rescale_single"][1]
+    assert prof["polynomialDegree"] == 1 << 15 and prof["levelUpperBound"] == top and "noiseTable" in prof
+    assert "latencyTableThroughput" not in profile.profile_json(lone, 15, 14)
+    from pathlib import Path
+    committed = json.loads((Path(__file__).resolve().parent.parent / "profiled_B200_GPU.json").read_text())
+    for k in ("earth.rotate_single", "earth.mul_double", "earth.bootstrap_single"):
+        assert len(committed["latencyTableThroughput"][k]) == top
+        assert all(t < e for t, e in zip(committed["latencyTableThroughput"][k], committed["latencyTableExact"][k])), k

@@ -116,7 +116,7 @@ def test_resnet20_program_bit_exact_vs_oracle(b200_lib, oracle_lib, tmp_path, ca
         print(f"\nResNet-20 program: oracle (CPU port, 1 thread) run() {t_oracle:.1f} s | GPU first run {out['gpu', 0][3]:.3f} s, capture run {out['gpu', 1][3]:.3f} s, replay {out['gpu', 2][3]:.3f} s | bit-exact, rms {rms:.2e}")
 
 
-@pytest.mark.parametrize("arm", ["dacapo", "pars"])
+@pytest.mark.parametrize("arm", ["dacapo", "pars", "dacapotp"])  # dacapotp: the DaCapo planner against latencyTableThroughput
 def test_resnet20_compiled_by_restated_reference_pipelines(b200_lib, tmp_path, arm):
     """BASELINE.json configs[3]: the same benchmark compiled by the restated `dacapo` planner (automatic bootstrap
     placement against profiled_B200_GPU.json) and by `pars` (the benchmark's hand placement), waterline 40."""
