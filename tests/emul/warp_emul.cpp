@@ -203,6 +203,10 @@ void emul_keyswitch_sharded_split(void *h, int mode, const u64 *a, const u64 *b,
     }
 }
 void emul_set_fused(void *h, int on) { ((Emu *)h)->la.use_fused = on != 0; }
+// shared-memory layout functions of the kernels (bank-conflict checks of tests/test_kernel_emul.py)
+int emul_xpad(int i) { return xpad(i); }
+int emul_twB_pos(int k, int g) { return twB_pos(k, g); }
+int emul_layout_const(int which) { return which == 0 ? TWB_ROW : which == 1 ? MAC_XROW : which == 2 ? MAC_TW_WORDS : TILE_B_WORDS; }
 // warp-job target of the fused pass-A launches (OpsIface::group_warps): 1 184 = lone op, 148 = scheduled program
 void emul_set_group_warps(void *h, int w) { ((Emu *)h)->ops->group_warps = w; }
 long emul_waits_checked(void *h) { return ((Emu *)h)->la.waits_checked; }

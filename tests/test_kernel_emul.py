@@ -277,3 +277,42 @@ def test_more_than_15_digits_vs_oracle(oracle_lib):
     got = np.zeros_like(a)
     lib.emul_keyswitch_sharded(h, 1, _p(a), None, _p(got), lvl, _p(gk), elt, 4)
     assert np.array_equal(got, vm.ct_read(2)), "sharded rotate"
+
+
+def test_shared_memory_layouts_are_bank_conflict_free(emul):
+    """The padded layouts of ntt_core.cuh / ntt_bodies.cuh (TWB_ROW / twB_pos, MAC_XROW / xpad), checked with the hardware's
+    rule for 16-byte shared-memory accesses: a quarter-warp (8 lanes) is served in one wavefront iff its 8 x 16 bytes
+    fall into 32 distinct 4-byte banks.  Covers the accesses ncu attributed the round-1 conflicts to: the twiddle reads of
+    the last two pass-B stages (layout C: lane holds indices 8 lane .. 8 lane + 7) and the stores / loads of the
+    transformed digit rows in the key inner product."""
+    lib, _ = emul
+    lib.emul_xpad.argtypes = [C.c_int]
+    lib.emul_twB_pos.argtypes = [C.c_int, C.c_int]
+    lib.emul_layout_const.argtypes = [C.c_int]
+    twb_row, xrow = lib.emul_layout_const(0), lib.emul_layout_const(1)
+
+    def conflict_free(byte_addrs):  # 8 lanes x 16 bytes
+        banks = [((a // 4) + j) % 32 for a in byte_addrs for j in range(4)]
+        return len(set(banks)) == 32 and all(a % 16 == 0 for a in byte_addrs)
+
+    # twiddle entries are 16 bytes; stage k = 6: lane reads g = 2 lane + j, stage 7: g = 4 lane + j
+    for k, per_lane in ((6, 2), (7, 4)):
+        used = set()
+        for j in range(per_lane):
+            for q in range(4):
+                lanes = range(8 * q, 8 * q + 8)
+                assert conflict_free([16 * lib.emul_twB_pos(k, per_lane * l + j) for l in lanes]), (k, j, q)
+        for g in range(1 << k):
+            used.add(lib.emul_twB_pos(k, g))
+        assert len(used) == 1 << k and max(used) < twb_row
+    # every (stage, group) has an entry of its own inside the row
+    allpos = [lib.emul_twB_pos(k, g) for k in range(8) for g in range(1 << k)]
+    assert len(set(allpos)) == 255 and max(allpos) < twb_row and min(allpos) == 0
+    # digit rows: phase 1 stores words 8 lane + e (four 16-byte stores per lane), phase 2 loads words 2 tid, 2 tid + 1
+    for e in (0, 2, 4, 6):
+        for q in range(4):
+            assert conflict_free([8 * (lib.emul_xpad(8 * l) + e) for l in range(8 * q, 8 * q + 8)]), ("store", e, q)
+    for q in range(16):
+        assert conflict_free([8 * lib.emul_xpad(2 * t) for t in range(8 * q, 8 * q + 8)]), ("load", q)
+    assert all(lib.emul_xpad(i + 1) == lib.emul_xpad(i) + 1 for i in range(0, 256, 2))  # pairs stay adjacent (16-byte accesses)
+    assert lib.emul_xpad(255) < xrow
